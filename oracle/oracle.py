@@ -1,0 +1,144 @@
+"""ctypes front-end of the C oracle (oracle/snp_oracle.c).  Test infrastructure, not product code.
+
+Array conventions are the reference's own (AoS float64): state rows of 13
+(src/agent.py:256), params rows of 20 (src/agent.py:269), goals [N,G,2] and walls [W,S,2,2] NaN padded
+(src/motion_model_manager.py:262-276), all with a leading env axis E.
+"""
+import ctypes
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import build as _build
+
+N_STATE = 13
+N_PARAMS = 20
+# src/motion_model_manager.py:15-17
+SFMS = ["sfm_helbing", "sfm_guo", "sfm_moussaid", "hsfm_farina", "hsfm_guo", "hsfm_moussaid",
+        "hsfm_new", "hsfm_new_guo", "hsfm_new_moussaid"]
+
+
+def type_code(title: str) -> int:
+    return SFMS.index(title)
+
+
+def default_params(title: str) -> np.ndarray:
+    """The 20-vector Agent.get_parameters builds for a model title (src/agent.py:94-243,268-388)."""
+    t = type_code(title)
+    p = np.zeros(N_PARAMS)
+    p[0] = 0.5
+    p[2], p[4] = 2000.0, 0.08
+    p[10], p[11] = 120000.0, 240000.0
+    soc = t % 3
+    if soc in (0, 1):
+        p[1], p[3] = 2000.0, 0.08
+    if soc == 1:
+        p[5], p[6], p[7], p[8] = 120.0, 120.0, 0.6, 0.6
+    if soc == 2:
+        p[9], p[12], p[13], p[14], p[15] = 360.0, 2.0, 0.35, 2.0, 3.0
+    if t >= 3:
+        p[16], p[17], p[18], p[19] = 1.0, 500.0, 3.0, 0.1
+    return p
+
+
+class _Cfg(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int) for k in ("type", "n", "g", "n_walls", "n_segs", "consider_robot", "symmetric",
+                                             "numba_compat", "walls_per_env")]
+
+
+@dataclass
+class OracleConfig:
+    type: int
+    consider_robot: bool = False
+    symmetric: bool = True
+    numba_compat: bool = False
+
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(_build.build())
+        dp = ctypes.POINTER(ctypes.c_double)
+        _lib.orc_update_humans.argtypes = [ctypes.POINTER(_Cfg), ctypes.c_int, dp, dp, dp, dp, dp, dp, ctypes.c_double,
+                                           ctypes.c_int, dp, dp, ctypes.c_int]
+        _lib.orc_update_humans.restype = None
+        _lib.orc_checks.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, dp, dp]
+        _lib.orc_checks.restype = None
+        _lib.orc_laser.argtypes = [ctypes.c_int] * 5 + [dp, dp, dp, ctypes.c_double, ctypes.c_int, ctypes.c_double, dp,
+                                                        ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
+        _lib.orc_laser.restype = None
+    return _lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def update_humans(cfg: OracleConfig, states, goals, walls, params, safety, desired, dt, n_steps=1, robot_vel=None,
+                  want_forces=False, n_threads=1):
+    """Batched MotionModelManager.update_humans (serial Euler path).  All arrays carry a leading env axis:
+    states [E,N(+1),13], goals [E,N,G,2], walls [W,S,2,2] or [E,W,S,2,2] or None, params [E,N,20],
+    safety [E,N(+1)], desired [E,N,2].  Returns (states, goals, desired[, forces]) as NEW arrays."""
+    lib = _load()
+    states = _c(states).copy()
+    goals = _c(goals).copy()
+    desired = _c(desired).copy()
+    params = _c(params)
+    safety = _c(safety)
+    E, rows, _ = states.shape
+    n = goals.shape[1]
+    assert rows == n + int(cfg.consider_robot), (rows, n, cfg.consider_robot)
+    if walls is None or np.size(walls) == 0 or walls.shape[-4] == 0:
+        W, S, per_env, walls_c = 0, 1, 0, np.zeros(4)
+    else:
+        walls_c = _c(walls)
+        per_env = int(walls_c.ndim == 5)
+        W, S = walls_c.shape[-4], walls_c.shape[-3]
+    c = _Cfg(cfg.type, n, goals.shape[2], W, S, int(cfg.consider_robot), int(cfg.symmetric), int(cfg.numba_compat), per_env)
+    forces = np.zeros((E, n, 9)) if want_forces else None
+    rv = None if robot_vel is None else _c(robot_vel)
+    lib.orc_update_humans(ctypes.byref(c), E, _dp(states), _dp(goals), _dp(walls_c), _dp(params), _dp(safety), _dp(desired),
+                          float(dt), int(n_steps), _dp(rv), _dp(forces), int(n_threads))
+    if want_forces:
+        return states, goals, desired, forces
+    return states, goals, desired
+
+
+def checks(states, n_humans, robot, action, time_now, consts):
+    """states [E,rows,13] (first n_humans rows are humans), robot [E,13], action [E,2], time_now [E],
+    consts = (time_limit, collision_penalty, success_reward, discomfort_dist, discomfort_penalty_factor, robot_time_step).
+    Returns [E,12], see orc_checks."""
+    lib = _load()
+    states = _c(states)
+    E, rows, _ = states.shape
+    out = np.zeros((E, 12))
+    lib.orc_checks(E, int(n_humans), rows, _dp(states), _dp(_c(robot)), _dp(_c(action)), _dp(_c(time_now)), _dp(_c(consts)), _dp(out))
+    return out
+
+
+def laser(humans, walls, pose, range_, samples, max_distance, n_threads=1):
+    """humans [E,N,3] (x,y,r), walls [W,S,2,2] / [E,W,S,2,2] / None, pose [E,3] (x,y,yaw).
+    Returns (ranges [E,samples] float64, hits [E,samples] int64)."""
+    lib = _load()
+    humans = _c(humans)
+    pose = _c(pose)
+    E, n, _ = humans.shape
+    if walls is None or np.size(walls) == 0 or walls.shape[-4] == 0:
+        W, S, per_env, walls_c = 0, 1, 0, np.zeros(4)
+    else:
+        walls_c = _c(walls)
+        per_env = int(walls_c.ndim == 5)
+        W, S = walls_c.shape[-4], walls_c.shape[-3]
+    ranges = np.zeros((E, samples))
+    hits = np.zeros((E, samples), np.int64)
+    lib.orc_laser(E, n, W, S, per_env, _dp(humans), _dp(walls_c), _dp(pose), float(range_), int(samples), float(max_distance),
+                  _dp(ranges), hits.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), int(n_threads))
+    return ranges, hits

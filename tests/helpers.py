@@ -1,0 +1,65 @@
+"""Shared helpers for the parity tests: load golden fixtures recorded from the live reference
+(tests/golden/make_golden.py) and rebuild the inputs of a single update from a recorded row."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def traj_names():
+    return sorted(os.path.basename(f)[5:-4] for f in glob.glob(os.path.join(GOLDEN, "traj_*.npz")))
+
+
+def load_traj(name):
+    d = dict(np.load(os.path.join(GOLDEN, f"traj_{name}.npz")))
+    d["name"] = name
+    d["consider_robot"], d["all_equal"] = bool(d["flags"][0]), bool(d["flags"][1])
+    d["n"] = d["states0"].shape[0]
+    return d
+
+
+def rel_err(got, ref, scale=1.0):
+    """|got-ref| / max(|ref|, scale): the parity metric of SURVEY.md section 8(d)."""
+    return np.abs(got - ref) / np.maximum(np.abs(ref), scale)
+
+
+def rotate_goals_to(goals0, current):
+    """Rotate each NaN-padded goal list left until its head equals `current` (what the reference's list
+    rotation mmm:66-70 has done by the time `current` was recorded)."""
+    G = goals0.copy()
+    for i in range(G.shape[0]):
+        cnt = int((~np.isnan(G[i, :, 0])).sum())
+        for _ in range(cnt):
+            if np.array_equal(G[i, 0], current[i]):
+                break
+            G[i, :cnt] = np.roll(G[i, :cnt], -1, axis=0)
+        assert np.array_equal(G[i, 0], current[i]), "recorded goal not in goal list"
+    return G
+
+
+def inputs_at(d, k):
+    """Inputs of the update that turns recorded row k into row k+1 (requires steps[k+1] == steps[k]+1).
+    Returns states [N(+1),13], goals [N,G,2], desired [N,2], robot_vel [2]."""
+    n = d["n"]
+    row = d["traj"][k]
+    S = d["states0"].copy()
+    S[:, :8] = row[:, :8]
+    S[:, 10:12] = row[:, 8:10]
+    G = rotate_goals_to(d["goals0"], row[:, 8:10])
+    if d["consider_robot"]:
+        rb = d["robot0"].copy()
+        rb[0:2] = d["robot_traj"][k]
+        S = np.concatenate([S, rb[None]], 0)
+    return S, G, row[:, 10:12].copy(), d["robot_vel"].copy()
+
+
+def observed(states, desired, n):
+    """Pack oracle/engine output into the fixture's 12-column row layout."""
+    return np.concatenate([states[:n, :8], states[:n, 10:12], desired[:n]], 1)
+
+
+def consecutive_pairs(d):
+    s = d["steps"]
+    return [k for k in range(len(s) - 1) if s[k + 1] == s[k] + 1]
