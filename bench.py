@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- HSFM agent-steps/s of the fused crowd step on B200, next to the reference algorithm on the host CPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--dtype f64|f32] [--workload NAME]
+
+One "step" = one SocialNavGym.step over the whole batch: swept collision / goal / reward checks, then 20 fused
+(robot.step + update_humans) sub-steps at dt = 0.0125 (social_gym/social_nav_gym.py:227-250) -- ONE kernel launch.
+agent-steps per step = envs x humans x 20.
+
+Default workload = BASELINE.json configs[2]: 4096 envs x 25 humans, HSFM (hsfm_farina), static obstacles (3 zero-speed
+humans, reference CCSO style) + the 3 wall polygons of config_example.py, robot visible, collision checks on.
+Multi-GPU (torchrun): every rank steps its own 4096 envs (no data-path collective) -> weak scaling.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT, SUBSTEPS = 0.0125, 20
+METRIC = "HSFM agent-steps/sec (envs x humans x steps)"
+WORKLOADS = {
+    # name: (model, E, N, walls, consider_robot)
+    "4096x25_hsfm_ccso_walls_robot": ("hsfm_farina", 4096, 25, True, True),
+    "4096x25_hsfm_ccso_robot": ("hsfm_farina", 4096, 25, False, True),
+    "4096x5_sfm_helbing_cc": ("sfm_helbing", 4096, 5, False, False),
+}
+
+
+def build_inputs(workload, seed0):
+    from social_navigation_pyenvs_b200 import scenarios
+    model, E, N, with_walls, robot_visible = WORKLOADS[workload]
+    cache = os.path.join(ROOT, "gpurun_out", f"scenario_{workload}_{seed0}.npz")
+    if os.path.exists(cache):
+        z = np.load(cache)
+        sc = dict(states=z["states"], goals=z["goals"], robot=z["robot"])
+    else:
+        sc = scenarios.ccso_synthetic(E, N, seed0) if "ccso" in workload else scenarios.circular_crossing(E, N, seed0)
+        try:
+            os.makedirs(os.path.dirname(cache), exist_ok=True)
+            np.savez(cache, **sc)
+        except OSError:
+            pass
+    walls = scenarios.pack_walls(scenarios.EXAMPLE_WALLS) if with_walls else None
+    states = np.concatenate([sc["states"], sc["robot"][:, None]], 1) if robot_visible else sc["states"]
+    safety = np.zeros(states.shape[:2])
+    return dict(model=model, E=E, N=N, walls=walls, robot_visible=robot_visible, states=states, goals=sc["goals"],
+                robot=sc["robot"], safety=safety)
+
+
+def algorithmic_cost(inp):
+    """Per agent-sub-step figures of SURVEY.md 8(d): bytes for ONE HBM round trip of the state a launch touches
+    (divided by the fused sub-steps outside), flops F = P*f_pair + f_self + sum_walls(20*S_w + 35), SFU ops."""
+    model, N = inp["model"], inp["N"]
+    headed = model.startswith("hsfm")
+    soc = 1 if "guo" in model else (2 if "moussaid" in model else 0)
+    f_pair = (31, 35, 110)[soc]
+    P = N - 1 + (1 if inp["robot_visible"] else 0)
+    segs = [] if inp["walls"] is None else [int((~np.isnan(w[:, 0, 0])).sum()) for w in inp["walls"]]
+    flops = P * f_pair + (150 if headed else 50) + sum(20 * s + 35 for s in segs)
+    sfu = (3, 4, 9)[soc] * P + (8 if headed else 4) + sum(s + 3 for s in segs)
+    words = 19 if headed else 13  # HSFM reads 11 + writes 8 words, SFM reads 9 + writes 4
+    return dict(flops=flops, sfu=sfu, words=words)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_rate(inp, n_envs, threads, substeps, repeats=1):
+    """The reference's algorithm on the host: C restatement (oracle/snp_oracle.c, serial semantics), OpenMP over envs."""
+    import oracle
+    from oracle import OracleConfig
+    cfg = OracleConfig(oracle.type_code(inp["model"]), inp["robot_visible"], True, False)
+    N = inp["N"]
+    S, G = inp["states"][:n_envs], inp["goals"][:n_envs]
+    params = np.tile(oracle.default_params(inp["model"]), (n_envs, N, 1))
+    D = np.zeros((n_envs, N, 2))
+    rv = np.tile([0.0, 1.0], (n_envs, 1))
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        oracle.update_humans(cfg, S, G, inp["walls"], params, inp["safety"][:n_envs], D, DT, substeps,
+                             robot_vel=rv if inp["robot_visible"] else None, n_threads=threads)
+        best = min(best, time.perf_counter() - t0)
+    return n_envs * N * substeps / best, best
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm for the same path/config on the host cores (oracle port; the Python
+    reference itself cannot travel to the GPU box).  Rank 0 only."""
+    if rank != 0:
+        return
+    inp = build_inputs(args.workload, 2000)
+    threads = os.cpu_count() or 1
+    n_envs = min(inp["E"], max(threads * 4, 128))
+    for _ in range(args.warmup):
+        oracle_rate(inp, n_envs, threads, 2)
+    times = []
+    for _ in range(args.steps):
+        _, t = oracle_rate(inp, n_envs, threads, SUBSTEPS)
+        times.append(t)
+    total = sum(times)
+    value = n_envs * inp["N"] * SUBSTEPS * args.steps / total
+    sample = f"{n_envs} of {inp['E']} envs x {SUBSTEPS} sub-steps per step, C restatement of the serial Python/NumPy path, OpenMP over envs"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": 0, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "substeps_per_step": SUBSTEPS, "dt": DT, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--workload", default="4096x25_hsfm_ccso_walls_robot", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    # host-side scenario generation forks worker processes: do it before CUDA is initialised in this process
+    inp = build_inputs(args.workload, 2000 + rank * 4096)  # every rank owns different envs
+    E, N = inp["E"], inp["N"]
+
+    import torch
+    import torch.distributed as dist
+    from social_navigation_pyenvs_b200 import CrowdEngine, _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.lib()
+    tdtype = torch.float64 if args.dtype == "f64" else torch.float32
+    def make_engine(dt_):
+        return CrowdEngine.from_reference_arrays(inp["model"], inp["states"], inp["goals"], walls=inp["walls"], safety=inp["safety"],
+                                                 consider_robot=inp["robot_visible"], all_params_equal=True, dtype=dt_,
+                                                 robot=None if inp["robot_visible"] else inp["robot"])
+
+    eng = make_engine(tdtype)
+    action_host = torch.tensor(np.tile([[0.0], [1.0]], (1, E)), dtype=tdtype).pin_memory()  # [2,E] holonomic action
+    eng.action.copy_(action_host)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def one_step():
+        eng.step(None, DT, n_substeps=SUBSTEPS, pre_checks=True, post_checks=False, track_touch=True)
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, each its own CUDA-event pair on the launching stream, L2 flushed between steps ----
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    lib.snp_launch_count(1)
+    with ClockSampler(local_rank) as clocks:
+        wall0 = time.perf_counter()
+        for s in range(args.steps):
+            flush.fill_(s & 0xFF)
+            ev[s][0].record(stream)
+            one_step()
+            ev[s][1].record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - wall0
+    launches = int(lib.snp_launch_count(0))
+    if world > 1:
+        dist.barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    agent_steps = E * N * SUBSTEPS * args.steps
+    value = world * agent_steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers: H2D action from pinned memory, launch, D2H of the
+    #      observation (px,py,vx,vy of every human), flags, reward/dmin ----
+    obs_host = torch.empty((4, E, N), dtype=tdtype).pin_memory()
+    flags_host = torch.empty((E,), dtype=torch.int32).pin_memory()
+    checks_host = torch.empty((E, 4), dtype=torch.float64).pin_memory()
+    e2e_steps = max(10, args.steps // 2)
+    for it in range(3 + e2e_steps):
+        if it == 3:
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        eng.action.copy_(action_host, non_blocking=True)
+        one_step()
+        obs_host.copy_(eng.dyn[:4], non_blocking=True)
+        flags_host.copy_(eng.flags, non_blocking=True)
+        checks_host.copy_(eng.checks, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * E * N * SUBSTEPS * e2e_steps / e2e_s
+    h2d = action_host.numel() * action_host.element_size()
+    d2h = sum(x.numel() * x.element_size() for x in (obs_host, flags_host, checks_host))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel: k_step ----
+    cost = algorithmic_cost(inp)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback"
+    if os.path.exists(peaks_path):
+        hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+    import ctypes
+    pipe = ctypes.c_double()
+    _lib.check(lib.snp_measure_pipe_peak(1 if args.dtype == "f64" else 0, ctypes.byref(pipe)))
+    mufu = ctypes.c_double()
+    _lib.check(lib.snp_measure_pipe_peak(2, ctypes.byref(mufu)))
+    per_launch_s = (total_ms / args.steps) * 1e-3
+    wbytes = 8 if args.dtype == "f64" else 4
+    launch_bytes = E * N * cost["words"] * wbytes  # one HBM round trip of the state per launch (k fused sub-steps share it)
+    launch_flops = E * N * SUBSTEPS * cost["flops"]
+    ach_tflops = launch_flops / per_launch_s / 1e12
+    ach_gbs = launch_bytes / per_launch_s / 1e9
+    ach_sfu = E * N * SUBSTEPS * cost["sfu"] / per_launch_s / 1e9
+    roofline = {"bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": ach_tflops, "peak": pipe.value, "unit": "TFLOP/s",
+                "frac": ach_tflops / pipe.value, "traffic": None,
+                "peak_source": "measured in this run: register-resident FMA loop on all SMs (snp_measure_pipe_peak)",
+                "kernel": "snp::k_step (fused 20 sub-steps)", "flops_per_agent_substep": cost["flops"],
+                "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": hbm_peak, "frac": ach_gbs / hbm_peak, "peak_source": hbm_src,
+                        "bytes_per_agent_step": cost["words"] * wbytes / SUBSTEPS},
+                "sfu": {"achieved_gops": ach_sfu, "peak_gops": mufu.value, "frac": ach_sfu / mufu.value if args.dtype == "f32" else None,
+                        "ops_per_agent_substep": cost["sfu"]}}
+
+    line = {"metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": args.workload, "envs_per_gpu": E, "humans": N, "model": inp["model"], "substeps_per_step": SUBSTEPS,
+                       "dt": DT, "walls": 0 if inp["walls"] is None else int(inp["walls"].shape[0]), "robot_visible": inp["robot_visible"],
+                       "checks": "swept collision/goal/reward + per-sub-step touch", "l2": "256 MiB flush write between timed steps",
+                       "timing": "sum of per-step CUDA-event pairs on the launch stream, max over ranks"},
+            "clocks": clocks.summary(), "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "CrowdEngine.step(action): pinned H2D action, fused launch, D2H observation + flags + reward", "steps": e2e_steps},
+            "roofline": roofline, "wall_s_timed_region": wall}
+
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        n_envs = min(E, max(threads * 4, 128))
+        oracle_rate(inp, n_envs, threads, 2)
+        reps, spent, done = 0, 0.0, 0
+        while spent < 10.0 and reps < 200:
+            _, t = oracle_rate(inp, n_envs, threads, SUBSTEPS)
+            spent += t; reps += 1; done += n_envs * N * SUBSTEPS
+        line["cpu_baseline"] = {"value": done / spent, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                                "sample": f"{reps} x ({n_envs} of {E} envs x {SUBSTEPS} sub-steps), oracle/snp_oracle.c (C restatement of the "
+                                          f"serial Python/NumPy path), OpenMP over envs; the Python reference itself measured 3.9e3 agent-steps/s "
+                                          f"per core at N=25 (BASELINE.md)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

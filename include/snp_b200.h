@@ -1,0 +1,180 @@
+/*
+ * snp_b200.h -- C ABI of libsnp_b200.so: the B200 (sm_100a) batched crowd-stepping engine that drops in for the
+ * per-step human motion update of Social-Navigation-PyEnvs.
+ *
+ * Everything here is plain C: pointers, ints, doubles.  No torch / C++ types cross this boundary.  Device-pointer
+ * entry points are stream-ordered, allocate nothing and never synchronise; host-pointer entry points (suffix _host)
+ * copy in, run the same kernels, copy out and synchronise the stream they use.
+ *
+ * Every function returns 0 on success or a negative snp_status; snp_last_error() gives the message
+ * (the Python adapter turns it into ValueError / RuntimeError, matching the reference's exceptions,
+ * social_gym/src/forces_parallel.py:211).
+ *
+ * Reference interfaces replaced (paths relative to the reference's social_gym/):
+ *   snp_step / snp_update_humans_parallel_host   <- src/forces_parallel.py:184-284 update_humans_parallel  (sole call
+ *                                                   site src/motion_model_manager.py:360), and the serial path it
+ *                                                   shadows: motion_model_manager.py:354-373,424-459 + src/forces.py
+ *   fused sub-step loop + robot motion            <- social_nav_gym.py:240-245 (20 x robot.step + update_humans),
+ *                                                   src/robot_agent.py:126-136
+ *   snp_checks (+ fused into snp_step)            <- social_nav_sim.py:949-984 collision_detection_and_reaching_goal,
+ *                                                   :986-1029 compute_reward_and_infos, :702-703;
+ *                                                   social_nav_gym.py:107-118 check_actual_collisions_and_goal
+ *   snp_laser / snp_laser_host                    <- src/sensors.py:53-69 LaserSensor.get_laser_measurements
+ *                                                   (:24-33 circle, :35-51 segment), src/robot_agent.py:77-82
+ *   snp_pack_states / snp_unpack_states           <- src/agent.py:256-266 get_safe_state / set_state row layout
+ *   snp_large_step                                <- same update for one very large crowd (tiled all-pairs)
+ */
+#ifndef SNP_B200_H
+#define SNP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNP_ABI_VERSION 1
+
+typedef enum snp_status {
+    SNP_OK = 0,
+    SNP_ERR_INVALID = -1, /* bad argument (type outside 0..8, sizes, null pointers) -> ValueError */
+    SNP_ERR_CUDA = -2,    /* CUDA runtime error */
+    SNP_ERR_UNSUPPORTED = -3
+} snp_status;
+
+enum { SNP_F32 = 0, SNP_F64 = 1 };
+
+/* Field order of the structure-of-arrays buffers (each field is a contiguous run of E*N elements). */
+enum { SNP_DYN_PX = 0, SNP_DYN_PY, SNP_DYN_VX, SNP_DYN_VY, SNP_DYN_TH, SNP_DYN_BVX, SNP_DYN_BVY, SNP_DYN_OM,
+       SNP_DYN_DFX, SNP_DYN_DFY, SNP_DYN_FIELDS };                        /* dfx,dfy: carried desired force (forces.py:12-15) */
+enum { SNP_STAT_R = 0, SNP_STAT_M, SNP_STAT_VD, SNP_STAT_SAFETY, SNP_STAT_FIELDS };
+enum { SNP_ROBOT_PX = 0, SNP_ROBOT_PY, SNP_ROBOT_VX, SNP_ROBOT_VY, SNP_ROBOT_R, SNP_ROBOT_SAFETY, SNP_ROBOT_GX,
+       SNP_ROBOT_GY, SNP_ROBOT_TH, SNP_ROBOT_FIELDS };
+
+/* Bits of the per-env flags word written by snp_step / snp_checks. */
+enum {
+    SNP_FLAG_COLLISION = 1 << 0,        /* swept test over one robot step (social_nav_sim.py:949-979) */
+    SNP_FLAG_REACHING_GOAL = 1 << 1,    /* social_nav_sim.py:980-983 */
+    SNP_FLAG_TERMINATED = 1 << 2,       /* social_nav_sim.py:986-1029 */
+    SNP_FLAG_TRUNCATED = 1 << 3,
+    SNP_FLAG_INFO_SHIFT = 4,            /* 3 bits: 0 Nothing 1 Timeout 2 Collision 3 ReachGoal 4 Danger */
+    SNP_FLAG_ACTUAL_COLLISION = 1 << 7, /* social_nav_gym.py:107-118 on the post-step state */
+    SNP_FLAG_ACTUAL_GOAL = 1 << 8,
+    SNP_FLAG_TOUCHED = 1 << 9           /* |p_h - p_r| < r_h + r_r after any sub-step (social_nav_sim.py:702-703) */
+};
+
+/* A batch of E independent environments with N humans each, resident in device memory.
+ * `dtype` selects float or double for every `void*` array below. */
+typedef struct snp_crowd {
+    int32_t E, N, G;          /* envs, humans per env, goal slots per human */
+    int32_t dtype;            /* SNP_F32 / SNP_F64 */
+    void *dyn;                /* [SNP_DYN_FIELDS][E*N]   updated in place */
+    const void *stat;         /* [SNP_STAT_FIELDS][E*N] */
+    const void *goals;        /* [G][2][E*N]  goal lists; slots >= goal_cnt are ignored */
+    int32_t *goal_idx;        /* [E*N] index of the current goal (the reference rotates the list instead,
+                                 motion_model_manager.py:66-70); updated in place */
+    const int32_t *goal_cnt;  /* [E*N] number of valid goals (>= 1) */
+    const void *agent_params; /* optional [20][E*N] per-agent parameter rows (agent.py:269); NULL -> `params` for all */
+    double params[20];        /* uniform parameter row used when agent_params == NULL */
+    void *robot;              /* optional [SNP_ROBOT_FIELDS][E]; required when consider_robot or checks are on */
+    const void *walls;        /* optional [walls_per_env ? E : 1][W*S][4] = ax,ay,bx,by per segment slot, NaN-padded
+                                 (motion_model_manager.py:268-276), endpoints ordered as obstacle.py:31-32 */
+    int32_t W, S;             /* wall polygons, segment slots per polygon */
+    int32_t walls_per_env;
+} snp_crowd;
+
+typedef struct snp_step_opts {
+    int32_t type;             /* 0..8 index into SFMS (motion_model_manager.py:15-17) */
+    int32_t consider_robot;   /* robot exerts force on humans (motion_model_manager.py:35) */
+    int32_t symmetric;        /* all_equal_humans: pair (i,j), i<j evaluated with i as agent1 and applied +/- (forces.py:130-151);
+                                 0 -> per-agent path (forces.py:153-218) */
+    int32_t numba_compat;     /* 0: serial Python/NumPy semantics (oracle of record); 1: forces_parallel.py semantics
+                                 ('<=' goal test, zeroed desired force, Guo wall force / W, first-wins closest segment) */
+    int32_t n_substeps;       /* fused update_humans calls per launch (20 in SocialNavGym.step) */
+    int32_t robot_mode;       /* 0: robot row fixed during the launch; 1: holonomic action: before every sub-step
+                                 p += a*dt, v = a (robot_agent.py:126-131) */
+    double dt;
+    const void *action;       /* [2][E] (dtype of the crowd) when robot_mode == 1 or pre_checks */
+    int32_t pre_checks;       /* swept collision / goal / reward on the PRE-step state (social_nav_gym.py:232-234) */
+    int32_t post_checks;      /* actual collision / goal on the POST-step state (social_nav_gym.py:269) */
+    int32_t track_touch;      /* OR of the run_k_steps collision test after every sub-step */
+    int32_t reserved;
+    double consts[6];         /* time_limit, collision_penalty, success_reward, discomfort_dist,
+                                 discomfort_penalty_factor, robot_time_step */
+    double *time_now;         /* optional [E] global_time; read by the reward, advanced by dt per sub-step */
+    int32_t *flags;           /* [E] out, required when any check is on */
+    double *checks;           /* [E][4] out: dmin (swept), reward, dmin (actual), unused */
+} snp_step_opts;
+
+typedef struct snp_laser_args {
+    int32_t E, N;             /* envs, circles (humans) per env */
+    int32_t dtype;
+    int32_t samples;
+    const void *px, *py, *radius; /* [E*N] each (SoA fields of a crowd work as is) */
+    const void *walls;        /* as snp_crowd.walls */
+    int32_t W, S, walls_per_env;
+    int32_t reserved;
+    const void *pose;         /* [3][E] x, y, yaw of the sensor */
+    double range, max_distance, robot_radius; /* robot_radius is subtracted from the ranges (robot_agent.py:81); 0 for raw */
+    void *ranges;             /* [E][samples] out */
+    int32_t *hits;            /* [E][samples] out (optional): human index, N + segment ordinal, or -1 */
+} snp_laser_args;
+
+int snp_abi_version(void);
+const char *snp_last_error(void);
+/* Device properties the host side sizes grids with: sm_count, cc_major, cc_minor, l2_bytes. */
+int snp_device_info(int32_t *out4);
+
+/* ---- device-pointer API ---- */
+int snp_step(const snp_crowd *crowd, const snp_step_opts *opts, void *cuda_stream);
+int snp_checks(const snp_crowd *crowd, const snp_step_opts *opts, void *cuda_stream);
+int snp_laser(const snp_laser_args *args, void *cuda_stream);
+/* AoS <-> SoA: rows are the reference's 13-wide float64 state rows [E][rows][13] with the robot (if any) as row N. */
+int snp_unpack_states(const snp_crowd *crowd, const double *rows_dev, int32_t rows_per_env, const double *safety_dev,
+                      void *cuda_stream);
+int snp_pack_states(const snp_crowd *crowd, double *rows_dev, int32_t rows_per_env, void *cuda_stream);
+/* Goal lists: reference rows [E][N][G][2] NaN padded (motion_model_manager.py:262-267) -> crowd->goals / goal_idx (= 0) and
+ * goal_cnt_dev (writable alias of crowd->goal_cnt).  snp_rotate_goal_rows applies the rotation the reference would have
+ * performed in place (forces_parallel.py:229-232) to the caller's float64 rows, given the crowd's goal_idx. */
+int snp_unpack_goals(const snp_crowd *crowd, const double *goal_rows_dev, int32_t *goal_cnt_dev, void *cuda_stream);
+int snp_rotate_goal_rows(const snp_crowd *crowd, double *goal_rows_dev, void *cuda_stream);
+/* One very large crowd (the crowd's E*N agents form ONE environment): one sub-step, shared-memory tiled all-pairs.
+ * `others` = [5][M] x,y,vx,vy,r+safety (SoA) of ALL M entities exerting force -- the crowd itself (gathered over ranks
+ * when it is sharded by agent) plus, optionally, the robot as last entry; `self_offset` = index of this crowd's agent 0
+ * in that view.  Own state is updated in place; when `next_view` is non-NULL the updated x,y,vx,vy,r+safety of the own
+ * agents are also written into it (same [5][M] layout, same offset), ready to be all-gathered for the next sub-step. */
+int snp_large_step(const snp_crowd *crowd, const snp_step_opts *opts, const void *others, int64_t M, int64_t self_offset,
+                   void *next_view, void *cuda_stream);
+/* Writes this crowd's [5][.] entity view (x,y,vx,vy,r+safety; v = R(yaw) bv for headed models) into `view` (field stride
+ * `stride` elements, starting at element `offset`). */
+int snp_large_publish(const snp_crowd *crowd, int32_t type, void *view, int64_t stride, int64_t offset, void *cuda_stream);
+
+/* ---- host-pointer API (the reference operator, batched over a leading env axis) ----
+ * update_humans_parallel(type, agents_state, goals, obstacles, agents_params, dt, safety_space,
+ *                        all_params_equal, last_is_robot) -> updated_state        forces_parallel.py:184
+ * agents_state [E][rows][13] (rows = N + last_is_robot), goals [E][N][G][2] NaN-padded and ROTATED IN PLACE on goal
+ * reach, agents_state[:,:,10:12] refreshed and (headed models) [:,:,3:5] overwritten as the reference does
+ * (fp:229-234,256); obstacles [W][S][2][2] NaN-padded or NULL; agents_params [E][N][20]; safety_space [E][rows];
+ * desired_force [E][N][2] in/out or NULL (zeros; only the serial semantics carry it); out_state [E][rows][13]. */
+int snp_update_humans_parallel_host(int32_t type, int32_t E, int32_t N, int32_t G, double *agents_state, double *goals,
+                                    const double *obstacles, int32_t W, int32_t S, const double *agents_params, double dt,
+                                    const double *safety_space, int32_t all_params_equal, int32_t last_is_robot,
+                                    int32_t numba_compat, int32_t dtype, int32_t n_substeps, double *desired_force,
+                                    double *out_state);
+/* LaserSensor.get_laser_measurements over E sensors: humans [E][N][3] = x,y,r; walls [W][S][2][2]; pose [E][3];
+ * ranges [E][samples]; hits [E][samples] or NULL. */
+int snp_laser_host(int32_t E, int32_t N, const double *humans, const double *walls, int32_t W, int32_t S, const double *pose,
+                   double range, int32_t samples, double max_distance, double robot_radius, int32_t dtype, double *ranges,
+                   int32_t *hits);
+
+/* ---- measurement helpers (bench.py) ---- */
+/* Runs a register-resident FMA / MUFU loop on every SM and returns achieved TFLOP/s (kind 0 fp32 FMA, 1 fp64 FMA)
+ * or Gop/s (kind 2 MUFU.EX2).  Used as the measured denominator of the compute roofline. */
+int snp_measure_pipe_peak(int32_t kind, double *out);
+/* Launch statistics since the last reset: number of kernels this library launched. */
+int64_t snp_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNP_B200_H */

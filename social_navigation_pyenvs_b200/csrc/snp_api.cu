@@ -1,0 +1,120 @@
+// snp_api.cu -- extern "C" entry points of libsnp_b200.so (include/snp_b200.h): argument validation, translation of the
+// plain-C descriptors into kernel argument blocks, error reporting and the launch counter.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+#include "snp_kernels.cuh"
+
+namespace snp {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int device_sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+template <typename T> static int build_args(const snp_crowd *c, const snp_step_opts *o, KArgs<T> &a) {
+    if (!c || !o) { set_error("null descriptor"); return SNP_ERR_INVALID; }
+    if (c->E <= 0 || c->N <= 0 || c->G <= 0) { set_error("E, N and G must be positive (E=%d N=%d G=%d)", c->E, c->N, c->G); return SNP_ERR_INVALID; }
+    if (o->type < 0 || o->type > 8) { set_error("Type %d does not exist for this implementation", o->type); return SNP_ERR_INVALID; }
+    if (!c->dyn || !c->stat || !c->goals || !c->goal_idx || !c->goal_cnt) { set_error("dyn/stat/goals/goal_idx/goal_cnt must be device pointers"); return SNP_ERR_INVALID; }
+    if (o->n_substeps < 0) { set_error("n_substeps must be >= 0"); return SNP_ERR_INVALID; }
+    const bool need_robot = o->consider_robot || o->pre_checks || o->post_checks || o->track_touch || o->robot_mode;
+    if (need_robot && !c->robot) { set_error("a robot array is required when consider_robot, robot_mode or any check is on"); return SNP_ERR_INVALID; }
+    if ((o->robot_mode == 1 || o->pre_checks) && !o->action) { set_error("an action array is required for robot_mode=1 / pre_checks"); return SNP_ERR_INVALID; }
+    if ((o->pre_checks || o->post_checks || o->track_touch) && !o->flags) { set_error("flags output required when checks are on"); return SNP_ERR_INVALID; }
+    if (c->W < 0 || c->S < 0 || (c->W > 0 && (!c->walls || c->S == 0))) { set_error("walls: W=%d S=%d but no segment array", c->W, c->S); return SNP_ERR_INVALID; }
+    if (c->agent_params && o->symmetric && !o->numba_compat) {
+        set_error("per-agent parameter rows with the symmetric (all_equal_humans) path are not supported: pass a uniform row");
+        return SNP_ERR_UNSUPPORTED;
+    }
+    a.E = c->E; a.N = c->N; a.G = c->G; a.EN = (long long)c->E * c->N;
+    a.dyn = (T *)c->dyn; a.stat = (const T *)c->stat; a.goals = (const T *)c->goals;
+    a.goal_idx = c->goal_idx; a.goal_cnt = c->goal_cnt;
+    a.agent_params = (o->symmetric && o->numba_compat) ? nullptr : (const T *)c->agent_params;
+    a.P = make_params<T>(c->params);
+    a.robot = (T *)c->robot;
+    a.walls = (const T *)c->walls; a.W = c->W; a.S = c->W > 0 ? c->S : 0; a.walls_per_env = c->walls_per_env;
+    a.consider_robot = o->consider_robot; a.symmetric = o->symmetric; a.numba = o->numba_compat;
+    a.n_substeps = o->n_substeps; a.robot_mode = o->robot_mode;
+    a.dt = (T)o->dt; a.dt_d = o->dt;
+    a.action = (const T *)o->action;
+    a.pre_checks = o->pre_checks; a.post_checks = o->post_checks; a.track_touch = o->track_touch;
+    for (int k = 0; k < 6; ++k) a.consts[k] = o->consts[k];
+    a.time_now = o->time_now; a.flags = o->flags; a.checks = o->checks;
+    a.epw = 1;
+    return SNP_OK;
+}
+
+}  // namespace snp
+
+using namespace snp;
+
+extern "C" {
+
+int snp_abi_version(void) { return SNP_ABI_VERSION; }
+const char *snp_last_error(void) { return g_err; }
+
+int snp_device_info(int32_t *out4) {
+    if (!out4) { set_error("null output"); return SNP_ERR_INVALID; }
+    int dev = 0;
+    SNP_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    SNP_CUDA_OK(cudaGetDeviceProperties(&p, dev));
+    out4[0] = p.multiProcessorCount; out4[1] = p.major; out4[2] = p.minor; out4[3] = p.l2CacheSize;
+    return SNP_OK;
+}
+
+int snp_step(const snp_crowd *crowd, const snp_step_opts *opts, void *stream) {
+    if (!crowd) { set_error("null crowd"); return SNP_ERR_INVALID; }
+    if (crowd->dtype == SNP_F64) {
+        KArgs<double> a;
+        int rc = build_args<double>(crowd, opts, a);
+        if (rc) return rc;
+        return launch_step_small<double>(a, opts->type, (cudaStream_t)stream);
+    } else if (crowd->dtype == SNP_F32) {
+        KArgs<float> a;
+        int rc = build_args<float>(crowd, opts, a);
+        if (rc) return rc;
+        return launch_step_small<float>(a, opts->type, (cudaStream_t)stream);
+    }
+    set_error("dtype %d is neither SNP_F32 nor SNP_F64", crowd->dtype);
+    return SNP_ERR_INVALID;
+}
+
+int snp_checks(const snp_crowd *crowd, const snp_step_opts *opts, void *stream) {
+    if (!opts) { set_error("null opts"); return SNP_ERR_INVALID; }
+    snp_step_opts o = *opts;
+    o.n_substeps = 0;  // the fused kernel with an empty sub-step loop is exactly the checks
+    o.robot_mode = 0;
+    o.time_now = nullptr;
+    if (opts->time_now && !opts->pre_checks) { /* nothing to read */ }
+    // the reward needs the time but must not advance it: hand the kernel a read through `consts`-free path
+    o.time_now = opts->time_now;
+    return snp_step(crowd, &o, stream);
+}
+
+int64_t snp_launch_count(int32_t reset) {
+    long long v = reset ? g_launches.exchange(0) : g_launches.load();
+    return (int64_t)v;
+}
+
+}  // extern "C"

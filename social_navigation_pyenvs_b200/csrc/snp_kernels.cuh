@@ -1,0 +1,53 @@
+// snp_kernels.cuh -- argument blocks shared by the kernels and the C-ABI glue.
+#pragma once
+#include <cstdint>
+#include "snp_physics.cuh"
+#include "../../include/snp_b200.h"
+
+namespace snp {
+
+template <typename T> struct alignas(16) Ent { T x, y, vx, vy; };  // float4 / double4-sized entity record staged in shared memory
+
+template <typename T> struct KArgs {
+    int E, N, G;
+    long long EN;
+    T *dyn;
+    const T *stat;
+    const T *goals;
+    int *goal_idx;
+    const int *goal_cnt;
+    const T *agent_params;
+    Params<T> P;
+    T *robot;
+    const T *walls;
+    int W, S, walls_per_env;
+    int consider_robot, symmetric, numba, n_substeps, robot_mode;
+    T dt;
+    double dt_d;
+    const T *action;
+    int pre_checks, post_checks, track_touch;
+    double consts[6];
+    double *time_now;
+    int *flags;
+    double *checks;
+    int epw;  // envs per warp (warp-packed kernel)
+};
+
+// Host-side launchers implemented per translation unit.
+template <typename T> int launch_step_small(const KArgs<T> &a, int type, cudaStream_t st);
+template <typename T> int launch_checks(const KArgs<T> &a, cudaStream_t st);
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+int device_sm_count();
+
+#define SNP_CUDA_OK(expr)                                                                 \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            snp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return SNP_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+}  // namespace snp

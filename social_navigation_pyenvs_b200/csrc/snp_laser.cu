@@ -1,0 +1,219 @@
+// snp_laser.cu -- the laser range finder as a ray-vs-circle / ray-vs-segment intersection kernel.
+//
+// Reference: social_gym/src/sensors.py:53-69 get_laser_measurements (angles = linspace(yaw - range/2, yaw + range/2, samples),
+// per ray the minimum over humans then over wall segments with strict '<'), :24-33 sphere_ray_intersect, :35-51
+// segment_ray_intersect (one-sided: denominator <= 0 -> miss; 0 < t < 1, u > 0), src/robot_agent.py:81 (minus robot radius).
+// The hit index is the first entity attaining the minimum in the reference's iteration order: humans 0..N-1, then the
+// non-padding segment slots in (wall, slot) order offset by N; -1 when nothing is closer than max_distance.
+//
+// Two mappings:
+//   k_laser_rays : one thread per ray, the env's circles and segments staged once in shared memory (small crowds);
+//   k_laser_warp : one warp per ray, lanes stride over the entities and a warp-shuffle (value, index) min-reduction picks
+//                  the winner, ties to the lowest index (large crowds).
+#include "snp_kernels.cuh"
+
+namespace snp {
+namespace {
+
+template <typename T> struct Circ { T sx, sy, cc; };       // s = sensor - centre, cc = s.s - r^2
+template <typename T> struct RaySeg { T x1, y1, x2, y2; };
+
+// Exact-formula arithmetic for double (matches the oracle bit for bit given the same ray direction); plain for float.
+template <typename T> struct Ops;
+template <> struct Ops<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ void sincos(double a, double *s, double *c) { ::sincos(a, s, c); }
+};
+template <> struct Ops<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float div(float a, float b) { return a / b; }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
+    static __device__ __forceinline__ void sincos(float a, float *s, float *c) { sincosf(a, s, c); }
+};
+
+template <typename T> __device__ __forceinline__ Circ<T> make_circ(T ox, T oy, T cx, T cy, T r) {
+    using O = Ops<T>;
+    Circ<T> c;
+    c.sx = O::sub(ox, cx); c.sy = O::sub(oy, cy);
+    c.cc = O::sub(O::fma(c.sy, c.sy, O::mul(c.sx, c.sx)), O::mul(r, r));  // np.dot(s,s) - r*r
+    return c;
+}
+
+template <typename T> __device__ __forceinline__ T circle_hit(const Circ<T> &c, T dx, T dy, T maxd) {  // sensors.py:24-33
+    using O = Ops<T>;
+    const T b = O::fma(c.sy, dy, O::mul(c.sx, dx));  // np.dot(s, dir)
+    T h = O::sub(O::mul(b, b), c.cc);
+    if (h < T(0)) return maxd;
+    h = Real<T>::sqrt_(h);
+    const T t = O::sub(-b, h);
+    if (t < T(0)) return maxd;
+    return t < maxd ? t : maxd;
+}
+
+template <typename T> __device__ __forceinline__ T segment_hit(const RaySeg<T> &s, T x3, T y3, T dx, T dy, T maxd) {  // sensors.py:35-51
+    using O = Ops<T>;
+    const T x4 = O::add(x3, dx), y4 = O::add(y3, dy);
+    const T a = O::sub(s.x1, s.x2), b = O::sub(s.y1, s.y2), c = O::sub(y3, y4), d = O::sub(x3, x4);
+    const T den = O::sub(O::mul(a, c), O::mul(b, d));
+    if (den <= T(0)) return maxd;
+    const T e = O::sub(s.x1, x3), f = O::sub(s.y1, y3);
+    const T t = O::div(O::sub(O::mul(e, c), O::mul(f, d)), den);
+    const T u = -O::div(O::sub(O::mul(a, f), O::mul(b, e)), den);
+    if (t > T(0) && t < T(1) && u > T(0)) {
+        const T ix = O::add(s.x1, O::mul(t, O::sub(s.x2, s.x1))), iy = O::add(s.y1, O::mul(t, O::sub(s.y2, s.y1)));
+        const T ex = O::sub(x3, ix), ey = O::sub(y3, iy);
+        const T dist = Real<T>::sqrt_(O::fma(ey, ey, O::mul(ex, ex)));  // np.linalg.norm
+        return dist < maxd ? dist : maxd;
+    }
+    return maxd;
+}
+
+template <typename T> __device__ __forceinline__ void ray_direction(T yaw, T range, int samples, int k, T &dx, T &dy) {
+    // numpy.linspace(start, stop, samples): start + k*step with step = (stop-start)/(samples-1), last element = stop exactly
+    using O = Ops<T>;
+    const T half = O::div(range, T(2));
+    const T start = O::sub(yaw, half), stop = O::add(yaw, half);
+    const int div = samples - 1;
+    T ang = start;
+    if (div > 0) {
+        const T step = O::div(O::sub(stop, start), T(div));
+        ang = (k == div) ? stop : O::add(O::mul(T(k), step), start);
+    }
+    O::sincos(ang, &dy, &dx);
+}
+
+template <typename T> struct LArgs {
+    int E, N, samples, W, S, walls_per_env;
+    const T *px, *py, *radius, *walls, *pose;
+    T range, maxd, robot_radius;
+    T *ranges;
+    int *hits;
+};
+
+template <typename T> __global__ void __launch_bounds__(128) k_laser_rays(const LArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int e = blockIdx.y;
+    const int nseg = a.W * a.S;
+    Circ<T> *circ = reinterpret_cast<Circ<T> *>(smem_raw);
+    RaySeg<T> *segs = reinterpret_cast<RaySeg<T> *>(smem_raw + ((sizeof(Circ<T>) * a.N + 15) & ~size_t(15)));
+    const T ox = a.pose[e], oy = a.pose[(size_t)a.E + e], yaw = a.pose[2 * (size_t)a.E + e];
+    for (int k = threadIdx.x; k < a.N; k += blockDim.x) {
+        const size_t idx = (size_t)e * a.N + k;
+        circ[k] = make_circ<T>(ox, oy, a.px[idx], a.py[idx], a.radius[idx]);
+    }
+    const T *w = a.walls + (a.walls_per_env ? (size_t)e * nseg * 4 : 0);
+    for (int k = threadIdx.x; k < nseg; k += blockDim.x) segs[k] = RaySeg<T>{w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]};
+    __syncthreads();
+    const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= a.samples) return;
+    T dx, dy;
+    ray_direction<T>(yaw, a.range, a.samples, ray, dx, dy);
+    T best = a.maxd;
+    int hit = -1;
+    for (int k = 0; k < a.N; ++k) {
+        const T rc = circle_hit<T>(circ[k], dx, dy, a.maxd);
+        if (rc < best) { best = rc; hit = k; }
+    }
+    int ord = a.N;
+    for (int k = 0; k < nseg; ++k) {
+        const RaySeg<T> s = segs[k];
+        if (s.x1 != s.x1) continue;  // NaN padding slot
+        const T rc = segment_hit<T>(s, ox, oy, dx, dy, a.maxd);
+        if (rc < best) { best = rc; hit = ord; }
+        ++ord;
+    }
+    a.ranges[(size_t)e * a.samples + ray] = best - a.robot_radius;
+    if (a.hits) a.hits[(size_t)e * a.samples + ray] = hit;
+}
+
+// One warp per ray.  Segment ordinals need the count of non-padding slots before each slot; padding is a suffix of each
+// wall's slots (motion_model_manager.py:270-275), so ordinal(w, s) = (valid slots of walls < w) + s, built in smem.
+template <typename T> __global__ void __launch_bounds__(256) k_laser_warp(const LArgs<T> a) {
+    extern __shared__ int wall_base[];  // [W] ordinal of each wall's first segment
+    const int e = blockIdx.y;
+    const int nseg = a.W * a.S;
+    const T *w = a.walls + (a.walls_per_env ? (size_t)e * nseg * 4 : 0);
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int k = 0; k < a.W; ++k) {
+            wall_base[k] = acc;
+            for (int s = 0; s < a.S; ++s) { const T x = w[4 * (k * a.S + s)]; acc += (x == x) ? 1 : 0; }
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int ray = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ray >= a.samples) return;
+    const T ox = a.pose[e], oy = a.pose[(size_t)a.E + e], yaw = a.pose[2 * (size_t)a.E + e];
+    T dx, dy;
+    ray_direction<T>(yaw, a.range, a.samples, ray, dx, dy);
+    T best = a.maxd;
+    int hit = 0x7fffffff;
+    for (int k = lane; k < a.N; k += 32) {
+        const size_t idx = (size_t)e * a.N + k;
+        const Circ<T> c = make_circ<T>(ox, oy, a.px[idx], a.py[idx], a.radius[idx]);
+        const T rc = circle_hit<T>(c, dx, dy, a.maxd);
+        if (rc < best) { best = rc; hit = k; }
+    }
+    for (int k = lane; k < nseg; k += 32) {
+        const RaySeg<T> s{w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]};
+        if (s.x1 != s.x1) continue;
+        const int wi = k / a.S;
+        const T rc = segment_hit<T>(s, ox, oy, dx, dy, a.maxd);
+        if (rc < best) { best = rc; hit = a.N + wall_base[wi] + (k - wi * a.S); }
+    }
+    // (value, index) min-reduction; ties -> lowest index == the reference's first strict-'<' winner
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const T ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oh = __shfl_xor_sync(0xffffffffu, hit, off);
+        if (ob < best || (ob == best && oh < hit)) { best = ob; hit = oh; }
+    }
+    if (lane == 0) {
+        a.ranges[(size_t)e * a.samples + ray] = best - a.robot_radius;
+        if (a.hits) a.hits[(size_t)e * a.samples + ray] = (hit == 0x7fffffff) ? -1 : hit;
+    }
+}
+
+template <typename T> int run_laser(const snp_laser_args *g, cudaStream_t st) {
+    LArgs<T> a;
+    a.E = g->E; a.N = g->N; a.samples = g->samples; a.W = g->W; a.S = g->W > 0 ? g->S : 0; a.walls_per_env = g->walls_per_env;
+    a.px = (const T *)g->px; a.py = (const T *)g->py; a.radius = (const T *)g->radius; a.walls = (const T *)g->walls; a.pose = (const T *)g->pose;
+    a.range = (T)g->range; a.maxd = (T)g->max_distance; a.robot_radius = (T)g->robot_radius;
+    a.ranges = (T *)g->ranges; a.hits = g->hits;
+    const int entities = a.N + a.W * a.S;
+    const size_t smem_rays = ((sizeof(Circ<T>) * a.N + 15) & ~size_t(15)) + sizeof(RaySeg<T>) * (size_t)(a.W * a.S);
+    if (entities <= 512 && smem_rays <= 48 * 1024) {
+        dim3 grid((a.samples + 127) / 128, a.E);
+        k_laser_rays<T><<<grid, 128, smem_rays, st>>>(a);
+    } else {
+        dim3 grid((a.samples + 7) / 8, a.E);
+        k_laser_warp<T><<<grid, 256, sizeof(int) * (a.W > 0 ? a.W : 1), st>>>(a);
+    }
+    count_launch();
+    SNP_CUDA_OK(cudaGetLastError());
+    return SNP_OK;
+}
+
+}  // namespace
+}  // namespace snp
+
+using namespace snp;
+
+extern "C" int snp_laser(const snp_laser_args *g, void *stream) {
+    if (!g || !g->px || !g->py || !g->radius || !g->pose || !g->ranges) { set_error("snp_laser: null array"); return SNP_ERR_INVALID; }
+    if (g->E <= 0 || g->N < 0 || g->samples <= 0) { set_error("snp_laser: E=%d N=%d samples=%d", g->E, g->N, g->samples); return SNP_ERR_INVALID; }
+    if (g->E > 65535) { set_error("snp_laser: at most 65535 envs per call (got %d)", g->E); return SNP_ERR_INVALID; }
+    if (g->max_distance > 10.0) { set_error("Maxium distance for laser is 10 meters"); return SNP_ERR_INVALID; }  // sensors.py:13
+    if (g->W > 0 && !g->walls) { set_error("snp_laser: W=%d but walls is null", g->W); return SNP_ERR_INVALID; }
+    if (g->dtype == SNP_F64) return run_laser<double>(g, (cudaStream_t)stream);
+    if (g->dtype == SNP_F32) return run_laser<float>(g, (cudaStream_t)stream);
+    set_error("snp_laser: bad dtype %d", g->dtype);
+    return SNP_ERR_INVALID;
+}

@@ -1,0 +1,385 @@
+// snp_step_small.cu -- fused small-crowd step: goal switching, wall closest points, all-pairs social force, desired
+// force, HSFM torque + body-frame projection, explicit Euler, robot motion and the collision / goal / reward
+// reductions, for `n_substeps` consecutive update_humans calls in ONE launch.  Agent state makes one HBM round trip per
+// launch: it lives in registers across sub-steps and only (x, y, vx, vy) of each entity is republished to shared memory.
+//
+// Two mappings of the same body:
+//   warp-packed (CTA = false): N <= 32 humans per env; floor(32/N) envs share a warp, one lane per human; the only
+//       synchronisation is __syncwarp; flag reductions are segmented warp shuffles.
+//   CTA-per-env (CTA = true): 32 < N <= 512; one thread per human, __syncthreads per sub-step, reductions through
+//       shared memory.
+// Reference: social_gym/src/motion_model_manager.py:354-373,424-459 (serial path), src/forces.py, src/forces_parallel.py:184-284,
+// social_gym/social_nav_gym.py:227-250 (sub-step loop), social_nav_sim.py:949-1029 and social_nav_gym.py:107-118 (checks).
+#include <cstdio>
+#include "snp_kernels.cuh"
+
+namespace snp {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kSlotsPerWarp = 64;  // >= epw * (N + 1) for every N <= 32
+
+// ---- checks (double arithmetic, formula-exact; see snp_math.cuh) ----
+
+// utils.py:22-36 point_to_segment_dist(x1, y1, x2, y2, 0, 0) with (x1,y1) = d, (x2,y2) = e.
+__device__ __forceinline__ double origin_to_segment(double x1, double y1, double x2, double y2) {
+    const double px = __dsub_rn(x2, x1), py = __dsub_rn(y2, y1);
+    if (px == 0.0 && py == 0.0) return xnorm_plain(-x1, -y1);
+    double u = __ddiv_rn(__dadd_rn(__dmul_rn(-x1, px), __dmul_rn(-y1, py)), __dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
+    if (u > 1.0) u = 1.0; else if (u < 0.0) u = 0.0;
+    const double x = __dadd_rn(x1, __dmul_rn(u, px)), y = __dadd_rn(y1, __dmul_rn(u, py));
+    return xnorm_plain(x, y);
+}
+
+// social_nav_sim.py:962-976: closest boundary distance between human and robot over one robot step of length T.
+__device__ __forceinline__ double swept_distance(double hx, double hy, double hvx, double hvy, double hr, double rx, double ry,
+                                                 double rr, double ax, double ay, double T) {
+    const double dx = __dsub_rn(hx, rx), dy = __dsub_rn(hy, ry);
+    const double vx = __dsub_rn(hvx, ax), vy = __dsub_rn(hvy, ay);
+    const double ex = __dadd_rn(dx, __dmul_rn(vx, T)), ey = __dadd_rn(dy, __dmul_rn(vy, T));
+    return __dsub_rn(__dsub_rn(origin_to_segment(dx, dy, ex, ey), hr), rr);
+}
+
+// social_nav_sim.py:986-1029.  Returns info code, writes reward / terminated / truncated.
+__device__ __forceinline__ int reward_and_info(bool collision, double dmin, bool goal, double t, const double *c, double &reward,
+                                               bool &terminated, bool &truncated) {
+    if (t >= __dsub_rn(c[0], 1.0)) { reward = 0.0; truncated = true; terminated = false; return 1; }
+    if (collision) { reward = c[1]; truncated = false; terminated = true; return 2; }
+    if (goal) { reward = c[2]; truncated = false; terminated = true; return 3; }
+    if (dmin < c[3]) { reward = __dmul_rn(__dmul_rn(__dsub_rn(dmin, c[3]), c[4]), c[5]); truncated = false; terminated = false; return 4; }
+    reward = 0.0; truncated = false; terminated = false; return 0;
+}
+
+// Segmented min over the lanes [gbase, gbase + n) of a warp; result valid in the group's lane 0.
+__device__ __forceinline__ double seg_min(double v, int i, int n, unsigned mask) {
+    for (int off = 1; off < n; off <<= 1) {
+        const double o = __shfl_down_sync(mask, v, off);
+        if (i + off < n) v = o < v ? o : v;
+    }
+    return v;
+}
+
+template <typename T, int SOC, int OBS, int HEADED, bool CTA, bool PER_AGENT>
+__global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32) k_step(const KArgs<T> a) {
+    using R = Real<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int N = a.N;
+    const int lane = threadIdx.x & 31;
+    // ---- thread -> (env, human) ----
+    int i, g;            // human index in env, group slot in the block
+    long long env;
+    bool live;
+    unsigned wmask = 0xffffffffu;
+    if constexpr (CTA) {
+        i = threadIdx.x; g = 0; env = blockIdx.x; live = i < N;
+    } else {
+        const int warp = threadIdx.x >> 5;
+        const int gw = lane / N;  // group within the warp
+        i = lane - gw * N;
+        g = warp * a.epw + gw;
+        env = ((long long)blockIdx.x * kWarpsPerBlock + warp) * a.epw + gw;
+        live = gw < a.epw && env < a.E;
+        wmask = __ballot_sync(0xffffffffu, live);
+    }
+    const int M = N + (a.consider_robot ? 1 : 0);  // entities exerting force
+    const int groups = CTA ? 1 : kWarpsPerBlock * a.epw;
+
+    // ---- shared memory carve-up ----
+    const int nseg = a.W * a.S;
+    Seg<T> *segs_all = reinterpret_cast<Seg<T> *>(smem_raw);
+    const int seg_groups = a.walls_per_env ? groups : 1;
+    size_t off = sizeof(Seg<T>) * (size_t)nseg * seg_groups;
+    off = (off + 31) & ~size_t(31);
+    const int slots = CTA ? (N + 1) : kWarpsPerBlock * kSlotsPerWarp;
+    Ent<T> *ents0 = reinterpret_cast<Ent<T> *>(smem_raw + off);
+    off += sizeof(Ent<T>) * (size_t)slots * 2;
+    T *rs_all = reinterpret_cast<T *>(smem_raw + off);
+    off += sizeof(T) * (size_t)slots;
+    off = (off + 7) & ~size_t(7);
+    double *red = reinterpret_cast<double *>(smem_raw + off);  // CTA mode only: [N] doubles
+
+    // walls -> shared memory (whole block cooperates, before anyone leaves)
+    if (nseg > 0) {
+        const int total = nseg * seg_groups;
+        for (int k = threadIdx.x; k < total; k += blockDim.x) {
+            const int sg = k / nseg, s = k - sg * nseg;
+            long long wenv = 0;
+            if (a.walls_per_env) {
+                wenv = CTA ? (long long)blockIdx.x : ((long long)blockIdx.x * kWarpsPerBlock * a.epw + sg);
+                if (wenv >= a.E) wenv = a.E - 1;
+            }
+            const T *w = a.walls + ((size_t)wenv * nseg + s) * 4;
+            segs_all[k] = make_seg<T>(w[0], w[1], w[2], w[3]);
+        }
+    }
+    __syncthreads();
+    if constexpr (!CTA) { if (!live) return; }
+
+    const int gslot = CTA ? 0 : ((threadIdx.x >> 5) * kSlotsPerWarp + (g - (threadIdx.x >> 5) * a.epw) * (N + 1));
+    const Seg<T> *segs = segs_all + (a.walls_per_env ? (size_t)g * nseg : 0);
+    T *rs_g = rs_all + gslot;
+    const bool leader = live && i == 0;
+    const bool has_robot = a.robot != nullptr;
+    const long long EN = a.EN;
+    const long long aidx = live ? env * N + i : 0;
+
+    // ---- load ----
+    Agent<T> me;
+    Params<T> P = a.P;
+    int gidx = 0, gcnt = 1;
+    if (live) {
+        me.px = a.dyn[SNP_DYN_PX * EN + aidx]; me.py = a.dyn[SNP_DYN_PY * EN + aidx];
+        me.vx = a.dyn[SNP_DYN_VX * EN + aidx]; me.vy = a.dyn[SNP_DYN_VY * EN + aidx];
+        me.dfx = a.dyn[SNP_DYN_DFX * EN + aidx]; me.dfy = a.dyn[SNP_DYN_DFY * EN + aidx];
+        if (HEADED) {
+            me.th = a.dyn[SNP_DYN_TH * EN + aidx];
+            me.bvx = a.dyn[SNP_DYN_BVX * EN + aidx]; me.bvy = a.dyn[SNP_DYN_BVY * EN + aidx];
+            me.om = a.dyn[SNP_DYN_OM * EN + aidx];
+        } else { me.th = me.bvx = me.bvy = me.om = T(0); }
+        me.r = a.stat[SNP_STAT_R * EN + aidx]; me.m = a.stat[SNP_STAT_M * EN + aidx];
+        me.vd = a.stat[SNP_STAT_VD * EN + aidx];
+        me.rs = me.r + a.stat[SNP_STAT_SAFETY * EN + aidx];
+        gidx = a.goal_idx[aidx]; gcnt = a.goal_cnt[aidx];
+        me.gx = a.goals[((size_t)gidx * 2 + 0) * EN + aidx]; me.gy = a.goals[((size_t)gidx * 2 + 1) * EN + aidx];
+        if constexpr (PER_AGENT) {
+            double p[20];
+#pragma unroll
+            for (int k = 0; k < 20; ++k) p[k] = (double)a.agent_params[(size_t)k * EN + aidx];
+            P = make_params<T>(p);
+        }
+        rs_g[i] = me.rs;
+    } else {
+        me = Agent<T>{};
+    }
+    me.cs = T(1); me.sn = T(0);
+    // robot (every lane keeps a copy; the group leader owns the shared-memory entity and the write-back)
+    T rpx = T(0), rpy = T(0), rvx = T(0), rvy = T(0), rr = T(0), rrs = T(0), rgx = T(0), rgy = T(0), ax = T(0), ay = T(0);
+    if (has_robot && live) {
+        const long long E = a.E;
+        rpx = a.robot[SNP_ROBOT_PX * E + env]; rpy = a.robot[SNP_ROBOT_PY * E + env];
+        rvx = a.robot[SNP_ROBOT_VX * E + env]; rvy = a.robot[SNP_ROBOT_VY * E + env];
+        rr = a.robot[SNP_ROBOT_R * E + env]; rrs = rr + a.robot[SNP_ROBOT_SAFETY * E + env];
+        rgx = a.robot[SNP_ROBOT_GX * E + env]; rgy = a.robot[SNP_ROBOT_GY * E + env];
+        if (a.action) { ax = a.action[env]; ay = a.action[E + env]; }
+        if (leader) rs_g[N] = rrs;
+    }
+    double tnow = (a.time_now && live) ? a.time_now[env] : 0.0;
+
+    int flags = 0;
+    double out_dmin = 0.0, out_reward = 0.0, out_admin = 0.0;
+
+    // ---- pre-step checks: swept collision + goal + reward (gym:232-234) ----
+    if (a.pre_checks) {
+        double cd = CUDART_INF;
+        if (live) cd = swept_distance((double)me.px, (double)me.py, (double)me.vx, (double)me.vy, (double)me.r, (double)rpx, (double)rpy,
+                                      (double)rr, (double)ax, (double)ay, a.consts[5]);
+        bool collision; double dmin;
+        if constexpr (CTA) {
+            if (live) red[i] = cd;
+            __syncthreads();
+            collision = false; dmin = CUDART_INF;
+            if (leader) for (int k = 0; k < N; ++k) { const double c = red[k]; if (c < 0) { collision = true; break; } else if (c < dmin) dmin = c; }
+            __syncthreads();
+        } else {
+            const int gbase = lane - i;
+            const unsigned gm = (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) << gbase;
+            const unsigned hit = __ballot_sync(wmask, cd < 0) & gm;
+            const int first = hit ? (__ffs(hit) - 1 - gbase) : N;
+            collision = hit != 0;
+            const double v = (i < first && cd >= 0) ? cd : CUDART_INF;
+            dmin = seg_min(v, i, N, wmask);
+        }
+        if (leader) {
+            const double endx = __dadd_rn((double)rpx, __dmul_rn((double)ax, a.consts[5]));
+            const double endy = __dadd_rn((double)rpy, __dmul_rn((double)ay, a.consts[5]));
+            const bool goal = xnorm_np(__dsub_rn(endx, (double)rgx), __dsub_rn(endy, (double)rgy)) < (double)rr;
+            bool term, trunc;
+            const int code = reward_and_info(collision, dmin, goal, tnow, a.consts, out_reward, term, trunc);
+            out_dmin = dmin;
+            flags |= (collision ? SNP_FLAG_COLLISION : 0) | (goal ? SNP_FLAG_REACHING_GOAL : 0) | (term ? SNP_FLAG_TERMINATED : 0) |
+                     (trunc ? SNP_FLAG_TRUNCATED : 0) | (code << SNP_FLAG_INFO_SHIFT);
+        }
+    }
+
+    if (HEADED && live && a.n_substeps > 0) {  // mmm:448 / fp:254-256: v = R(yaw) bv before any force is evaluated
+        R::sincos_(me.th, &me.sn, &me.cs);
+        me.vx = np_mv(me.cs, -me.sn, me.bvx, me.bvy);
+        me.vy = np_mv(me.sn, me.cs, me.bvx, me.bvy);
+    }
+
+    // ---- fused sub-steps ----
+    bool touched = false;
+    const T dt = a.dt;
+    for (int s = 0; s < a.n_substeps; ++s) {
+        Ent<T> *ents = ents0 + (size_t)(s & 1) * slots + gslot;
+        if (a.robot_mode == 1 && has_robot) {  // robot_agent.py:126-131 (holonomic): p = p + a*dt ; v = a
+            if (sizeof(T) == 8) { rpx = (T)__dadd_rn((double)rpx, __dmul_rn((double)ax, (double)dt)); rpy = (T)__dadd_rn((double)rpy, __dmul_rn((double)ay, (double)dt)); }
+            else { rpx = rpx + ax * dt; rpy = rpy + ay * dt; }
+            rvx = ax; rvy = ay;
+        }
+        if (live) { ents[i] = Ent<T>{me.px, me.py, me.vx, me.vy}; }
+        if (leader && a.consider_robot) ents[N] = Ent<T>{rpx, rpy, rvx, rvy};
+        if constexpr (CTA) __syncthreads(); else __syncwarp(wmask);
+
+        if (live) {
+            // goal switching (mmm:66-70 '<', fp:226 '<=')
+            {
+                const T dg = np_norm(me.gx - me.px, me.gy - me.py);
+                if (a.numba ? (dg <= me.r) : (dg < me.r)) {
+                    gidx = (gidx + 1 >= gcnt) ? 0 : gidx + 1;
+                    me.gx = a.goals[((size_t)gidx * 2 + 0) * EN + aidx]; me.gy = a.goals[((size_t)gidx * 2 + 1) * EN + aidx];
+                }
+            }
+            // wall force
+            T fox = T(0), foy = T(0);
+            if (a.W > 0) obstacle_force<T, OBS>(P, segs, a.W, a.S, a.numba != 0, me.px, me.py, me.vx, me.vy, me.rs, fox, foy);
+            // social force: j ascending, exactly the accumulation order of forces.py:145-151
+            T fsx = T(0), fsy = T(0);
+            const bool sym = a.symmetric != 0;
+#pragma unroll 2
+            for (int j = 0; j < M; ++j) {
+                if (j == i) continue;
+                const Ent<T> o = ents[j];
+                const T rsj = rs_g[j];
+                T fx, fy;
+                if (SOC == 2 && sym && j < i) {
+                    // symmetric path: the pair is evaluated once with the LOWER index as agent 1 and applied with a minus
+                    // sign to the other (forces.py:149-151); only Moussaid's sign(theta) makes that differ from f(i,j).
+                    pair_force<T, SOC>(P, o.x, o.y, o.vx, o.vy, rsj, me.px, me.py, me.vx, me.vy, me.rs, fx, fy);
+                    fsx -= fx; fsy -= fy;
+                } else {
+                    pair_force<T, SOC>(P, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+                    fsx += fx; fsy += fy;
+                }
+            }
+            desired_force<T>(P, me, a.numba != 0);
+            integrate<T, HEADED>(P, me, fox, foy, fsx, fsy, dt);
+            if (a.track_touch && has_robot)
+                touched |= xnorm_np((double)me.px - (double)rpx, (double)me.py - (double)rpy) < __dadd_rn((double)me.r, (double)rr);
+        }
+        if (a.time_now) tnow = __dadd_rn(tnow, a.dt_d);
+    }
+
+    // ---- post-step checks (gym:107-118) ----
+    if (a.post_checks || a.track_touch) {
+        double d = 10000.0;
+        if (live && a.post_checks) {
+            d = __dsub_rn(__dsub_rn(xnorm_np(__dsub_rn((double)me.px, (double)rpx), __dsub_rn((double)me.py, (double)rpy)), (double)me.r), (double)rr);
+            if (!(d < 10000.0)) d = 10000.0;
+        }
+        double admin; bool any_touch;
+        if constexpr (CTA) {
+            __syncthreads();
+            if (live) red[i] = d;
+            __syncthreads();
+            admin = 10000.0;
+            if (leader) for (int k = 0; k < N; ++k) admin = red[k] < admin ? red[k] : admin;
+            any_touch = __syncthreads_or(touched ? 1 : 0) != 0;
+        } else {
+            const int gbase = lane - i;
+            const unsigned gm = (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) << gbase;
+            admin = seg_min(d, i, N, wmask);
+            any_touch = (__ballot_sync(wmask, touched) & gm) != 0;
+        }
+        if (leader) {
+            if (a.post_checks) {
+                const bool agoal = xnorm_np(__dsub_rn((double)rpx, (double)rgx), __dsub_rn((double)rpy, (double)rgy)) < (double)rr;
+                out_admin = admin;
+                flags |= (admin <= 0.0 ? SNP_FLAG_ACTUAL_COLLISION : 0) | (agoal ? SNP_FLAG_ACTUAL_GOAL : 0);
+            }
+            if (any_touch) flags |= SNP_FLAG_TOUCHED;
+        }
+    }
+
+    // ---- store ----
+    if (live && a.n_substeps > 0) {
+        a.dyn[SNP_DYN_PX * EN + aidx] = me.px; a.dyn[SNP_DYN_PY * EN + aidx] = me.py;
+        a.dyn[SNP_DYN_VX * EN + aidx] = me.vx; a.dyn[SNP_DYN_VY * EN + aidx] = me.vy;
+        a.dyn[SNP_DYN_DFX * EN + aidx] = me.dfx; a.dyn[SNP_DYN_DFY * EN + aidx] = me.dfy;
+        if (HEADED) {
+            a.dyn[SNP_DYN_TH * EN + aidx] = me.th;
+            a.dyn[SNP_DYN_BVX * EN + aidx] = me.bvx; a.dyn[SNP_DYN_BVY * EN + aidx] = me.bvy;
+            a.dyn[SNP_DYN_OM * EN + aidx] = me.om;
+        }
+        a.goal_idx[aidx] = gidx;
+    }
+    if (leader) {
+        if (has_robot && a.robot_mode == 1) {
+            const long long E = a.E;
+            a.robot[SNP_ROBOT_PX * E + env] = rpx; a.robot[SNP_ROBOT_PY * E + env] = rpy;
+            a.robot[SNP_ROBOT_VX * E + env] = rvx; a.robot[SNP_ROBOT_VY * E + env] = rvy;
+        }
+        if (a.time_now) a.time_now[env] = tnow;
+        if (a.flags) a.flags[env] = flags;
+        if (a.checks) {
+            a.checks[env * 4 + 0] = out_dmin; a.checks[env * 4 + 1] = out_reward;
+            a.checks[env * 4 + 2] = out_admin; a.checks[env * 4 + 3] = 0.0;
+        }
+    }
+}
+
+template <typename T, int SOC, int OBS, int HEADED>
+int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
+    KArgs<T> a = a_in;
+    const int nseg = a.W * a.S;
+    const bool cta = a.N > 32;
+    if (a.N > 512) { set_error("snp_step handles N <= 512 humans per env (got %d); use snp_large_step", a.N); return SNP_ERR_UNSUPPORTED; }
+    const bool per_agent = a.agent_params != nullptr;
+    dim3 grid, block;
+    size_t smem;
+    if (!cta) {
+        a.epw = 32 / a.N;
+        const int epb = a.epw * kWarpsPerBlock;
+        grid = dim3((unsigned)((a.E + epb - 1) / epb));
+        block = dim3(kWarpsPerBlock * 32);
+        const int slots = kWarpsPerBlock * kSlotsPerWarp;
+        size_t off = sizeof(Seg<T>) * (size_t)nseg * (a.walls_per_env ? epb : 1);
+        off = (off + 31) & ~size_t(31);
+        smem = off + sizeof(Ent<T>) * slots * 2 + sizeof(T) * slots + 64;
+    } else {
+        a.epw = 1;
+        grid = dim3((unsigned)a.E);
+        block = dim3((unsigned)((a.N + 31) / 32 * 32));
+        size_t off = sizeof(Seg<T>) * (size_t)nseg;
+        off = (off + 31) & ~size_t(31);
+        smem = off + sizeof(Ent<T>) * (a.N + 1) * 2 + sizeof(T) * (a.N + 1) + 16 + sizeof(double) * a.N;
+    }
+    if (smem > 200 * 1024) { set_error("wall/segment tables need %zu bytes of shared memory (limit 200 KiB)", smem); return SNP_ERR_UNSUPPORTED; }
+#define SNP_LAUNCH(CTA_, PA_)                                                                                          \
+    do {                                                                                                               \
+        auto kern = k_step<T, SOC, OBS, HEADED, CTA_, PA_>;                                                            \
+        if (smem > 48 * 1024) SNP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, block, smem, st>>>(a);                                                                            \
+    } while (0)
+    if (cta) { if (per_agent) SNP_LAUNCH(true, true); else SNP_LAUNCH(true, false); }
+    else { if (per_agent) SNP_LAUNCH(false, true); else SNP_LAUNCH(false, false); }
+#undef SNP_LAUNCH
+    count_launch();
+    SNP_CUDA_OK(cudaGetLastError());
+    return SNP_OK;
+}
+
+}  // namespace
+
+template <typename T> int launch_step_small(const KArgs<T> &a, int type, cudaStream_t st) {
+    switch (type) {
+        case 0: return launch_one<T, 0, 0, 0>(a, st);
+        case 1: return launch_one<T, 1, 1, 0>(a, st);
+        case 2: return launch_one<T, 2, 0, 0>(a, st);
+        case 3: return launch_one<T, 0, 0, 1>(a, st);
+        case 4: return launch_one<T, 1, 1, 1>(a, st);
+        case 5: return launch_one<T, 2, 0, 1>(a, st);
+        case 6: return launch_one<T, 0, 0, 2>(a, st);
+        case 7: return launch_one<T, 1, 1, 2>(a, st);
+        case 8: return launch_one<T, 2, 0, 2>(a, st);
+    }
+    set_error("Type %d does not exist for this implementation", type);  // forces_parallel.py:211
+    return SNP_ERR_INVALID;
+}
+
+template int launch_step_small<float>(const KArgs<float> &, int, cudaStream_t);
+template int launch_step_small<double>(const KArgs<double> &, int, cudaStream_t);
+
+}  // namespace snp

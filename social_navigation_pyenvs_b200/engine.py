@@ -1,0 +1,291 @@
+"""CrowdEngine: E independent environments of N humans, resident on one B200, stepped by the fused CUDA kernels.
+
+Host-side mirror of the reference's MotionModelManager surface (social_gym/src/motion_model_manager.py):
+`update_humans` (:354), `get_human_states` (:285), `set_human_states` (:314), `get_next_human_observable_states` (:691),
+`set_safety_space` (:147) -- with a leading env axis on every array -- plus the gym-level fused step
+(social_gym/social_nav_gym.py:227-250) and the collision / goal checks (:107-118, social_nav_sim.py:949-1029).
+
+State is held in torch CUDA tensors in structure-of-arrays form (include/snp_b200.h); torch is plumbing only
+(memory, streams): all arithmetic happens inside libsnp_b200.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+# social_gym/src/motion_model_manager.py:15-17
+SFMS = ["sfm_helbing", "sfm_guo", "sfm_moussaid", "hsfm_farina", "hsfm_guo", "hsfm_moussaid",
+        "hsfm_new", "hsfm_new_guo", "hsfm_new_moussaid"]
+INFO_NAMES = ["Nothing", "Timeout", "Collision", "ReachGoal", "Danger"]  # social_gym/src/info.py
+
+
+def model_parameters(title: str) -> np.ndarray:
+    """The 20-vector [relax_t,Ai,Aw,Bi,Bw,Ci,Cw,Di,Dw,Ei,k1,k2,lambda,gamma,ns,ns1,ko,kd,alpha,k_lambda] that
+    Agent.set_parameters + get_parameters produce for `title` (social_gym/src/agent.py:94-243,268-388)."""
+    if title not in SFMS:
+        raise Exception(f"The human motion model '{title}' does not exist")  # motion_model_manager.py:252
+    t = SFMS.index(title)
+    p = np.zeros(20)
+    p[0] = 0.5
+    p[2], p[4] = 2000.0, 0.08
+    p[10], p[11] = 120000.0, 240000.0
+    soc = t % 3
+    if soc in (0, 1):
+        p[1], p[3] = 2000.0, 0.08
+    if soc == 1:
+        p[5], p[6], p[7], p[8] = 120.0, 120.0, 0.6, 0.6
+    if soc == 2:
+        p[9], p[12], p[13], p[14], p[15] = 360.0, 2.0, 0.35, 2.0, 3.0
+    if t >= 3:
+        p[16], p[17], p[18], p[19] = 1.0, 500.0, 3.0, 0.1
+    return p
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class CrowdEngine:
+    def __init__(self, model, E, N, G=2, dtype=torch.float64, device="cuda", consider_robot=False, symmetric=True,
+                 numba_compat=False, params=None, walls=None, has_robot=True):
+        if model not in SFMS:
+            raise Exception(f"The human motion model '{model}' does not exist")
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError("dtype must be torch.float32 or torch.float64")
+        self.lib = L.lib()
+        self.motion_model_title = model
+        self.type = SFMS.index(model)
+        self.headed = self.type >= 3
+        self.E, self.N, self.G = int(E), int(N), int(G)
+        self.dtype, self.device = dtype, torch.device(device)
+        self.consider_robot, self.symmetric, self.numba_compat = bool(consider_robot), bool(symmetric), bool(numba_compat)
+        self.params = model_parameters(model) if params is None else np.asarray(params, np.float64).reshape(20)
+        kw = dict(dtype=dtype, device=self.device)
+        self.dyn = torch.zeros((L.DYN_FIELDS, E, N), **kw)
+        self.stat = torch.zeros((L.STAT_FIELDS, E, N), **kw)
+        self.goals = torch.zeros((G, 2, E, N), **kw)
+        self.goal_idx = torch.zeros((E, N), dtype=torch.int32, device=self.device)
+        self.goal_cnt = torch.ones((E, N), dtype=torch.int32, device=self.device)
+        self.robot = torch.zeros((L.ROBOT_FIELDS, E), **kw) if (has_robot or consider_robot) else None
+        self.agent_params = None
+        self.action = torch.zeros((2, E), **kw)
+        self.time_now = torch.zeros((E,), dtype=torch.float64, device=self.device)
+        self.flags = torch.zeros((E,), dtype=torch.int32, device=self.device)
+        self.checks = torch.zeros((E, 4), dtype=torch.float64, device=self.device)
+        # reward constants of crowd_nav/configs/env.config: time_limit, collision_penalty, success_reward,
+        # discomfort_dist, discomfort_penalty_factor, robot_time_step
+        self.consts = [50.0, -0.25, 1.0, 0.2, 0.5, 0.25]
+        self.walls, self.W, self.S, self.walls_per_env = None, 0, 0, 0
+        if walls is not None:
+            self.set_walls(walls)
+
+    # ------------------------------------------------------------------ construction from reference arrays
+    @classmethod
+    def from_reference_arrays(cls, model, states, goals, walls=None, params=None, safety=None, consider_robot=False,
+                              all_params_equal=True, numba_compat=False, dtype=torch.float64, device="cuda", robot=None):
+        """states [E,rows,13] float64 rows (agent.py:256; rows = N + consider_robot), goals [E,N,G,2] NaN padded,
+        walls [W,S,2,2] or [E,W,S,2,2] NaN padded, params [20] / [E,N,20], safety [E,rows], robot [E,13] (when the robot is
+        not a row of `states` but checks are wanted)."""
+        states = np.ascontiguousarray(states, np.float64)
+        goals = np.ascontiguousarray(goals, np.float64)
+        E, rows, _ = states.shape
+        N, G = goals.shape[1], goals.shape[2]
+        if rows != N + int(consider_robot):
+            raise ValueError(f"states has {rows} rows per env, expected {N + int(consider_robot)}")
+        p_uniform, p_rows = None, None
+        if params is not None:
+            params = np.asarray(params, np.float64)
+            if params.ndim == 1:
+                p_uniform = params
+            else:
+                flat = params.reshape(-1, 20)
+                if np.all(flat == flat[0]):
+                    p_uniform = flat[0]
+                else:
+                    p_rows = params.reshape(E, N, 20)
+        eng = cls(model, E, N, G, dtype=dtype, device=device, consider_robot=consider_robot, symmetric=all_params_equal,
+                  numba_compat=numba_compat, params=p_uniform, walls=walls, has_robot=consider_robot or robot is not None)
+        if p_rows is not None:
+            eng.agent_params = torch.as_tensor(np.ascontiguousarray(p_rows.transpose(2, 0, 1)), dtype=dtype, device=eng.device)
+        eng.load_rows(states, safety)
+        eng.load_goals(goals)
+        if robot is not None and not consider_robot:
+            eng.set_robot_rows(robot)
+        return eng
+
+    # ------------------------------------------------------------------ descriptors
+    def _crowd(self):
+        c = L.SnpCrowd()
+        c.E, c.N, c.G = self.E, self.N, self.G
+        c.dtype = L.SNP_F64 if self.dtype == torch.float64 else L.SNP_F32
+        c.dyn, c.stat, c.goals = self.dyn.data_ptr(), self.stat.data_ptr(), self.goals.data_ptr()
+        c.goal_idx, c.goal_cnt = self.goal_idx.data_ptr(), self.goal_cnt.data_ptr()
+        c.agent_params = None if self.agent_params is None else self.agent_params.data_ptr()
+        c.params = (ctypes.c_double * 20)(*self.params.tolist())
+        c.robot = None if self.robot is None else self.robot.data_ptr()
+        c.walls = None if self.walls is None else self.walls.data_ptr()
+        c.W, c.S, c.walls_per_env = self.W, self.S, self.walls_per_env
+        return c
+
+    def _opts(self, dt, n_substeps, robot_mode=0, pre_checks=False, post_checks=False, track_touch=False, advance_time=False):
+        o = L.SnpStepOpts()
+        o.type, o.consider_robot, o.symmetric, o.numba_compat = self.type, int(self.consider_robot), int(self.symmetric), int(self.numba_compat)
+        o.n_substeps, o.robot_mode, o.dt = int(n_substeps), int(robot_mode), float(dt)
+        o.action = self.action.data_ptr()
+        o.pre_checks, o.post_checks, o.track_touch = int(pre_checks), int(post_checks), int(track_touch)
+        o.consts = (ctypes.c_double * 6)(*self.consts)
+        o.time_now = self.time_now.data_ptr() if (advance_time or pre_checks) else None
+        o.flags, o.checks = self.flags.data_ptr(), self.checks.data_ptr()
+        return o
+
+    # ------------------------------------------------------------------ loading / reading in the reference's layouts
+    def set_walls(self, walls):
+        """walls [W,S,2,2] (shared) or [E,W,S,2,2] float64, NaN padded (motion_model_manager.py:268-276)."""
+        walls = np.asarray(walls, np.float64)
+        if walls.size == 0 or walls.shape[-4] == 0:
+            self.walls, self.W, self.S, self.walls_per_env = None, 0, 0, 0
+            return
+        per_env = walls.ndim == 5
+        self.W, self.S, self.walls_per_env = walls.shape[-4], walls.shape[-3], int(per_env)
+        flat = walls.reshape((self.E if per_env else 1), self.W * self.S, 4)
+        self.walls = torch.as_tensor(np.ascontiguousarray(flat), dtype=self.dtype, device=self.device)
+
+    def load_rows(self, states, safety=None):
+        """Upload reference state rows [E,rows,13] (+ safety [E,rows]) and scatter them into the SoA on the device."""
+        states = np.ascontiguousarray(states, np.float64)
+        rows = states.shape[1]
+        d_rows = torch.from_numpy(states).to(self.device)
+        d_saf = None if safety is None else torch.from_numpy(np.ascontiguousarray(safety, np.float64)).to(self.device)
+        L.check(self.lib.snp_unpack_states(ctypes.byref(self._crowd()), _ptr(d_rows), rows, _ptr(d_saf), _stream()))
+
+    def load_goals(self, goals):
+        d = torch.from_numpy(np.ascontiguousarray(goals, np.float64)).to(self.device)
+        L.check(self.lib.snp_unpack_goals(ctypes.byref(self._crowd()), _ptr(d), _ptr(self.goal_cnt), _stream()))
+
+    def set_robot_rows(self, robot_rows, safety=None):
+        """robot_rows [E,13] reference rows (robot.get_safe_state(), motion_model_manager.py:359)."""
+        r = np.asarray(robot_rows, np.float64).reshape(self.E, 13)
+        out = np.zeros((L.ROBOT_FIELDS, self.E))
+        out[L.ROBOT_PX], out[L.ROBOT_PY], out[L.ROBOT_TH] = r[:, 0], r[:, 1], r[:, 2]
+        out[L.ROBOT_VX], out[L.ROBOT_VY] = r[:, 3], r[:, 4]
+        out[L.ROBOT_R], out[L.ROBOT_GX], out[L.ROBOT_GY] = r[:, 8], r[:, 10], r[:, 11]
+        if safety is not None:
+            out[L.ROBOT_SAFETY] = np.asarray(safety, np.float64).reshape(self.E)
+        else:
+            out[L.ROBOT_SAFETY] = self.robot[L.ROBOT_SAFETY].double().cpu().numpy()
+        self.robot.copy_(torch.as_tensor(out, dtype=self.dtype))
+
+    def rows(self, template):
+        """Download the state in reference row form: `template` [E,rows,13] provides the static columns and the robot row
+        (as update_humans_parallel's np.copy does, forces_parallel.py:214); columns 0..7 and 10..11 of human rows are replaced."""
+        d = torch.from_numpy(np.ascontiguousarray(template, np.float64)).to(self.device)
+        L.check(self.lib.snp_pack_states(ctypes.byref(self._crowd()), _ptr(d), template.shape[1], _stream()))
+        return d.cpu().numpy()
+
+    def desired_force(self):
+        return torch.stack([self.dyn[L.DYN_DFX], self.dyn[L.DYN_DFY]], -1).double().cpu().numpy()
+
+    def set_desired_force(self, df):
+        df = torch.as_tensor(np.asarray(df, np.float64), dtype=self.dtype, device=self.device)
+        self.dyn[L.DYN_DFX].copy_(df[..., 0]); self.dyn[L.DYN_DFY].copy_(df[..., 1])
+
+    def current_goals(self):
+        idx = self.goal_idx.long()[None, None]  # [1,1,E,N]
+        return torch.gather(self.goals, 0, idx.expand(1, 2, self.E, self.N))[0].permute(1, 2, 0)  # [E,N,2]
+
+    # ------------------------------------------------------------------ the hot path
+    def update_humans(self, t=0.0, dt=0.0125, post_update=True, n_substeps=1):
+        """MotionModelManager.update_humans (motion_model_manager.py:354) for every env: `n_substeps` Euler updates in one launch."""
+        L.check(self.lib.snp_step(ctypes.byref(self._crowd()), ctypes.byref(self._opts(dt, n_substeps)), _stream()))
+
+    def step(self, action=None, dt=0.0125, n_substeps=20, pre_checks=True, post_checks=False, track_touch=False):
+        """SocialNavGym.step for every env (social_nav_gym.py:227-250): swept collision / goal test and reward on the current
+        state, then `n_substeps` x (robot.step(action, dt); update_humans(dt)).  `action` [E,2] holonomic velocities
+        (device tensor or array); None reuses self.action.  Results land in self.flags / self.checks / self.time_now."""
+        if action is not None:
+            a = torch.as_tensor(action, dtype=self.dtype, device=self.device)
+            self.action.copy_(a.t() if a.shape == (self.E, 2) else a)
+        o = self._opts(dt, n_substeps, robot_mode=1, pre_checks=pre_checks, post_checks=post_checks, track_touch=track_touch, advance_time=True)
+        L.check(self.lib.snp_step(ctypes.byref(self._crowd()), ctypes.byref(o), _stream()))
+
+    def run_checks(self, action=None, pre=True, post=True):
+        """collision_detection_and_reaching_goal + compute_reward_and_infos (social_nav_sim.py:949-1029) and
+        check_actual_collisions_and_goal (social_nav_gym.py:107-118) on the current state, without stepping."""
+        if action is not None:
+            a = torch.as_tensor(action, dtype=self.dtype, device=self.device)
+            self.action.copy_(a.t() if a.shape == (self.E, 2) else a)
+        o = self._opts(0.0, 0, pre_checks=pre, post_checks=post)
+        L.check(self.lib.snp_checks(ctypes.byref(self._crowd()), ctypes.byref(o), _stream()))
+        return self.decode_flags()
+
+    def decode_flags(self):
+        f = self.flags.cpu().numpy()
+        c = self.checks.cpu().numpy()
+        return dict(collision=(f & L.FLAG_COLLISION) != 0, dmin=c[:, 0], reaching_goal=(f & L.FLAG_REACHING_GOAL) != 0,
+                    reward=c[:, 1], terminated=(f & L.FLAG_TERMINATED) != 0, truncated=(f & L.FLAG_TRUNCATED) != 0,
+                    info=(f >> L.FLAG_INFO_SHIFT) & 7, actual_collision=(f & L.FLAG_ACTUAL_COLLISION) != 0, actual_dmin=c[:, 2],
+                    actual_goal=(f & L.FLAG_ACTUAL_GOAL) != 0, touched=(f & L.FLAG_TOUCHED) != 0)
+
+    def check_actual_collisions_and_goal(self):
+        r = self.run_checks(pre=False, post=True)
+        return r["actual_collision"], r["actual_dmin"], r["actual_goal"]
+
+    # ------------------------------------------------------------------ MotionModelManager surface
+    def get_human_states(self, include_goal=True, headed=False):
+        """[E,N,8] / [E,N,6] / [E,N,4] in the layouts of motion_model_manager.py:285-312."""
+        d = self.dyn
+        if include_goal:
+            g = self.current_goals()
+            v = (d[L.DYN_BVX], d[L.DYN_BVY]) if headed else (d[L.DYN_VX], d[L.DYN_VY])
+            out = torch.stack([d[L.DYN_PX], d[L.DYN_PY], d[L.DYN_TH], v[0], v[1], d[L.DYN_OM], g[..., 0], g[..., 1]], -1)
+        elif headed:
+            out = torch.stack([d[L.DYN_PX], d[L.DYN_PY], d[L.DYN_TH], d[L.DYN_BVX], d[L.DYN_BVY], d[L.DYN_OM]], -1)
+        else:
+            out = torch.stack([d[L.DYN_PX], d[L.DYN_PY], d[L.DYN_VX], d[L.DYN_VY]], -1)
+        return out.double().cpu().numpy()
+
+    def set_human_states(self, state, just_visual=False):
+        """motion_model_manager.py:314-352: state [E,N,8] = [x,y,yaw,Vx|BVx,Vy|BVy,Omega,Gx,Gy]; the goal list is rewound so
+        that its head equals (Gx,Gy) (rewind_goals, :57-64); for headed models v = R(yaw) bv is refreshed (:324)."""
+        s = torch.as_tensor(np.asarray(state, np.float64), device=self.device)
+        d = self.dyn
+        d[L.DYN_PX].copy_(s[..., 0]); d[L.DYN_PY].copy_(s[..., 1]); d[L.DYN_TH].copy_(s[..., 2])
+        if just_visual:
+            return
+        if self.headed:
+            d[L.DYN_BVX].copy_(s[..., 3]); d[L.DYN_BVY].copy_(s[..., 4])
+            c, sn = torch.cos(s[..., 2]), torch.sin(s[..., 2])
+            d[L.DYN_VX].copy_(c * s[..., 3] - sn * s[..., 4]); d[L.DYN_VY].copy_(sn * s[..., 3] + c * s[..., 4])
+        else:
+            d[L.DYN_VX].copy_(s[..., 3]); d[L.DYN_VY].copy_(s[..., 4])
+        d[L.DYN_OM].copy_(s[..., 5])
+        # goal rewind: first slot whose goal equals (Gx, Gy); unknown goals overwrite the list (parallel traffic, :58)
+        g = self.goals.double().permute(2, 3, 0, 1)  # [E,N,G,2]
+        match = (g == s[..., None, 6:8]).all(-1) & (torch.arange(self.G, device=self.device) < self.goal_cnt[..., None])
+        has = match.any(-1)
+        self.goal_idx.copy_(torch.where(has, match.int().argmax(-1), torch.zeros_like(self.goal_idx)).int())
+        if (~has).any():
+            e, n = torch.nonzero(~has, as_tuple=True)
+            self.goals[0, 0, e, n] = s[e, n, 6].to(self.dtype); self.goals[0, 1, e, n] = s[e, n, 7].to(self.dtype)
+            self.goal_cnt[e, n] = 1
+
+    def get_next_human_observable_states(self, dt, theta_and_omega_visible=False):
+        """motion_model_manager.py:691-709: peek one update of length dt and restore pose, velocity and goal.  As in the
+        reference, the carried desired force is NOT restored."""
+        keep_dyn, keep_idx = self.dyn[:L.DYN_DFX].clone(), self.goal_idx.clone()
+        self.update_humans(0.0, dt, post_update=False)
+        out = self.get_human_states(include_goal=True, headed=False) if theta_and_omega_visible else self.get_human_states(False, False)
+        self.dyn[:L.DYN_DFX].copy_(keep_dyn); self.goal_idx.copy_(keep_idx)
+        return out
+
+    def set_safety_space(self, safety_space):
+        """motion_model_manager.py:147-164: humans (and a visible robot) get 0.01 + safety_space."""
+        self.stat[L.STAT_SAFETY].fill_(0.01 + safety_space)
+        if self.robot is not None and self.consider_robot:
+            self.robot[L.ROBOT_SAFETY].fill_(0.01 + safety_space)

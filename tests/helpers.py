@@ -63,3 +63,28 @@ def observed(states, desired, n):
 def consecutive_pairs(d):
     s = d["steps"]
     return [k for k in range(len(s) - 1) if s[k + 1] == s[k] + 1]
+
+
+def wrap_angle_cols(got, ref, col=2):
+    """Headings are angles: -pi and +pi are the same heading (bound_angle, utils.py:7-13, wraps at +-pi, and an fp32 -pi lies
+    on the other side of the fp64 one).  Returns a copy of `got` whose heading column is shifted by the multiple of 2*pi
+    that brings it closest to `ref`."""
+    out = got.copy()
+    out[..., col] = ref[..., col] + (got[..., col] - ref[..., col] + np.pi) % (2 * np.pi) - np.pi
+    return out
+
+
+def moussaid_rest_ambiguity(states, n, dt, Ei=360.0, gamma=0.35):
+    """Upper bound of what ONE step from rest can differ by when the sign k_ij = sign(theta_ij) of Moussaid's lateral term
+    flips (forces.py:100-110): theta_ij is zero up to rounding when both agents are at rest, so k_ij in {-1,0,+1} is decided by
+    the last ulp of atan2 -- in the reference itself.  Per human i the lateral force is ambiguous by at most
+    sum_j 2*Ei*exp(-d_ij/gamma) (|interaction vector| = 1 at rest), i.e. a velocity change of that times dt/m; the HSFM torque
+    law turns the same force ambiguity into at most k_lambda*(pi+1)*m times as much angular velocity."""
+    p = states[:, 0:2]
+    m = states[:n, 9]
+    bound = np.zeros(n)
+    for i in range(n):
+        d = np.linalg.norm(p[i] - p, axis=1)
+        d[i] = np.inf
+        bound[i] = (2 * Ei * np.exp(-d / gamma)).sum() * dt / m[i]
+    return bound, 0.1 * (np.pi + 1) * m * bound

@@ -1,0 +1,115 @@
+"""GPU parity of the fused step kernel (through the C ABI) against the golden vectors recorded from the live reference
+and against the CPU oracle, single step from identical input states.
+
+Tolerances are the project's: |delta| <= tol * max(|ref|, 1) with tol = 1e-9 (fp64 mode) / 1e-4 (fp32 mode).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import OracleConfig
+from helpers import (traj_names, load_traj, rel_err, inputs_at, observed, consecutive_pairs, wrap_angle_cols,
+                     moussaid_rest_ambiguity)
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float64: 1e-9, torch.float32: 1e-4}
+
+
+def _engine(d, S, G, D, dtype, numba=False):
+    from social_navigation_pyenvs_b200 import CrowdEngine, SFMS
+    eng = CrowdEngine.from_reference_arrays(SFMS[int(d["type"])], S[None], G[None], walls=d["walls"], params=d["params"][None],
+                                            safety=d["safety"][None, : S.shape[0]], consider_robot=d["consider_robot"],
+                                            all_params_equal=d["all_equal"], numba_compat=numba, dtype=dtype)
+    eng.set_desired_force(D[None])
+    return eng
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name", traj_names())
+def test_single_step_vs_reference_golden(name, dtype):
+    d = load_traj(name)
+    n = d["n"]
+    moussaid = int(d["type"]) % 3 == 2
+    ks = consecutive_pairs(d)
+    ks = ks[:: max(1, len(ks) // 8)]  # a spread of recorded states, including the at-rest first one
+    for k in ks:
+        S, G, D, rv = inputs_at(d, k)
+        if dtype == torch.float32:  # identical inputs: hand both sides fp32-representable values
+            S = S.astype(np.float32).astype(np.float64); D = D.astype(np.float32).astype(np.float64)
+        if d["consider_robot"]:  # robot.step happens before update_humans (gym:242-244)
+            S[n, 0:2] = S[n, 0:2] + rv * float(d["dt"]); S[n, 3:5] = rv
+        eng = _engine(d, S, G, D, dtype)
+        eng.update_humans(0.0, float(d["dt"]))
+        got = observed(eng.rows(S[None])[0], eng.desired_force()[0], n)
+        if dtype == torch.float64:
+            ref = d["traj"][k + 1]
+        else:  # fp32 inputs were rounded, so the reference value is the oracle on the same rounded inputs
+            cfg = OracleConfig(int(d["type"]), d["consider_robot"], d["all_equal"], False)
+            S2, _, D2 = oracle.update_humans(cfg, S[None], G[None], d["walls"], d["params"][None], d["safety"][None, : S.shape[0]],
+                                             D[None], float(d["dt"]), 1)
+            ref = observed(S2[0], D2[0], n)
+        got = wrap_angle_cols(got, ref)
+        tol = np.full((n, 1), TOL[dtype])
+        if moussaid and np.all(d["traj"][k][:, 3:5] == 0.0):
+            # from rest the Moussaid lateral term has an arbitrary sign in the reference itself: widen by that bound only
+            dv, dw = moussaid_rest_ambiguity(S, n, float(d["dt"]))
+            tol = tol + np.maximum(dv, dw)[:, None]
+        # desired-force columns are forces (hundreds of newtons): compare relative to their own scale
+        err_state = rel_err(got[:, :10], ref[:, :10])
+        err_force = rel_err(got[:, 10:], ref[:, 10:], scale=100.0)
+        assert (err_state <= tol).all() and (err_force <= tol).all(), (name, int(d["steps"][k]), err_state.max(), err_force.max())
+        assert np.array_equal(got[:, 8:10], ref[:, 8:10]) or dtype == torch.float32  # current goal: exact
+
+
+@pytest.mark.parametrize("name", ["cc25_robot_hsfm_farina", "walls7eq_hsfm_new_guo", "walls7_sfm_helbing", "jym_hsfm_new_guo", "corridor_sfm_guo"])
+def test_fused_substeps_match_stepwise_oracle(name):
+    """n_substeps fused in one launch == the same number of oracle updates (fp64), incl. goal switching and a moving robot."""
+    d = load_traj(name)
+    n = d["n"]
+    S, G, D, rv = inputs_at(d, 0)
+    cfg = OracleConfig(int(d["type"]), d["consider_robot"], d["all_equal"], False)
+    saf = d["safety"][None, : S.shape[0]]
+    k = 40
+    S2, G2, D2 = oracle.update_humans(cfg, S[None], G[None], d["walls"], d["params"][None], saf, D[None], float(d["dt"]), k,
+                                      robot_vel=rv[None] if d["consider_robot"] else None)
+    eng = _engine(d, S, G, D, torch.float64)
+    if d["consider_robot"]:
+        eng.action.copy_(torch.as_tensor(rv[:, None]))
+        eng.step(None, float(d["dt"]), n_substeps=k, pre_checks=False)
+    else:
+        eng.update_humans(0.0, float(d["dt"]), n_substeps=k)
+    got = observed(eng.rows(S[None])[0], eng.desired_force()[0], n)
+    ref = observed(S2[0], D2[0], n)
+    assert rel_err(got[:, :10], ref[:, :10]).max() < 1e-9, name
+    if d["consider_robot"]:
+        assert rel_err(eng.robot[:2, 0].cpu().numpy(), S2[0, n, 0:2]).max() < 1e-14
+
+
+def test_numba_semantics_operator():
+    """update_humans_parallel(..., semantics='numba') reproduces the reference's Numba operator outputs (fp:184)."""
+    import os
+    from helpers import GOLDEN
+    from social_navigation_pyenvs_b200 import update_humans_parallel
+    z = np.load(os.path.join(GOLDEN, "numba_operator.npz"))
+    keys = sorted(k[:-8] for k in z.files if k.endswith("_states0"))
+    for key in keys:
+        typ, equal, robot = (int(v) for v in z[key + "_flags"])
+        S, G = z[key + "_states0"].copy(), z[key + "_goals0"].copy()
+        walls = z[key + "_walls"]
+        for step in range(3):
+            S = update_humans_parallel(typ, S, G, walls if walls.shape[0] else None, z[key + "_params"], 0.0125, z[key + "_safety"],
+                                       all_params_equal=bool(equal), last_is_robot=bool(robot), semantics="numba")
+            ref = z[key + "_out"][step]
+            n = G.shape[0]
+            # Moussaid: the first updates start from rest, where the lateral term's sign is rounding noise (helpers.py)
+            tol = 1e-3 if typ % 3 == 2 else 1e-9
+            assert rel_err(S[:n, :8], ref[:n, :8]).max() <= tol, (key, step)
+            assert np.array_equal(S[:, 8:], ref[:, 8:]), (key, step)
+
+
+def test_operator_rejects_bad_type():
+    from social_navigation_pyenvs_b200 import update_humans_parallel
+    with pytest.raises(ValueError):
+        update_humans_parallel(9, np.zeros((2, 13)), np.zeros((2, 1, 2)), None, np.zeros((2, 20)), 0.01, np.zeros(2))
