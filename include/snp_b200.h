@@ -171,6 +171,8 @@ int snp_laser_host(int32_t E, int32_t N, const double *humans, const double *wal
 /* Runs a register-resident FMA / MUFU loop on every SM and returns achieved TFLOP/s (kind 0 fp32 FMA, 1 fp64 FMA)
  * or Gop/s (kind 2 MUFU.EX2).  Used as the measured denominator of the compute roofline. */
 int snp_measure_pipe_peak(int32_t kind, double *out);
+/* Test hook: y[i] = the kernels' table-based fp64 exp (csrc/snp_math.cuh exp_tbl) of x[i]; device pointers. */
+int snp_debug_exp(const double *x_dev, double *y_dev, int32_t n, void *cuda_stream);
 /* Launch statistics since the last reset: number of kernels this library launched. */
 int64_t snp_launch_count(int32_t reset);
 

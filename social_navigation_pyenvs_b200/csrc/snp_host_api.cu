@@ -248,12 +248,28 @@ __global__ void __launch_bounds__(256) k_mufu_peak(float *out, int iters) {
     if (x0 + x1 + x2 + x3 == -1.0f) out[0] = x0;
 }
 
+__global__ void k_debug_exp(const double *x, double *y, int n) {
+    __shared__ double tbl[64];
+    exp_table_init(tbl);
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = exp_tbl(x[i], tbl);
+}
+
 }  // namespace
 }  // namespace snp
 
 using namespace snp;
 
 extern "C" {
+
+int snp_debug_exp(const double *x_dev, double *y_dev, int32_t n, void *stream) {
+    if (!x_dev || !y_dev || n <= 0) { set_error("snp_debug_exp: bad argument"); return SNP_ERR_INVALID; }
+    k_debug_exp<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x_dev, y_dev, n);
+    count_launch();
+    SNP_CUDA_OK(cudaGetLastError());
+    return SNP_OK;
+}
 
 int snp_update_humans_parallel_host(int32_t type, int32_t E, int32_t N, int32_t G, double *agents_state, double *goals,
                                     const double *obstacles, int32_t W, int32_t S, const double *agents_params, double dt,

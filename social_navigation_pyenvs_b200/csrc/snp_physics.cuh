@@ -30,8 +30,8 @@ template <typename T> __host__ __device__ inline Params<T> make_params(const dou
 // Force exerted on agent 1 by agent 2 (forces.py:63-128).  rs = radius + safety_space.
 // SOC: 0 Helbing, 1 Guo, 2 Moussaid.
 template <typename T, int SOC>
-__device__ __forceinline__ void pair_force(const Params<T> &P, T x1, T y1, T vx1, T vy1, T rs1, T x2, T y2, T vx2, T vy2, T rs2,
-                                           T &fx, T &fy) {
+__device__ __forceinline__ void pair_force(const Params<T> &P, const double *tbl, T x1, T y1, T vx1, T vy1, T rs1, T x2, T y2, T vx2,
+                                           T vy2, T rs2, T &fx, T &fy) {
     using R = Real<T>;
     const T dx = x1 - x2, dy = y1 - y2;
     const T d2 = np_sq(dx, dy);
@@ -43,9 +43,9 @@ __device__ __forceinline__ void pair_force(const Params<T> &P, T x1, T y1, T vx1
     if (SOC < 2) {
         // t = (-ny, nx); dv = (v2 - v1) . t
         const T dv = np_dot(vx2 - vx1, vy2 - vy1, -ny, nx);
-        const T cn = fma_<T>(P.Ai, R::exp_(rd * P.inv_Bi), P.k1 * prd);
+        const T cn = fma_<T>(P.Ai, R::exp_(rd * P.inv_Bi, tbl), P.k1 * prd);
         T ct = P.k2 * prd * dv;
-        if (SOC == 1) ct = fma_<T>(P.Ci, R::exp_(rd * P.inv_Di), ct);
+        if (SOC == 1) ct = fma_<T>(P.Ci, R::exp_(rd * P.inv_Di, tbl), ct);
         fx = fma_<T>(cn, nx, ct * -ny);
         fy = fma_<T>(cn, ny, ct * nx);
     } else {
@@ -59,9 +59,9 @@ __device__ __forceinline__ void pair_force(const Params<T> &P, T x1, T y1, T vx1
         const T k = sign_(theta);
         const T F = P.gamma * inorm;
         const T dvh = np_dot(vx2 - vx1, vy2 - vy1, -iy, ix);
-        const T e0 = P.Ei * R::exp_(-dist * R::rcp_(F));
+        const T e0 = P.Ei * R::exp_(-dist * R::rcp_(F), tbl);
         const T a = P.ns1 * F * theta, b = P.ns * F * theta;
-        const T ea = R::exp_(-(a * a)), eb = k * R::exp_(-(b * b));
+        const T ea = R::exp_(-(a * a), tbl), eb = k * R::exp_(-(b * b), tbl);
         const T ci = fma_<T>(e0, ea, P.k1 * prd);       // coefficient of i_ij
         const T ch = fma_<T>(e0, eb, P.k2 * prd * dvh);  // coefficient of h_ij = (-iy, ix)
         fx = -fma_<T>(ci, ix, ch * -iy);
@@ -81,33 +81,34 @@ template <typename T> __device__ __forceinline__ Seg<T> make_seg(T ax, T ay, T b
 }
 
 // Closest point of one polygon (obstacle.py:53-66): serial keeps the LAST segment among ties ('<=', init 10000),
-// Numba keeps the first (np.argmin, fp:252).
+// Numba keeps the first (np.argmin, fp:252).  Distances are compared squared (sqrt is monotone; one sqrt per polygon is
+// then taken by the caller instead of one per segment).  Padding slots (ax = NaN) sit at the end of each polygon's slots
+// (motion_model_manager.py:270-275) and `cnt` excludes them.
 template <typename T>
-__device__ __forceinline__ void closest_point(const Seg<T> *segs, int S, T px, T py, bool first_wins, T &cx, T &cy) {
-    T best = first_wins ? Real<T>::inf() : T(10000);
+__device__ __forceinline__ void closest_point(const Seg<T> *segs, int cnt, T px, T py, bool first_wins, T &cx, T &cy) {
+    T best = first_wins ? Real<T>::inf() : T(1.0e8);
     cx = T(0); cy = T(0);
-    for (int s = 0; s < S; ++s) {
+    for (int s = 0; s < cnt; ++s) {
         const Seg<T> g = segs[s];
-        if (g.ax != g.ax) continue;  // NaN padding (uniform across the warp: walls are shared by the env)
         T t = np_dot(px - g.ax, py - g.ay, g.ex, g.ey) * g.inv_len2;
         t = t > T(0) ? t : T(0);
         t = t < T(1) ? t : T(1);
         const T hx = fma_<T>(t, g.ex, g.ax), hy = fma_<T>(t, g.ey, g.ay);
-        const T d = np_norm(hx - px, hy - py);
+        const T d = np_sq(hx - px, hy - py);
         const bool take = first_wins ? (d < best) : (d <= best);
-        if (take) { best = d; cx = hx; cy = hy; }
+        best = take ? d : best; cx = take ? hx : cx; cy = take ? hy : cy;
     }
 }
 
 // Wall force of all W polygons on one agent (forces.py:27-53).  OBS: 0 Helbing (mean over walls), 1 Guo (sum; mean in Numba).
 template <typename T, int OBS>
-__device__ __forceinline__ void obstacle_force(const Params<T> &P, const Seg<T> *segs, int W, int S, bool numba, T px, T py, T vx, T vy,
-                                               T rs, T &fx, T &fy) {
+__device__ __forceinline__ void obstacle_force(const Params<T> &P, const double *tbl, const Seg<T> *segs, const int *seg_cnt, int W, int S,
+                                               bool numba, T px, T py, T vx, T vy, T rs, T &fx, T &fy) {
     using R = Real<T>;
     fx = T(0); fy = T(0);
     for (int w = 0; w < W; ++w) {
         T cx, cy;
-        closest_point<T>(segs + w * S, S, px, py, numba, cx, cy);
+        closest_point<T>(segs + w * S, seg_cnt[w], px, py, numba, cx, cy);
         const T dx = px - cx, dy = py - cy;
         const T d2 = np_sq(dx, dy);
         const T inv = R::rsqrt_(d2);
@@ -116,10 +117,10 @@ __device__ __forceinline__ void obstacle_force(const Params<T> &P, const Seg<T> 
         const T dv = -np_dot(vx, vy, -ny, nx);
         const T rd = rs - dist;
         const T prd = max0(rd);
-        const T cn = fma_<T>(P.Aw, R::exp_(rd * P.inv_Bw), P.k1 * prd);
+        const T cn = fma_<T>(P.Aw, R::exp_(rd * P.inv_Bw, tbl), P.k1 * prd);
         T ct;
         if (OBS == 0) ct = -(P.k2 * prd * dv);
-        else ct = (-P.Cw * R::exp_(rd * P.inv_Dw) - P.k2 * prd) * dv;
+        else ct = (-P.Cw * R::exp_(rd * P.inv_Dw, tbl) - P.k2 * prd) * dv;
         fx += fma_<T>(cn, nx, ct * -ny);
         fy += fma_<T>(cn, ny, ct * nx);
     }

@@ -28,14 +28,23 @@ __global__ void __launch_bounds__(kTile) k_large_step(const LargeArgs<T> la) {
     const KArgs<T> &a = la.k;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nseg = a.W * a.S;
-    Seg<T> *segs = reinterpret_cast<Seg<T> *>(smem_raw);
-    size_t off = (sizeof(Seg<T>) * (size_t)nseg + 31) & ~size_t(31);
+    double *exp_tbl_s = reinterpret_cast<double *>(smem_raw);
+    Seg<T> *segs = reinterpret_cast<Seg<T> *>(smem_raw + 512);
+    size_t off = 512 + ((sizeof(Seg<T>) * (size_t)nseg + 31) & ~size_t(31));
     Ent<T> *tile = reinterpret_cast<Ent<T> *>(smem_raw + off);
     T *tile_rs = reinterpret_cast<T *>(smem_raw + off + sizeof(Ent<T>) * kTile);
+    int *seg_cnt = reinterpret_cast<int *>(smem_raw + off + sizeof(Ent<T>) * kTile + sizeof(T) * kTile);
 
+    if (sizeof(T) == 8) exp_table_init(exp_tbl_s);
     for (int k = threadIdx.x; k < nseg; k += blockDim.x) {
         const T *w = a.walls + (size_t)k * 4;
         segs[k] = make_seg<T>(w[0], w[1], w[2], w[3]);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < a.W; k += blockDim.x) {
+        int c = 0;
+        while (c < a.S && segs[(size_t)k * a.S + c].ax == segs[(size_t)k * a.S + c].ax) ++c;
+        seg_cnt[k] = c;
     }
 
     const long long N = a.EN;
@@ -87,16 +96,19 @@ __global__ void __launch_bounds__(kTile) k_large_step(const LargeArgs<T> la) {
             const long long jj = j0 + t - la.self_offset;  // index of the entity in this crowd's numbering
 #pragma unroll
             for (int q = 0; q < kAgentsPerThread; ++q) {
-                if (jj == idx[q]) continue;
                 Agent<T> &m = me[q];
+                const bool self = jj == idx[q];
+                const T ox = self ? o.x + T(1) : o.x;
                 T fx, fy;
-                if (SOC == 2 && sym && jj < idx[q]) {
-                    pair_force<T, SOC>(P, o.x, o.y, o.vx, o.vy, rsj, m.px, m.py, m.vx, m.vy, m.rs, fx, fy);
-                    fsx[q] -= fx; fsy[q] -= fy;
+                if (SOC == 2) {
+                    const bool sw = sym && jj < idx[q];
+                    pair_force<T, SOC>(P, exp_tbl_s, sw ? ox : m.px, sw ? o.y : m.py, sw ? o.vx : m.vx, sw ? o.vy : m.vy, sw ? rsj : m.rs,
+                                       sw ? m.px : ox, sw ? m.py : o.y, sw ? m.vx : o.vx, sw ? m.vy : o.vy, sw ? m.rs : rsj, fx, fy);
+                    fx = sw ? -fx : fx; fy = sw ? -fy : fy;
                 } else {
-                    pair_force<T, SOC>(P, m.px, m.py, m.vx, m.vy, m.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
-                    fsx[q] += fx; fsy[q] += fy;
+                    pair_force<T, SOC>(P, exp_tbl_s, m.px, m.py, m.vx, m.vy, m.rs, ox, o.y, o.vx, o.vy, rsj, fx, fy);
                 }
+                fsx[q] += self ? T(0) : fx; fsy[q] += self ? T(0) : fy;
             }
         }
     }
@@ -113,7 +125,7 @@ __global__ void __launch_bounds__(kTile) k_large_step(const LargeArgs<T> la) {
             m.gx = a.goals[((size_t)gidx[q] * 2 + 0) * N + i]; m.gy = a.goals[((size_t)gidx[q] * 2 + 1) * N + i];
         }
         T fox = T(0), foy = T(0);
-        if (a.W > 0) obstacle_force<T, OBS>(P, segs, a.W, a.S, a.numba != 0, m.px, m.py, m.vx, m.vy, m.rs, fox, foy);
+        if (a.W > 0) obstacle_force<T, OBS>(P, exp_tbl_s, segs, seg_cnt, a.W, a.S, a.numba != 0, m.px, m.py, m.vx, m.vy, m.rs, fox, foy);
         desired_force<T>(P, m, a.numba != 0);
         integrate<T, HEADED>(P, m, fox, foy, fsx[q], fsy[q], a.dt);
         a.dyn[SNP_DYN_PX * N + i] = m.px; a.dyn[SNP_DYN_PY * N + i] = m.py;
@@ -152,7 +164,7 @@ template <typename T> __global__ void k_large_publish(const T *dyn, const T *sta
 template <typename T, int SOC, int OBS, int HEADED> int launch_large(const LargeArgs<T> &la, cudaStream_t st) {
     const long long N = la.k.EN;
     const int nseg = la.k.W * la.k.S;
-    const size_t smem = ((sizeof(Seg<T>) * (size_t)nseg + 31) & ~size_t(31)) + sizeof(Ent<T>) * kTile + sizeof(T) * kTile;
+    const size_t smem = 512 + ((sizeof(Seg<T>) * (size_t)nseg + 31) & ~size_t(31)) + sizeof(Ent<T>) * kTile + sizeof(T) * kTile + sizeof(int) * (la.k.W + 1) + 16;
     const long long per_block = (long long)kTile * kAgentsPerThread;
     const unsigned blocks = (unsigned)((N + per_block - 1) / per_block);
     auto kern = k_large_step<T, SOC, OBS, HEADED>;

@@ -20,6 +20,24 @@ namespace {
 constexpr int kWarpsPerBlock = 4;
 constexpr int kSlotsPerWarp = 64;  // >= epw * (N + 1) for every N <= 32
 
+// Byte offsets of the dynamic shared-memory regions (same arithmetic on host and device).
+template <typename T> struct SmemLayout {
+    size_t segs, seg_cnt, ents, rs, red, total;
+    int slots;
+    __host__ __device__ SmemLayout(int nseg, int seg_groups, int W, int slots_, int red_doubles) : slots(slots_) {
+        size_t off = sizeof(T) == 8 ? 64 * sizeof(double) : 0;  // exp table (fp64 only)
+        segs = off; off += sizeof(Seg<T>) * (size_t)nseg * seg_groups;
+        off = (off + 15) & ~size_t(15);
+        seg_cnt = off; off += sizeof(int) * (size_t)(W > 0 ? W : 1) * seg_groups;
+        off = (off + 31) & ~size_t(31);
+        ents = off; off += sizeof(Ent<T>) * (size_t)slots * 2;
+        rs = off; off += sizeof(T) * (size_t)slots;
+        off = (off + 15) & ~size_t(15);
+        red = off; off += sizeof(double) * (size_t)red_doubles;
+        total = off + 16;
+    }
+};
+
 // ---- checks (double arithmetic, formula-exact; see snp_math.cuh) ----
 
 // utils.py:22-36 point_to_segment_dist(x1, y1, x2, y2, 0, 0) with (x1,y1) = d, (x2,y2) = e.
@@ -61,7 +79,7 @@ __device__ __forceinline__ double seg_min(double v, int i, int n, unsigned mask)
 }
 
 template <typename T, int SOC, int OBS, int HEADED, bool CTA, bool PER_AGENT>
-__global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32) k_step(const KArgs<T> a) {
+__global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (sizeof(T) == 4 ? 8 : 4)) k_step(const KArgs<T> a) {
     using R = Real<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -86,20 +104,19 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32) k_step(const 
     const int M = N + (a.consider_robot ? 1 : 0);  // entities exerting force
     const int groups = CTA ? 1 : kWarpsPerBlock * a.epw;
 
-    // ---- shared memory carve-up ----
+    // ---- shared memory carve-up: [exp table][segments][segment counts][entities x2][r+safety][reduction scratch] ----
     const int nseg = a.W * a.S;
-    Seg<T> *segs_all = reinterpret_cast<Seg<T> *>(smem_raw);
     const int seg_groups = a.walls_per_env ? groups : 1;
-    size_t off = sizeof(Seg<T>) * (size_t)nseg * seg_groups;
-    off = (off + 31) & ~size_t(31);
-    const int slots = CTA ? (N + 1) : kWarpsPerBlock * kSlotsPerWarp;
-    Ent<T> *ents0 = reinterpret_cast<Ent<T> *>(smem_raw + off);
-    off += sizeof(Ent<T>) * (size_t)slots * 2;
-    T *rs_all = reinterpret_cast<T *>(smem_raw + off);
-    off += sizeof(T) * (size_t)slots;
-    off = (off + 7) & ~size_t(7);
-    double *red = reinterpret_cast<double *>(smem_raw + off);  // CTA mode only: [N] doubles
+    const SmemLayout<T> lay(nseg, seg_groups, a.W, CTA ? (N + 1) : kWarpsPerBlock * kSlotsPerWarp, CTA ? N : 0);
+    double *exp_tbl_s = reinterpret_cast<double *>(smem_raw);
+    Seg<T> *segs_all = reinterpret_cast<Seg<T> *>(smem_raw + lay.segs);
+    int *seg_cnt_all = reinterpret_cast<int *>(smem_raw + lay.seg_cnt);
+    const int slots = lay.slots;
+    Ent<T> *ents0 = reinterpret_cast<Ent<T> *>(smem_raw + lay.ents);
+    T *rs_all = reinterpret_cast<T *>(smem_raw + lay.rs);
+    double *red = reinterpret_cast<double *>(smem_raw + lay.red);  // CTA mode only: [N] doubles
 
+    if (sizeof(T) == 8) exp_table_init(exp_tbl_s);
     // walls -> shared memory (whole block cooperates, before anyone leaves)
     if (nseg > 0) {
         const int total = nseg * seg_groups;
@@ -113,12 +130,20 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32) k_step(const 
             const T *w = a.walls + ((size_t)wenv * nseg + s) * 4;
             segs_all[k] = make_seg<T>(w[0], w[1], w[2], w[3]);
         }
+        __syncthreads();
+        // valid slots per polygon: NaN padding is a suffix of each polygon's slots (motion_model_manager.py:270-275)
+        for (int k = threadIdx.x; k < a.W * seg_groups; k += blockDim.x) {
+            int c = 0;
+            while (c < a.S && segs_all[(size_t)k * a.S + c].ax == segs_all[(size_t)k * a.S + c].ax) ++c;
+            seg_cnt_all[k] = c;
+        }
     }
     __syncthreads();
     if constexpr (!CTA) { if (!live) return; }
 
     const int gslot = CTA ? 0 : ((threadIdx.x >> 5) * kSlotsPerWarp + (g - (threadIdx.x >> 5) * a.epw) * (N + 1));
     const Seg<T> *segs = segs_all + (a.walls_per_env ? (size_t)g * nseg : 0);
+    const int *seg_cnt = seg_cnt_all + (a.walls_per_env ? g * a.W : 0);
     T *rs_g = rs_all + gslot;
     const bool leader = live && i == 0;
     const bool has_robot = a.robot != nullptr;
@@ -234,25 +259,30 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32) k_step(const 
             }
             // wall force
             T fox = T(0), foy = T(0);
-            if (a.W > 0) obstacle_force<T, OBS>(P, segs, a.W, a.S, a.numba != 0, me.px, me.py, me.vx, me.vy, me.rs, fox, foy);
+            if (a.W > 0) obstacle_force<T, OBS>(P, exp_tbl_s, segs, seg_cnt, a.W, a.S, a.numba != 0, me.px, me.py, me.vx, me.vy, me.rs, fox, foy);
             // social force: j ascending, exactly the accumulation order of forces.py:145-151
             T fsx = T(0), fsy = T(0);
             const bool sym = a.symmetric != 0;
+            // Branch-free body (the self pair is evaluated on a shifted copy and masked out) so that consecutive pairs
+            // interleave in the pipes instead of serialising on divergence barriers.
 #pragma unroll 2
             for (int j = 0; j < M; ++j) {
-                if (j == i) continue;
                 const Ent<T> o = ents[j];
                 const T rsj = rs_g[j];
+                const bool self = j == i;
+                const T ox = self ? o.x + T(1) : o.x;
                 T fx, fy;
-                if (SOC == 2 && sym && j < i) {
+                if (SOC == 2) {
                     // symmetric path: the pair is evaluated once with the LOWER index as agent 1 and applied with a minus
                     // sign to the other (forces.py:149-151); only Moussaid's sign(theta) makes that differ from f(i,j).
-                    pair_force<T, SOC>(P, o.x, o.y, o.vx, o.vy, rsj, me.px, me.py, me.vx, me.vy, me.rs, fx, fy);
-                    fsx -= fx; fsy -= fy;
+                    const bool sw = sym && j < i;
+                    pair_force<T, SOC>(P, exp_tbl_s, sw ? ox : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
+                                       sw ? me.px : ox, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
+                    fx = sw ? -fx : fx; fy = sw ? -fy : fy;
                 } else {
-                    pair_force<T, SOC>(P, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
-                    fsx += fx; fsy += fy;
+                    pair_force<T, SOC>(P, exp_tbl_s, me.px, me.py, me.vx, me.vy, me.rs, ox, o.y, o.vx, o.vy, rsj, fx, fy);
                 }
+                fsx += self ? T(0) : fx; fsy += self ? T(0) : fy;
             }
             desired_force<T>(P, me, a.numba != 0);
             integrate<T, HEADED>(P, me, fox, foy, fsx, fsy, dt);
@@ -334,17 +364,12 @@ int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
         const int epb = a.epw * kWarpsPerBlock;
         grid = dim3((unsigned)((a.E + epb - 1) / epb));
         block = dim3(kWarpsPerBlock * 32);
-        const int slots = kWarpsPerBlock * kSlotsPerWarp;
-        size_t off = sizeof(Seg<T>) * (size_t)nseg * (a.walls_per_env ? epb : 1);
-        off = (off + 31) & ~size_t(31);
-        smem = off + sizeof(Ent<T>) * slots * 2 + sizeof(T) * slots + 64;
+        smem = SmemLayout<T>(nseg, a.walls_per_env ? epb : 1, a.W, kWarpsPerBlock * kSlotsPerWarp, 0).total;
     } else {
         a.epw = 1;
         grid = dim3((unsigned)a.E);
         block = dim3((unsigned)((a.N + 31) / 32 * 32));
-        size_t off = sizeof(Seg<T>) * (size_t)nseg;
-        off = (off + 31) & ~size_t(31);
-        smem = off + sizeof(Ent<T>) * (a.N + 1) * 2 + sizeof(T) * (a.N + 1) + 16 + sizeof(double) * a.N;
+        smem = SmemLayout<T>(nseg, 1, a.W, a.N + 1, a.N).total;
     }
     if (smem > 200 * 1024) { set_error("wall/segment tables need %zu bytes of shared memory (limit 200 KiB)", smem); return SNP_ERR_UNSUPPORTED; }
 #define SNP_LAUNCH(CTA_, PA_)                                                                                          \
