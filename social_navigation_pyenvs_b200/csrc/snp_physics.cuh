@@ -34,7 +34,7 @@ __device__ __forceinline__ void pair_force(const Params<T> &P, const double *tbl
                                            T vy2, T rs2, T &fx, T &fy) {
     using R = Real<T>;
     const T dx = x1 - x2, dy = y1 - y2;
-    const T d2 = np_sq(dx, dy);
+    const T d2 = np_sq(dx, dy) + tiny_<T>();  // self pair: n = (0,0) -> zero force, no branch (see tiny_)
     const T inv = R::rsqrt_(d2);
     const T dist = d2 * inv;
     const T nx = dx * inv, ny = dy * inv;
@@ -51,7 +51,7 @@ __device__ __forceinline__ void pair_force(const Params<T> &P, const double *tbl
     } else {
         const T ivx = fma_<T>(P.lambda, vx1 - vx2, -nx);
         const T ivy = fma_<T>(P.lambda, vy1 - vy2, -ny);
-        const T i2 = np_sq(ivx, ivy);
+        const T i2 = np_sq(ivx, ivy) + tiny_<T>();
         const T iinv = R::rsqrt_(i2);
         const T inorm = i2 * iinv;
         const T ix = ivx * iinv, iy = ivy * iinv;

@@ -97,18 +97,16 @@ __global__ void __launch_bounds__(kTile) k_large_step(const LargeArgs<T> la) {
 #pragma unroll
             for (int q = 0; q < kAgentsPerThread; ++q) {
                 Agent<T> &m = me[q];
-                const bool self = jj == idx[q];
-                const T ox = self ? o.x + T(1) : o.x;
-                T fx, fy;
+                T fx, fy;  // the self pair (jj == idx[q]) contributes exactly zero by construction (tiny_ in pair_force)
                 if (SOC == 2) {
                     const bool sw = sym && jj < idx[q];
-                    pair_force<T, SOC>(P, exp_tbl_s, sw ? ox : m.px, sw ? o.y : m.py, sw ? o.vx : m.vx, sw ? o.vy : m.vy, sw ? rsj : m.rs,
-                                       sw ? m.px : ox, sw ? m.py : o.y, sw ? m.vx : o.vx, sw ? m.vy : o.vy, sw ? m.rs : rsj, fx, fy);
+                    pair_force<T, SOC>(P, exp_tbl_s, sw ? o.x : m.px, sw ? o.y : m.py, sw ? o.vx : m.vx, sw ? o.vy : m.vy, sw ? rsj : m.rs,
+                                       sw ? m.px : o.x, sw ? m.py : o.y, sw ? m.vx : o.vx, sw ? m.vy : o.vy, sw ? m.rs : rsj, fx, fy);
                     fx = sw ? -fx : fx; fy = sw ? -fy : fy;
                 } else {
-                    pair_force<T, SOC>(P, exp_tbl_s, m.px, m.py, m.vx, m.vy, m.rs, ox, o.y, o.vx, o.vy, rsj, fx, fy);
+                    pair_force<T, SOC>(P, exp_tbl_s, m.px, m.py, m.vx, m.vy, m.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
                 }
-                fsx[q] += self ? T(0) : fx; fsy[q] += self ? T(0) : fy;
+                fsx[q] += fx; fsy[q] += fy;
             }
         }
     }

@@ -263,26 +263,24 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             // social force: j ascending, exactly the accumulation order of forces.py:145-151
             T fsx = T(0), fsy = T(0);
             const bool sym = a.symmetric != 0;
-            // Branch-free body (the self pair is evaluated on a shifted copy and masked out) so that consecutive pairs
-            // interleave in the pipes instead of serialising on divergence barriers.
+            // Branch-free body: the self pair contributes an exactly zero force by construction (tiny_ in pair_force), so
+            // consecutive pairs interleave in the pipes instead of serialising on divergence barriers.
 #pragma unroll 2
             for (int j = 0; j < M; ++j) {
                 const Ent<T> o = ents[j];
                 const T rsj = rs_g[j];
-                const bool self = j == i;
-                const T ox = self ? o.x + T(1) : o.x;
                 T fx, fy;
                 if (SOC == 2) {
                     // symmetric path: the pair is evaluated once with the LOWER index as agent 1 and applied with a minus
                     // sign to the other (forces.py:149-151); only Moussaid's sign(theta) makes that differ from f(i,j).
                     const bool sw = sym && j < i;
-                    pair_force<T, SOC>(P, exp_tbl_s, sw ? ox : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
-                                       sw ? me.px : ox, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
+                    pair_force<T, SOC>(P, exp_tbl_s, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
+                                       sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
                     fx = sw ? -fx : fx; fy = sw ? -fy : fy;
                 } else {
-                    pair_force<T, SOC>(P, exp_tbl_s, me.px, me.py, me.vx, me.vy, me.rs, ox, o.y, o.vx, o.vy, rsj, fx, fy);
+                    pair_force<T, SOC>(P, exp_tbl_s, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
                 }
-                fsx += self ? T(0) : fx; fsy += self ? T(0) : fy;
+                fsx += fx; fsy += fy;
             }
             desired_force<T>(P, me, a.numba != 0);
             integrate<T, HEADED>(P, me, fox, foy, fsx, fsy, dt);

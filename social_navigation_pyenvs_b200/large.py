@@ -1,0 +1,60 @@
+"""One very large crowd (tens of thousands of humans in ONE environment), optionally sharded by agent across GPUs.
+
+Every rank owns a contiguous slice of agents and evaluates their forces against ALL agents (ordered pairs: the reference's
+symmetric accumulation, forces.py:148, is not carried across ranks).  The only exchange per sub-step is an all-gather of the
+entity view (x, y, vx, vy, r+safety) over NCCL / NVLink; it is double buffered so the step kernel writes the next view's own
+slice while reading the current one.  Reference semantics: motion_model_manager.py:354-373 for a single env.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import CrowdEngine, SFMS
+from .parallel import all_gather_columns, agent_shard
+
+
+class LargeCrowd:
+    def __init__(self, model, states, goals, walls=None, dtype=torch.float64, device="cuda", symmetric=True, numba_compat=False,
+                 rank=0, world=1, group=None, safety=None):
+        """states [N_total,13], goals [N_total,G,2] (the WHOLE crowd on every rank; each rank keeps its slice)."""
+        states = np.asarray(states, np.float64)
+        goals = np.asarray(goals, np.float64)
+        self.n_total = states.shape[0]
+        self.rank, self.world, self.group = rank, world, group
+        self.offset, self.n_local = agent_shard(self.n_total, rank, world)
+        sl = slice(self.offset, self.offset + self.n_local)
+        saf = None if safety is None else np.asarray(safety, np.float64)[None, sl]
+        self.eng = CrowdEngine.from_reference_arrays(model, states[None, sl], goals[None, sl], walls=walls, safety=saf, consider_robot=False,
+                                                     all_params_equal=symmetric, numba_compat=numba_compat, dtype=dtype, device=device)
+        self.type = SFMS.index(model)
+        self.view = [torch.zeros((5, self.n_total), dtype=dtype, device=self.eng.device) for _ in range(2)]
+        self.cur = 0
+        self._publish()
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _gather(self, buf):
+        all_gather_columns(buf, self.offset, self.n_local, self.world, self.group)
+
+    def _publish(self):
+        v = self.view[self.cur]
+        L.check(self.eng.lib.snp_large_publish(ctypes.byref(self.eng._crowd()), self.type, ctypes.c_void_p(v.data_ptr()), self.n_total,
+                                               self.offset, self._stream()))
+        self._gather(v)
+
+    def step(self, dt=0.0125, n_substeps=1):
+        c = self.eng._crowd()
+        o = self.eng._opts(dt, 1)
+        for _ in range(n_substeps):
+            cur, nxt = self.view[self.cur], self.view[self.cur ^ 1]
+            L.check(self.eng.lib.snp_large_step(ctypes.byref(c), ctypes.byref(o), ctypes.c_void_p(cur.data_ptr()), self.n_total, self.offset,
+                                                ctypes.c_void_p(nxt.data_ptr()), self._stream()))
+            self._gather(nxt)
+            self.cur ^= 1
+
+    def local_rows(self, template):
+        """This rank's agents as reference rows; `template` [n_local,13] supplies the static columns."""
+        return self.eng.rows(np.asarray(template, np.float64)[None])[0]

@@ -1,0 +1,119 @@
+"""LaserSensor: host-side mirror of social_gym/src/sensors.py backed by the ray-cast kernel (csrc/snp_laser.cu).
+
+Same constructor, `update_pose` and `get_laser_measurements` as the reference class for ONE sensor
+(sensors.py:10-22,53-69), plus `scan_batch` for E sensors at once (arrays in, arrays out) and device-resident scans through
+`CrowdEngine`-owned tensors (`scan_engine`).
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _walls_array(walls):
+    """Accepts the reference's wall objects (anything with a `.segments` dict, obstacle.py:26-32), a list of vertex lists,
+    or an already packed [W,S,2,2] NaN padded array."""
+    if walls is None:
+        return None
+    if isinstance(walls, np.ndarray):
+        return walls if walls.size and walls.shape[0] else None
+    walls = list(walls)
+    if not walls:
+        return None
+    seg_lists = []
+    for w in walls:
+        if hasattr(w, "segments"):
+            seg_lists.append([[list(s[0]), list(s[1])] for s in w.segments.values()])
+        else:
+            verts = [list(v) for v in w]
+            seg_lists.append([[min(verts[i], verts[(i + 1) % len(verts)]), max(verts[i], verts[(i + 1) % len(verts)])]
+                              for i in range(len(verts))])
+    smax = max(len(s) for s in seg_lists)
+    out = np.full((len(seg_lists), smax, 2, 2), np.nan)
+    for i, segs in enumerate(seg_lists):
+        out[i, : len(segs)] = np.asarray(segs, np.float64)
+    return out
+
+
+def scan_batch(humans, walls, pose, range_, samples, max_distance, robot_radius=0.0, dtype="float64", want_hits=True):
+    """E sensors in one launch.  humans [E,N,3] = x,y,r; walls [W,S,2,2] NaN padded or None; pose [E,3] = x,y,yaw.
+    Returns (ranges [E,samples] float64, hits [E,samples] int32 or None)."""
+    if max_distance > 10:
+        raise ValueError("Maxium distance for laser is 10 meters")  # sensors.py:13
+    humans = np.ascontiguousarray(humans, np.float64)
+    pose = np.ascontiguousarray(pose, np.float64)
+    if np.any(pose[:, 2] > math.pi) or np.any(pose[:, 2] < -math.pi):
+        raise ValueError("Angle passed ust be wrapped between [-pi,pi]")  # sensors.py:20
+    E, N = humans.shape[0], humans.shape[1]
+    w = _walls_array(walls)
+    W, S = (0, 0) if w is None else (w.shape[0], w.shape[1])
+    w = None if w is None else np.ascontiguousarray(w, np.float64)
+    ranges = np.empty((E, samples))
+    hits = np.empty((E, samples), np.int32) if want_hits else None
+    rc = L.lib().snp_laser_host(E, N, _p(humans), _p(w), W, S, _p(pose), float(range_), int(samples), float(max_distance),
+                                float(robot_radius), L.SNP_F64 if dtype in ("float64", np.float64) else L.SNP_F32, _p(ranges), _p(hits))
+    L.check(rc)
+    return ranges, hits
+
+
+class LaserSensor:
+    """social_gym/src/sensors.py:6-74 for one sensor.  `uncertainty` must be None or 0: the Gaussian noise of
+    add_uncertainty (sensors.py:71-74) draws from the caller's global np.random stream and is applied on the host."""
+
+    def __init__(self, init_pos, init_yaw, range, samples, max_distance, uncertainty=None):
+        self.range = range
+        self.samples = samples
+        if max_distance > 10:
+            raise ValueError("Maxium distance for laser is 10 meters")
+        self.max_distance = max_distance
+        self.uncertainty = uncertainty
+        self.update_pose(init_pos, init_yaw)
+
+    def update_pose(self, position, yaw):
+        if yaw > math.pi or yaw < -math.pi:
+            raise ValueError("Angle passed ust be wrapped between [-pi,pi]")
+        self.position = position
+        self.yaw = yaw
+
+    def get_laser_measurements(self, humans, walls):
+        """humans: objects with .position/.radius (HumanAgent) or an [N,3] array; walls: reference wall objects, vertex lists
+        or a packed array.  Returns {angle: range} like the reference."""
+        if isinstance(humans, np.ndarray):
+            h = np.asarray(humans, np.float64).reshape(-1, 3)
+        else:
+            h = np.array([[p.position[0], p.position[1], p.radius] for p in humans], np.float64).reshape(-1, 3)
+        pose = np.array([[self.position[0], self.position[1], self.yaw]], np.float64)
+        ranges, _ = scan_batch(h[None], walls, pose, self.range, self.samples, self.max_distance, want_hits=False)
+        angles = np.linspace(self.yaw - (self.range / 2), self.yaw + (self.range / 2), self.samples)
+        meas = ranges[0]
+        if self.uncertainty:
+            meas = np.array([max(min(np.random.normal(m, self.uncertainty), self.max_distance), 0) for m in meas])
+        return dict(zip(angles, meas))
+
+
+def scan_engine(engine, pose, range_, samples, max_distance, robot_radius=0.0, want_hits=True):
+    """Device-resident scan over a CrowdEngine's humans and walls: pose [3,E] tensor (x,y,yaw) of the engine's dtype.
+    Returns (ranges [E,samples] tensor, hits [E,samples] int32 tensor or None) on the device, no host round trip."""
+    import torch
+    a = L.SnpLaserArgs()
+    a.E, a.N, a.samples = engine.E, engine.N, int(samples)
+    a.dtype = L.SNP_F64 if engine.dtype == torch.float64 else L.SNP_F32
+    a.px, a.py = engine.dyn[L.DYN_PX].data_ptr(), engine.dyn[L.DYN_PY].data_ptr()
+    a.radius = engine.stat[L.STAT_R].data_ptr()
+    a.walls = None if engine.walls is None else engine.walls.data_ptr()
+    a.W, a.S, a.walls_per_env = engine.W, engine.S, engine.walls_per_env
+    pose = pose.to(device=engine.device, dtype=engine.dtype).contiguous()
+    a.pose = pose.data_ptr()
+    a.range, a.max_distance, a.robot_radius = float(range_), float(max_distance), float(robot_radius)
+    ranges = torch.empty((engine.E, samples), dtype=engine.dtype, device=engine.device)
+    hits = torch.empty((engine.E, samples), dtype=torch.int32, device=engine.device) if want_hits else None
+    a.ranges = ranges.data_ptr()
+    a.hits = None if hits is None else hits.data_ptr()
+    L.check(L.lib().snp_laser(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return ranges, hits

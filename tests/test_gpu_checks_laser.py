@@ -1,0 +1,164 @@
+"""GPU parity of the batched collision / goal / reward reductions, the gym-level fused step and the laser kernel, against
+golden vectors recorded from the live reference (tests/golden) and against the CPU oracle.  Flags, info codes, dmin / reward
+values and ray hit indices must be BIT-EXACT (fp64 mode); laser ranges within 1e-12."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import OracleConfig
+from helpers import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+CONSTS = np.array([50, -0.25, 1.0, 0.2, 0.5, 0.25])
+
+
+def _engine(model, states, goals, robot, visible, dtype=torch.float64, walls=None):
+    from social_navigation_pyenvs_b200 import CrowdEngine
+    S = np.concatenate([states, robot[:, None]], 1) if visible else states
+    return CrowdEngine.from_reference_arrays(model, S, goals, walls=walls, consider_robot=visible, all_params_equal=True, dtype=dtype,
+                                             robot=None if visible else robot)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_flags_bit_exact_vs_reference_golden(dtype):
+    """400 recorded (state, action) cases: swept collision + dmin + goal (sim:949-984), reward/terminated/truncated/info
+    (sim:986-1029), actual collision/dmin/goal (gym:107-118) -- all envs in one launch."""
+    z = np.load(os.path.join(GOLDEN, "flags.npz"))
+    H, R, A, ref = z["humans"], z["robot"], z["action"], z["result"]
+    if dtype == torch.float32:  # identical inputs: fp32-representable values on both sides, flags computed in double from them
+        H, R, A = (x.astype(np.float32).astype(np.float64) for x in (H, R, A))
+        ref = oracle.checks(H, H.shape[1], R, A, ref[:, 11], CONSTS)
+        ref = np.concatenate([ref[:, :11], z["result"][:, 11:12]], 1)
+    goals = np.repeat(H[:, :, None, 10:12], 2, axis=2)
+    eng = _engine("hsfm_farina", H, goals, R, visible=False, dtype=dtype)
+    eng.time_now.copy_(torch.as_tensor(ref[:, 11]))
+    out = eng.run_checks(A, pre=True, post=True)
+    assert np.array_equal(out["collision"], ref[:, 0] != 0)
+    assert np.array_equal(out["reaching_goal"], ref[:, 2] != 0)
+    assert np.array_equal(out["terminated"], ref[:, 4] != 0) and np.array_equal(out["truncated"], ref[:, 5] != 0)
+    assert np.array_equal(out["info"], ref[:, 6].astype(int))
+    assert np.array_equal(out["actual_collision"], ref[:, 7] != 0) and np.array_equal(out["actual_goal"], ref[:, 9] != 0)
+    assert np.array_equal(out["dmin"], ref[:, 1]) and np.array_equal(out["reward"], ref[:, 3]) and np.array_equal(out["actual_dmin"], ref[:, 8])
+    assert out["collision"].sum() > 50 and (out["info"] == 4).sum() > 20
+
+
+def test_gym_step_sequence_vs_reference_golden():
+    """SocialNavGym.step recorded for 60 steps (gym:227-250): terminated / truncated / info identical, observation (px,py,vx,vy)
+    and reward within 1e-9, robot position exact -- pre-checks + 20 fused sub-steps + robot motion in ONE launch per step.
+    (The discomfort reward is a function of dmin of a state the GPU has integrated for k*20 sub-steps, so it carries that
+    state's 1e-15 rounding differences; bit-exactness on IDENTICAL inputs is test_flags_bit_exact_vs_reference_golden.)"""
+    z = np.load(os.path.join(GOLDEN, "gym_step.npz"))
+    from social_navigation_pyenvs_b200 import SFMS
+    for key in ["hsfm_farina_0", "sfm_helbing_1", "hsfm_new_guo_1"]:
+        visible = key.endswith("_1")
+        eng = _engine(SFMS[int(z[key + "_type"])], z[key + "_states0"][None], z[key + "_goals0"][None], z[key + "_robot0"][None], visible)
+        for k, a in enumerate(z[key + "_actions"]):
+            eng.step(a[None], 0.0125, n_substeps=20, pre_checks=True)
+            r = eng.decode_flags()
+            ref = z[key + "_result"][k]
+            assert r["terminated"][0] == bool(ref[1]) and r["truncated"][0] == bool(ref[2]) and r["info"][0] == int(ref[3]), (key, k)
+            assert abs(r["reward"][0] - ref[0]) <= 1e-9, (key, k)
+            obs = eng.get_human_states(include_goal=False, headed=False)[0]
+            assert rel_err(obs, z[key + "_obs"][k][:, :4]).max() < 1e-9, (key, k)
+            assert rel_err(eng.robot[:2, 0].cpu().numpy(), z[key + "_robot_pos"][k]).max() < 1e-13
+        assert abs(float(eng.time_now[0]) - 15.0) < 1e-9
+
+
+def test_fused_post_checks_and_touch_match_oracle_4096_envs():
+    """Full-size batch (4096 x 25 + robot + walls): flags produced inside the fused launch equal the oracle's checks applied to
+    the oracle's own pre-state / the kernel's own post-state (identical inputs -> bit-exact)."""
+    from social_navigation_pyenvs_b200 import scenarios
+    E, N, k, dt = 4096, 25, 20, 0.0125
+    sc = scenarios.ccso_synthetic(E, N, seed0=7000)
+    rng = np.random.RandomState(1)
+    sc["robot"][:, 0:2] = sc["states"][np.arange(E), rng.randint(3, N, E), 0:2] + rng.uniform(-1.2, 1.2, (E, 2))  # robot near a human
+    walls = scenarios.pack_walls(scenarios.EXAMPLE_WALLS)
+    action = rng.uniform(-1, 1, (E, 2))
+    eng = _engine("hsfm_farina", sc["states"], sc["goals"], sc["robot"], visible=True, walls=walls)
+    states = np.concatenate([sc["states"], sc["robot"][:, None]], 1)
+    pre = oracle.checks(states, N, sc["robot"], action, np.zeros(E), CONSTS)
+    eng.step(action, dt, n_substeps=k, pre_checks=True, post_checks=True, track_touch=True)
+    r = eng.decode_flags()
+    assert np.array_equal(r["collision"], pre[:, 0] != 0) and np.array_equal(r["dmin"], pre[:, 1]) and np.array_equal(r["reward"], pre[:, 3])
+    assert np.array_equal(r["info"], pre[:, 6].astype(int))
+    post_rows = eng.rows(states)
+    rob = sc["robot"].copy()
+    rob[:, 0:2] = eng.robot[:2].cpu().numpy().T
+    post = oracle.checks(post_rows, N, rob, action, np.zeros(E), CONSTS)
+    assert np.array_equal(r["actual_collision"], post[:, 7] != 0) and np.array_equal(r["actual_dmin"], post[:, 8])
+    assert r["collision"].sum() > 100 and r["actual_collision"].sum() > 10
+    # touched (any sub-step) is implied by a post-step overlap
+    assert np.all(r["touched"][post[:, 10] != 0])
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_laser_vs_reference_golden(dtype):
+    from social_navigation_pyenvs_b200 import sensors
+    z = np.load(os.path.join(GOLDEN, "laser.npz"))
+    keys = sorted(k[:-5] for k in z.files if k.endswith("_pose"))
+    for key in keys:
+        x, y, yaw, rng, samples, maxd = z[key + "_pose"]
+        ranges, hits = sensors.scan_batch(z[key + "_humans"][None], z[key + "_walls"], np.array([[x, y, yaw]]), rng, int(samples), maxd, dtype=dtype)
+        if dtype == "float64":
+            assert np.array_equal(hits[0], z[key + "_hits"]), key
+            assert np.abs(ranges[0] - z[key + "_ranges"]).max() <= 1e-12, key
+        else:  # fp32: ranges to 1e-4 relative wherever both agree on hit/miss; grazing rays may flip
+            same = hits[0] == z[key + "_hits"]
+            assert same.mean() > 0.97, (key, same.mean())
+            assert (np.abs(ranges[0] - z[key + "_ranges"])[same] <= 1e-4 * np.maximum(z[key + "_ranges"][same], 1)).all(), key
+
+
+def test_laser_class_matches_reference_dict():
+    from social_navigation_pyenvs_b200.sensors import LaserSensor
+    z = np.load(os.path.join(GOLDEN, "laser.npz"))
+    x, y, yaw, rng, samples, maxd = z["dense_0_pose"]
+    s = LaserSensor(np.array([x, y]), yaw, rng, int(samples), maxd, uncertainty=None)
+    m = s.get_laser_measurements(z["dense_0_humans"], z["dense_0_walls"])
+    assert np.array_equal(np.array(list(m.keys())), z["dense_0_angles"])
+    assert np.abs(np.array(list(m.values())) - z["dense_0_ranges"]).max() <= 1e-12
+    with pytest.raises(ValueError):
+        LaserSensor(np.zeros(2), 4.0, rng, 10, 10.0)
+    with pytest.raises(ValueError):
+        LaserSensor(np.zeros(2), 0.0, rng, 10, 11.0)
+
+
+def test_laser_4096_envs_360_rays_vs_oracle_and_warp_kernel():
+    """BASELINE config 4 at full size: 4096 envs x 360 rays over 25 humans + 14 wall segments; hit indices bit-exact vs the
+    oracle; the warp-per-ray kernel (used for large crowds) must agree with the thread-per-ray kernel."""
+    from social_navigation_pyenvs_b200 import scenarios, sensors
+    E, N = 4096, 25
+    sc = scenarios.ccso_synthetic(E, N, seed0=2000)
+    humans = sc["states"][:, :, [0, 1, 8]]
+    walls = scenarios.pack_walls(scenarios.EXAMPLE_WALLS)
+    pose = np.concatenate([sc["robot"][:, 0:2], np.full((E, 1), np.pi / 2)], 1)
+    ranges, hits = sensors.scan_batch(humans, walls, pose, 2 * np.pi, 360, 10.0)
+    r_ref, h_ref = oracle.laser(humans[:256], walls, pose[:256], 2 * np.pi, 360, 10.0)
+    # ranges: CUDA's sincos and glibc's differ in the last ulp of the ray direction -> 1e-13 relative on a 10 m range
+    assert np.array_equal(hits[:256], h_ref) and np.abs(ranges[:256] - r_ref).max() <= 1e-11
+    assert (hits >= 0).mean() > 0.2
+    # one crowd of 600 circles -> warp-per-ray path; compare with the oracle
+    big = np.concatenate([humans[:24].reshape(1, -1, 3)], 1)
+    big[0, :, 0:2] += np.repeat(np.arange(24)[:, None] * 0.37, N, 0)
+    r2, h2 = sensors.scan_batch(big, walls, pose[:1], 2 * np.pi, 720, 10.0)
+    r2_ref, h2_ref = oracle.laser(big, walls, pose[:1], 2 * np.pi, 720, 10.0)
+    assert np.array_equal(h2, h2_ref) and np.abs(r2 - r2_ref).max() <= 1e-11
+
+
+def test_peek_next_observable_states_vs_reference_golden():
+    """get_next_human_observable_states (mmm:691-709): dt=0.25 peek, pose/velocity/goal restored, desired force not."""
+    from social_navigation_pyenvs_b200 import CrowdEngine
+    z = np.load(os.path.join(GOLDEN, "peek.npz"))
+    for model in ["sfm_helbing", "hsfm_farina", "hsfm_new_guo"]:
+        S = np.concatenate([z[model + "_states"], z[model + "_robot"][None]], 0)[None]
+        eng = CrowdEngine.from_reference_arrays(model, S, z[model + "_goals"][None], consider_robot=True, all_params_equal=True)
+        eng.set_desired_force(z[model + "_desired"][None])
+        before = eng.get_human_states(include_goal=True, headed=eng.headed)
+        obs4 = eng.get_next_human_observable_states(0.25)
+        assert rel_err(obs4[0], z[model + "_obs4"]).max() < 1e-9
+        assert np.array_equal(eng.get_human_states(include_goal=True, headed=eng.headed), before)
+        obs8 = eng.get_next_human_observable_states(0.25, theta_and_omega_visible=True)
+        assert rel_err(obs8[0], z[model + "_obs8"]).max() < 1e-9
+        assert rel_err(eng.desired_force()[0], z[model + "_after"][:, 10:12], scale=100.0).max() < 1e-9
