@@ -61,6 +61,7 @@ template <typename T> static int build_args(const snp_crowd *c, const snp_step_o
     for (int k = 0; k < 6; ++k) a.consts[k] = o->consts[k];
     a.time_now = o->time_now; a.flags = o->flags; a.checks = o->checks;
     a.epw = 1;
+    a.full_pair_loop = o->reserved & 1;  // bit 0 of `reserved`: SNP_OPT_FULL_PAIR_LOOP
     return SNP_OK;
 }
 
@@ -103,12 +104,8 @@ int snp_step(const snp_crowd *crowd, const snp_step_opts *opts, void *stream) {
 int snp_checks(const snp_crowd *crowd, const snp_step_opts *opts, void *stream) {
     if (!opts) { set_error("null opts"); return SNP_ERR_INVALID; }
     snp_step_opts o = *opts;
-    o.n_substeps = 0;  // the fused kernel with an empty sub-step loop is exactly the checks
+    o.n_substeps = 0;  // the fused kernel with an empty sub-step loop is exactly the checks (time is read, not advanced)
     o.robot_mode = 0;
-    o.time_now = nullptr;
-    if (opts->time_now && !opts->pre_checks) { /* nothing to read */ }
-    // the reward needs the time but must not advance it: hand the kernel a read through `consts`-free path
-    o.time_now = opts->time_now;
     return snp_step(crowd, &o, stream);
 }
 

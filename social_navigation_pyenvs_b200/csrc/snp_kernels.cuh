@@ -31,6 +31,7 @@ template <typename T> struct KArgs {
     int *flags;
     double *checks;
     int epw;  // envs per warp (warp-packed kernel)
+    int full_pair_loop;  // 1: always evaluate ordered pairs in j-ascending order (the reference's accumulation order)
 };
 
 // Host-side launchers implemented per translation unit.

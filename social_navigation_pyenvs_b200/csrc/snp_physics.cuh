@@ -85,18 +85,19 @@ template <typename T> __device__ __forceinline__ Seg<T> make_seg(T ax, T ay, T b
 // then taken by the caller instead of one per segment).  Padding slots (ax = NaN) sit at the end of each polygon's slots
 // (motion_model_manager.py:270-275) and `cnt` excludes them.
 template <typename T>
-__device__ __forceinline__ void closest_point(const Seg<T> *segs, int cnt, T px, T py, bool first_wins, T &cx, T &cy) {
-    T best = first_wins ? Real<T>::inf() : T(1.0e8);
-    cx = T(0); cy = T(0);
+__device__ __forceinline__ void closest_point(const Seg<T> *segs, int cnt, T px, T py, bool first_wins, T &dxb, T &dyb, T &best) {
+    best = first_wins ? Real<T>::inf() : T(1.0e8);
+    dxb = px; dyb = py;  // closest point (0,0) when no segment qualifies (obstacle.py:55)
     for (int s = 0; s < cnt; ++s) {
         const Seg<T> g = segs[s];
-        T t = np_dot(px - g.ax, py - g.ay, g.ex, g.ey) * g.inv_len2;
-        t = t > T(0) ? t : T(0);
+        const T qx = px - g.ax, qy = py - g.ay;
+        T t = np_dot(qx, qy, g.ex, g.ey) * g.inv_len2;
+        t = max0(t);
         t = t < T(1) ? t : T(1);
-        const T hx = fma_<T>(t, g.ex, g.ax), hy = fma_<T>(t, g.ey, g.ay);
-        const T d = np_sq(hx - px, hy - py);
+        const T ux = fma_<T>(-t, g.ex, qx), uy = fma_<T>(-t, g.ey, qy);  // p - h,  h = a + t e
+        const T d = np_sq(ux, uy);
         const bool take = first_wins ? (d < best) : (d <= best);
-        best = take ? d : best; cx = take ? hx : cx; cy = take ? hy : cy;
+        best = take ? d : best; dxb = take ? ux : dxb; dyb = take ? uy : dyb;
     }
 }
 
@@ -107,10 +108,9 @@ __device__ __forceinline__ void obstacle_force(const Params<T> &P, const double 
     using R = Real<T>;
     fx = T(0); fy = T(0);
     for (int w = 0; w < W; ++w) {
-        T cx, cy;
-        closest_point<T>(segs + w * S, seg_cnt[w], px, py, numba, cx, cy);
-        const T dx = px - cx, dy = py - cy;
-        const T d2 = np_sq(dx, dy);
+        T dx, dy, d2;
+        closest_point<T>(segs + w * S, seg_cnt[w], px, py, numba, dx, dy, d2);
+        d2 = np_sq(dx, dy) + tiny_<T>();
         const T inv = R::rsqrt_(d2);
         const T dist = d2 * inv;
         const T nx = dx * inv, ny = dy * inv;
@@ -131,13 +131,24 @@ __device__ __forceinline__ void obstacle_force(const Params<T> &P, const double 
 template <typename T> struct Agent {
     T px, py, vx, vy, th, bvx, bvy, om, dfx, dfy;  // dynamic
     T r, m, vd, rs;                                // static (rs = r + safety)
+    T inv_m, mr, inertia, inv_inertia;             // static derived: 1/m, m/relax_t, 0.5 m r^2 (agent.py:30) and its inverse
     T gx, gy;                                      // current goal
     T cs, sn;                                      // cos/sin(th) (headed models)
 };
 
+template <typename T> __device__ __forceinline__ void agent_static(const Params<T> &P, Agent<T> &a) {
+    a.inv_m = Real<T>::rcp_(a.m);
+    a.mr = a.m * P.inv_relax;
+    a.inertia = T(0.5) * a.m * a.r * a.r;
+    a.inv_inertia = Real<T>::rcp_(a.inertia);
+}
+
 template <typename T> __device__ __forceinline__ void clip_speed(T &vx, T &vy, T lim) {  // mmm:52-55
-    const T n = np_norm(vx, vy);
-    if (n > lim) { const T s = lim * Real<T>::rcp_(n); vx *= s; vy *= s; }
+    const T n2 = np_sq(vx, vy);
+    if (n2 > lim * lim) {  // |v| > vd  (vd >= 0; the squares compare identically up to one rounding of vd^2)
+        const T s = lim * Real<T>::rsqrt_(n2 + tiny_<T>());
+        vx *= s; vy *= s;
+    }
 }
 
 // Desired force (forces.py:9-16): refreshed only outside the goal radius; inside, the serial path keeps the previous
@@ -148,9 +159,8 @@ template <typename T> __device__ __forceinline__ void desired_force(const Params
     const T dist = Real<T>::sqrt_(d2);
     if (dist > a.r) {
         const T inv = Real<T>::rcp_(dist);
-        const T mr = a.m * P.inv_relax;
-        a.dfx = mr * fma_<T>(dx * inv, a.vd, -a.vx);
-        a.dfy = mr * fma_<T>(dy * inv, a.vd, -a.vy);
+        a.dfx = a.mr * fma_<T>(dx * inv, a.vd, -a.vx);
+        a.dfy = a.mr * fma_<T>(dy * inv, a.vd, -a.vy);
     } else if (numba) {
         a.dfx = T(0); a.dfy = T(0);
     }
@@ -161,7 +171,7 @@ template <typename T> __device__ __forceinline__ void desired_force(const Params
 template <typename T, int HEADED>
 __device__ __forceinline__ void integrate(const Params<T> &P, Agent<T> &a, T fox, T foy, T fsx, T fsy, T dt) {
     using R = Real<T>;
-    const T inv_m = R::rcp_(a.m);
+    const T inv_m = a.inv_m;
     if (HEADED == 0) {
         const T gx = a.dfx + fox + fsx, gy = a.dfy + foy + fsy;
         a.px = fma_<T>(a.vx, dt, a.px); a.py = fma_<T>(a.vy, dt, a.py);
@@ -170,7 +180,7 @@ __device__ __forceinline__ void integrate(const Params<T> &P, Agent<T> &a, T fox
     } else {
         const T sx = a.dfx + fox + fsx, sy = a.dfy + foy + fsy;
         const T tfx = HEADED == 1 ? a.dfx : sx, tfy = HEADED == 1 ? a.dfy : sy;
-        const T inertia = T(0.5) * a.m * a.r * a.r;  // agent.py:30
+        const T inertia = a.inertia;
         const T fn = np_norm(tfx, tfy);
         const T k_theta = inertia * P.k_lambda * fn;
         const T k_omega = inertia * P.alpha1 * R::sqrt_(P.k_lambda * fn * P.inv_alpha);
@@ -180,7 +190,7 @@ __device__ __forceinline__ void integrate(const Params<T> &P, Agent<T> &a, T fox
         a.px = fma_<T>(a.vx, dt, a.px); a.py = fma_<T>(a.vy, dt, a.py);
         a.th = bound_angle<T>(fma_<T>(a.om, dt, a.th));
         a.bvx = fma_<T>(g0 * inv_m, dt, a.bvx); a.bvy = fma_<T>(g1 * inv_m, dt, a.bvy);
-        a.om = fma_<T>(tq * R::rcp_(inertia), dt, a.om);
+        a.om = fma_<T>(tq * a.inv_inertia, dt, a.om);
         clip_speed(a.bvx, a.bvy, a.vd);
         R::sincos_(a.th, &a.sn, &a.cs);
         a.vx = np_mv(a.cs, -a.sn, a.bvx, a.bvy);

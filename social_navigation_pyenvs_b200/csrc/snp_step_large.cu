@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(kTile) k_large_step(const LargeArgs<T> la) {
         } else { m.th = m.bvx = m.bvy = m.om = T(0); m.cs = T(1); m.sn = T(0); }
         m.r = a.stat[SNP_STAT_R * N + i]; m.m = a.stat[SNP_STAT_M * N + i]; m.vd = a.stat[SNP_STAT_VD * N + i];
         m.rs = m.r + a.stat[SNP_STAT_SAFETY * N + i];
+        agent_static<T>(P, m);
         gidx[q] = a.goal_idx[i]; gcnt[q] = a.goal_cnt[i];
         m.gx = a.goals[((size_t)gidx[q] * 2 + 0) * N + i]; m.gy = a.goals[((size_t)gidx[q] * 2 + 1) * N + i];
         fsx[q] = T(0); fsy[q] = T(0);
@@ -183,7 +184,7 @@ template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, 
     a.walls = (const T *)c->walls; a.W = c->W; a.S = c->W > 0 ? c->S : 0; a.walls_per_env = 0;
     a.consider_robot = 0; a.symmetric = o->symmetric; a.numba = o->numba_compat; a.n_substeps = 1; a.robot_mode = 0;
     a.dt = (T)o->dt; a.dt_d = o->dt; a.action = nullptr; a.pre_checks = a.post_checks = a.track_touch = 0;
-    a.time_now = nullptr; a.flags = nullptr; a.checks = nullptr; a.epw = 1;
+    a.time_now = nullptr; a.flags = nullptr; a.checks = nullptr; a.epw = 1; a.full_pair_loop = 1;
     la.others = (const T *)others; la.M = M; la.self_offset = self_offset; la.next_view = (T *)next_view;
     switch (o->type) {
         case 0: return launch_large<T, 0, 0, 0>(la, st);

@@ -78,7 +78,57 @@ __device__ __forceinline__ double seg_min(double v, int i, int n, unsigned mask)
     return v;
 }
 
-template <typename T, int SOC, int OBS, int HEADED, bool CTA, bool PER_AGENT>
+// Social force of one human with every pair of humans evaluated ONCE per warp (newton's third law): in round k lane i
+// evaluates the pair {i, (i+k) mod N}, keeps +f and hands -f to the partner's lane through a warp shuffle, so a crowd of N
+// needs (N-1)/2 evaluations per lane instead of N-1 (for even N the antipodal pair is evaluated by both ends).  Valid when the
+// law is antisymmetric: uniform parameters, and for Moussaid the reference's symmetric path (lower index is agent 1,
+// forces.py:145-151).  Accumulation order differs from the reference's j-ascending order (rounding-level effect only).
+template <typename T, int SOC>
+__device__ __forceinline__ void social_force_halved(const Params<T> &P, const double *tbl, const Ent<T> *ents, const T *rs_g, const Agent<T> &me,
+                                                    int i, int N, bool with_robot, unsigned wmask, int gbase, T &fsx, T &fsy) {
+    int p = i, q = i;
+    const int rounds = (N - 1) >> 1;
+    for (int k = 1; k <= rounds; ++k) {
+        p = (p + 1 == N) ? 0 : p + 1;  // partner (i + k) mod N
+        q = (q == 0) ? N - 1 : q - 1;  // the lane whose partner in this round is me: (i - k) mod N
+        const Ent<T> o = ents[p];
+        const T rsj = rs_g[p];
+        T fx, fy;
+        if (SOC == 2) {
+            const bool sw = p < i;  // the lower index is agent 1
+            pair_force<T, SOC>(P, tbl, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
+                               sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
+            fx = sw ? -fx : fx; fy = sw ? -fy : fy;
+        } else {
+            pair_force<T, SOC>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+        }
+        const T rx = __shfl_sync(wmask, fx, gbase + q), ry = __shfl_sync(wmask, fy, gbase + q);
+        fsx += fx - rx; fsy += fy - ry;
+    }
+    if (!(N & 1)) {  // antipodal pair: both ends evaluate it
+        p = (p + 1 == N) ? 0 : p + 1;
+        const Ent<T> o = ents[p];
+        const T rsj = rs_g[p];
+        T fx, fy;
+        if (SOC == 2) {
+            const bool sw = p < i;
+            pair_force<T, SOC>(P, tbl, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
+                               sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
+            fx = sw ? -fx : fx; fy = sw ? -fy : fy;
+        } else {
+            pair_force<T, SOC>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+        }
+        fsx += fx; fsy += fy;
+    }
+    if (with_robot) {  // the robot exerts force but feels none (forces.py:146,151)
+        const Ent<T> o = ents[N];
+        T fx, fy;
+        pair_force<T, SOC>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rs_g[N], fx, fy);
+        fsx += fx; fsy += fy;
+    }
+}
+
+template <typename T, int SOC, int OBS, int HEADED, bool CTA, bool PER_AGENT, bool HALF>
 __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (sizeof(T) == 4 ? 8 : 4)) k_step(const KArgs<T> a) {
     using R = Real<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -174,6 +224,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             for (int k = 0; k < 20; ++k) p[k] = (double)a.agent_params[(size_t)k * EN + aidx];
             P = make_params<T>(p);
         }
+        agent_static<T>(P, me);
         rs_g[i] = me.rs;
     } else {
         me = Agent<T>{};
@@ -260,27 +311,30 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             // wall force
             T fox = T(0), foy = T(0);
             if (a.W > 0) obstacle_force<T, OBS>(P, exp_tbl_s, segs, seg_cnt, a.W, a.S, a.numba != 0, me.px, me.py, me.vx, me.vy, me.rs, fox, foy);
-            // social force: j ascending, exactly the accumulation order of forces.py:145-151
             T fsx = T(0), fsy = T(0);
-            const bool sym = a.symmetric != 0;
-            // Branch-free body: the self pair contributes an exactly zero force by construction (tiny_ in pair_force), so
-            // consecutive pairs interleave in the pipes instead of serialising on divergence barriers.
+            if constexpr (HALF) {
+                social_force_halved<T, SOC>(P, exp_tbl_s, ents, rs_g, me, i, N, a.consider_robot != 0, wmask, lane - i, fsx, fsy);
+            } else {
+                // j ascending: exactly the accumulation order of forces.py:145-151.  Branch-free body: the self pair contributes
+                // an exactly zero force by construction (tiny_ in pair_force), so consecutive pairs interleave in the pipes.
+                const bool sym = a.symmetric != 0;
 #pragma unroll 2
-            for (int j = 0; j < M; ++j) {
-                const Ent<T> o = ents[j];
-                const T rsj = rs_g[j];
-                T fx, fy;
-                if (SOC == 2) {
-                    // symmetric path: the pair is evaluated once with the LOWER index as agent 1 and applied with a minus
-                    // sign to the other (forces.py:149-151); only Moussaid's sign(theta) makes that differ from f(i,j).
-                    const bool sw = sym && j < i;
-                    pair_force<T, SOC>(P, exp_tbl_s, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
-                                       sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
-                    fx = sw ? -fx : fx; fy = sw ? -fy : fy;
-                } else {
-                    pair_force<T, SOC>(P, exp_tbl_s, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+                for (int j = 0; j < M; ++j) {
+                    const Ent<T> o = ents[j];
+                    const T rsj = rs_g[j];
+                    T fx, fy;
+                    if (SOC == 2) {
+                        // symmetric path: the pair is evaluated once with the LOWER index as agent 1 and applied with a minus
+                        // sign to the other (forces.py:149-151); only Moussaid's sign(theta) makes that differ from f(i,j).
+                        const bool sw = sym && j < i;
+                        pair_force<T, SOC>(P, exp_tbl_s, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
+                                           sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
+                        fx = sw ? -fx : fx; fy = sw ? -fy : fy;
+                    } else {
+                        pair_force<T, SOC>(P, exp_tbl_s, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+                    }
+                    fsx += fx; fsy += fy;
                 }
-                fsx += fx; fsy += fy;
             }
             desired_force<T>(P, me, a.numba != 0);
             integrate<T, HEADED>(P, me, fox, foy, fsx, fsy, dt);
@@ -370,14 +424,18 @@ int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
         smem = SmemLayout<T>(nseg, 1, a.W, a.N + 1, a.N).total;
     }
     if (smem > 200 * 1024) { set_error("wall/segment tables need %zu bytes of shared memory (limit 200 KiB)", smem); return SNP_ERR_UNSUPPORTED; }
-#define SNP_LAUNCH(CTA_, PA_)                                                                                          \
+#define SNP_LAUNCH(CTA_, PA_, HALF_)                                                                                   \
     do {                                                                                                               \
-        auto kern = k_step<T, SOC, OBS, HEADED, CTA_, PA_>;                                                            \
+        auto kern = k_step<T, SOC, OBS, HEADED, CTA_, PA_, HALF_>;                                                     \
         if (smem > 48 * 1024) SNP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, block, smem, st>>>(a);                                                                            \
     } while (0)
-    if (cta) { if (per_agent) SNP_LAUNCH(true, true); else SNP_LAUNCH(true, false); }
-    else { if (per_agent) SNP_LAUNCH(false, true); else SNP_LAUNCH(false, false); }
+    // pairs evaluated once per warp whenever the law is antisymmetric (see social_force_halved)
+    const bool half = !cta && !per_agent && !a.full_pair_loop && (SOC != 2 || a.symmetric);
+    if (cta) { if (per_agent) SNP_LAUNCH(true, true, false); else SNP_LAUNCH(true, false, false); }
+    else if (per_agent) SNP_LAUNCH(false, true, false);
+    else if (half) SNP_LAUNCH(false, false, true);
+    else SNP_LAUNCH(false, false, false);
 #undef SNP_LAUNCH
     count_launch();
     SNP_CUDA_OK(cudaGetLastError());

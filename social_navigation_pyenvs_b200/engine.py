@@ -53,7 +53,7 @@ def _stream():
 
 class CrowdEngine:
     def __init__(self, model, E, N, G=2, dtype=torch.float64, device="cuda", consider_robot=False, symmetric=True,
-                 numba_compat=False, params=None, walls=None, has_robot=True):
+                 numba_compat=False, params=None, walls=None, has_robot=True, full_pair_loop=False):
         if model not in SFMS:
             raise Exception(f"The human motion model '{model}' does not exist")
         if dtype not in (torch.float32, torch.float64):
@@ -65,6 +65,9 @@ class CrowdEngine:
         self.E, self.N, self.G = int(E), int(N), int(G)
         self.dtype, self.device = dtype, torch.device(device)
         self.consider_robot, self.symmetric, self.numba_compat = bool(consider_robot), bool(symmetric), bool(numba_compat)
+        # False (default): every unordered pair is evaluated once per warp (Newton's third law); True: every ordered pair in
+        # j-ascending order, the reference's own accumulation order (forces.py:145-151).  Same result up to rounding.
+        self.full_pair_loop = bool(full_pair_loop)
         self.params = model_parameters(model) if params is None else np.asarray(params, np.float64).reshape(20)
         kw = dict(dtype=dtype, device=self.device)
         self.dyn = torch.zeros((L.DYN_FIELDS, E, N), **kw)
@@ -88,7 +91,8 @@ class CrowdEngine:
     # ------------------------------------------------------------------ construction from reference arrays
     @classmethod
     def from_reference_arrays(cls, model, states, goals, walls=None, params=None, safety=None, consider_robot=False,
-                              all_params_equal=True, numba_compat=False, dtype=torch.float64, device="cuda", robot=None):
+                              all_params_equal=True, numba_compat=False, dtype=torch.float64, device="cuda", robot=None,
+                              full_pair_loop=False):
         """states [E,rows,13] float64 rows (agent.py:256; rows = N + consider_robot), goals [E,N,G,2] NaN padded,
         walls [W,S,2,2] or [E,W,S,2,2] NaN padded, params [20] / [E,N,20], safety [E,rows], robot [E,13] (when the robot is
         not a row of `states` but checks are wanted)."""
@@ -110,7 +114,8 @@ class CrowdEngine:
                 else:
                     p_rows = params.reshape(E, N, 20)
         eng = cls(model, E, N, G, dtype=dtype, device=device, consider_robot=consider_robot, symmetric=all_params_equal,
-                  numba_compat=numba_compat, params=p_uniform, walls=walls, has_robot=consider_robot or robot is not None)
+                  numba_compat=numba_compat, params=p_uniform, walls=walls, has_robot=consider_robot or robot is not None,
+                  full_pair_loop=full_pair_loop)
         if p_rows is not None:
             eng.agent_params = torch.as_tensor(np.ascontiguousarray(p_rows.transpose(2, 0, 1)), dtype=dtype, device=eng.device)
         eng.load_rows(states, safety)
@@ -139,6 +144,7 @@ class CrowdEngine:
         o.n_substeps, o.robot_mode, o.dt = int(n_substeps), int(robot_mode), float(dt)
         o.action = self.action.data_ptr()
         o.pre_checks, o.post_checks, o.track_touch = int(pre_checks), int(post_checks), int(track_touch)
+        o.reserved = 1 if self.full_pair_loop else 0
         o.consts = (ctypes.c_double * 6)(*self.consts)
         o.time_now = self.time_now.data_ptr() if (advance_time or pre_checks) else None
         o.flags, o.checks = self.flags.data_ptr(), self.checks.data_ptr()

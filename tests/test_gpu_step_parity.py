@@ -87,6 +87,29 @@ def test_fused_substeps_match_stepwise_oracle(name):
         assert rel_err(eng.robot[:2, 0].cpu().numpy(), S2[0, n, 0:2]).max() < 1e-14
 
 
+@pytest.mark.parametrize("name", ["cc25_robot_hsfm_new_guo", "ccso8_sfm_moussaid", "walls7eq_hsfm_new_moussaid", "cc6_robot_sfm_guo", "jym_sfm_helbing"])
+def test_halved_and_full_pair_loops_agree(name):
+    """The default path evaluates each unordered pair once per warp; full_pair_loop=True replays the reference's j-ascending
+    ordered-pair loop.  Both must sit within 1e-9 of the recorded reference and within 1e-12 of each other (moving crowd)."""
+    from social_navigation_pyenvs_b200 import CrowdEngine, SFMS
+    d = load_traj(name)
+    n = d["n"]
+    k = consecutive_pairs(d)[-1]
+    S, G, D, rv = inputs_at(d, k)
+    if d["consider_robot"]:
+        S[n, 0:2] = S[n, 0:2] + rv * float(d["dt"]); S[n, 3:5] = rv
+    out = []
+    for full in (False, True):
+        eng = CrowdEngine.from_reference_arrays(SFMS[int(d["type"])], S[None], G[None], walls=d["walls"], params=d["params"][None],
+                                                safety=d["safety"][None, : S.shape[0]], consider_robot=d["consider_robot"],
+                                                all_params_equal=d["all_equal"], full_pair_loop=full)
+        eng.set_desired_force(D[None])
+        eng.update_humans(0.0, float(d["dt"]))
+        out.append(observed(eng.rows(S[None])[0], eng.desired_force()[0], n))
+        assert rel_err(out[-1][:, :10], d["traj"][k + 1][:, :10]).max() < 1e-9
+    assert rel_err(out[0][:, :10], out[1][:, :10]).max() < 1e-12
+
+
 def test_numba_semantics_operator():
     """update_humans_parallel(..., semantics='numba') reproduces the reference's Numba operator outputs (fp:184)."""
     import os
