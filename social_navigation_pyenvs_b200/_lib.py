@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsnp_b200.so")
+LIB_PATH = os.environ.get("SNP_B200_LIB", os.path.join(_HERE, "libsnp_b200.so"))  # override: tuning experiments only
 
 SNP_F32, SNP_F64 = 0, 1
 # field order of the SoA buffers (include/snp_b200.h)

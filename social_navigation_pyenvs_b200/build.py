@@ -30,9 +30,9 @@ def _deps_mtime():
     return max(os.path.getmtime(f) for f in files)
 
 
-def _compile(src, verbose):
-    obj = os.path.join(OBJ, src[:-3] + ".o")
-    cmd = ["nvcc", *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+def _compile(src, verbose, extra=(), obj_dir=OBJ):
+    obj = os.path.join(obj_dir, src[:-3] + ".o")
+    cmd = ["nvcc", *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -57,6 +57,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB
+
+
+def build_variant(tag: str, defines) -> str:
+    """Tuning experiments: a second library built with extra -D flags into variants/<tag>/ (select with SNP_B200_LIB)."""
+    out_dir = os.path.join(PKG, "variants", tag)
+    os.makedirs(out_dir, exist_ok=True)
+    extra = [f"-D{d}" for d in defines]
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
+        objs = [o for o, _ in ex.map(lambda s: _compile(s, False, extra, out_dir), _sources())]
+    lib = os.path.join(out_dir, "libsnp_b200.so")
+    subprocess.run(["nvcc", "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"], check=True)
+    return lib
 
 
 if __name__ == "__main__":

@@ -155,10 +155,10 @@ template <typename T> __device__ __forceinline__ void clip_speed(T &vx, T &vy, T
 // value (stale) while the Numba path returns zero (fp:34-40).
 template <typename T> __device__ __forceinline__ void desired_force(const Params<T> &P, Agent<T> &a, bool numba) {
     const T dx = a.gx - a.px, dy = a.gy - a.py;
-    const T d2 = np_sq(dx, dy);
-    const T dist = Real<T>::sqrt_(d2);
+    const T d2 = np_sq(dx, dy) + tiny_<T>();
+    const T inv = Real<T>::rsqrt_(d2);
+    const T dist = d2 * inv;
     if (dist > a.r) {
-        const T inv = Real<T>::rcp_(dist);
         a.dfx = a.mr * fma_<T>(dx * inv, a.vd, -a.vx);
         a.dfy = a.mr * fma_<T>(dy * inv, a.vd, -a.vy);
     } else if (numba) {

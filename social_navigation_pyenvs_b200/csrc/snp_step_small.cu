@@ -17,6 +17,15 @@ namespace snp {
 
 namespace {
 
+// Resident CTAs per SM the compiler must allow for (register cap = 65536 / (128 threads * min blocks)); tuned on B200, see
+// profiles/.  Overridable at build time for experiments.
+#ifndef SNP_MINB_F32
+#define SNP_MINB_F32 5
+#endif
+#ifndef SNP_MINB_F64
+#define SNP_MINB_F64 4
+#endif
+
 constexpr int kWarpsPerBlock = 4;
 constexpr int kSlotsPerWarp = 64;  // >= epw * (N + 1) for every N <= 32
 
@@ -129,7 +138,7 @@ __device__ __forceinline__ void social_force_halved(const Params<T> &P, const do
 }
 
 template <typename T, int SOC, int OBS, int HEADED, bool CTA, bool PER_AGENT, bool HALF>
-__global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (sizeof(T) == 4 ? 8 : 4)) k_step(const KArgs<T> a) {
+__global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (sizeof(T) == 4 ? SNP_MINB_F32 : SNP_MINB_F64)) k_step(const KArgs<T> a) {
     using R = Real<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
