@@ -32,6 +32,8 @@ WORKLOADS = {
     "4096x25_hsfm_ccso_walls_robot": ("hsfm_farina", 4096, 25, True, True),
     "4096x25_hsfm_ccso_robot": ("hsfm_farina", 4096, 25, False, True),
     "4096x5_sfm_helbing_cc": ("sfm_helbing", 4096, 5, False, False),
+    # BASELINE configs[4]: ONE crowd of 65536 humans, sharded by agent across the GPUs (strong scaling, all-gather per sub-step)
+    "65536_hsfm_single_crowd": ("hsfm_farina", 1, 65536, False, False),
 }
 
 
@@ -156,6 +158,93 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def run_large_crowd(args, rank, world, local_rank):
+    """Config 5: one 65536-human HSFM crowd (256 x 256 jittered grid); a step = ONE sub-step = one tiled
+    all-pairs launch per rank + one all-gather of the [5, N] entity view.  Total work is fixed -> strong scaling."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from social_navigation_pyenvs_b200 import scenarios, _lib
+    from social_navigation_pyenvs_b200.large import LargeCrowd
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.lib()
+    tdtype = torch.float64 if args.dtype == "f64" else torch.float32
+    sc = scenarios.jittered_grid_crowd(256, pitch=2.0, jitter=0.5, seed=0)
+    n = sc["states"].shape[1]
+    crowd = LargeCrowd("hsfm_farina", sc["states"][0], sc["goals"][0], dtype=tdtype, rank=rank, world=world)
+    steps = min(args.steps, 50)
+    for _ in range(args.warmup):
+        crowd.step(DT, 1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    stream = torch.cuda.current_stream()
+    lib.snp_launch_count(1)
+    with ClockSampler(local_rank) as clocks:
+        for s in range(steps):
+            flush.fill_(s & 0xFF)
+            ev[s][0].record(stream)
+            crowd.step(DT, 1)
+            ev[s][1].record(stream)
+        torch.cuda.synchronize()
+    launches = int(lib.snp_launch_count(0))
+    from social_navigation_pyenvs_b200.parallel import max_over_ranks
+    total_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), "cuda", world)
+    # the same steps with the exact far-tile culling switched off: every ordered pair is evaluated -> the all-pairs roofline
+    crowd.culling = False
+    crowd.step(DT, 1)
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(max(3, steps // 3))]
+    for a_, b_ in ev2:
+        flush.fill_(1)
+        a_.record(stream)
+        crowd.step(DT, 1)
+        b_.record(stream)
+    torch.cuda.synchronize()
+    allpairs_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev2), "cuda", world) / len(ev2)
+    crowd.culling = True
+    # end to end: host rows in, host rows out around one sub-step of the whole crowd (public API of LargeCrowd)
+    tmpl = sc["states"][0][crowd.offset:crowd.offset + crowd.n_local]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        crowd.eng.load_rows(tmpl[None])
+        crowd._publish()
+        crowd.step(DT, 1)
+        crowd.local_rows(tmpl)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, "cuda", world)
+    if rank == 0:
+        pipe = ctypes.c_double()
+        _lib.check(lib.snp_measure_pipe_peak(1 if args.dtype == "f64" else 0, ctypes.byref(pipe)))
+        flops = n * ((n - 1) * 31 + 150)  # SURVEY 8(d): 65535 ordered pairs x 31 + 150 per agent-step
+        per_s = allpairs_ms * 1e-3
+        ach = flops / per_s / 1e12
+        line = {"metric": METRIC, "value": n * steps / (total_ms * 1e-3), "unit": "agent-steps/s", "n_gpus": world, "steps": steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": args.workload, "humans": n, "model": "hsfm_farina", "substeps_per_step": 1, "dt": DT,
+                           "sharding": f"by agent over {world} GPU(s), all-gather of the [5,N] entity view per sub-step",
+                           "culling": "exact far-tile culling on for `value` (tiles beyond the exp-underflow distance contribute exactly 0); "
+                                      "roofline measured with culling off (every ordered pair evaluated)",
+                           "ms_per_step_all_pairs": allpairs_ms,
+                           "l2": "256 MiB flush write between timed steps"},
+                "clocks": clocks.summary(), "gpu_launches": launches,
+                "e2e": {"value": n * reps / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": int(tmpl.size * 8), "d2h_bytes_per_step": int(tmpl.size * 8),
+                        "api": "LargeCrowd: load_rows (H2D) + step + local_rows (D2H)", "steps": reps},
+                "roofline": {"bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": ach * world / world, "peak": pipe.value * world, "unit": "TFLOP/s",
+                             "frac": ach / (pipe.value * world), "traffic": None, "kernel": "snp::k_large_pairs (tiled all-pairs, culling off)",
+                             "flops_per_agent_substep": (n - 1) * 31 + 150,
+                             "peak_source": "measured in this run on rank 0 (snp_measure_pipe_peak) x n_gpus"}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -175,6 +264,9 @@ def main():
         run_reference(args, rank, world)
         return
 
+    if args.workload == "65536_hsfm_single_crowd":
+        run_large_crowd(args, rank, world, local_rank)
+        return
     # host-side scenario generation forks worker processes: do it before CUDA is initialised in this process
     inp = build_inputs(args.workload, 2000 + rank * 4096)  # every rank owns different envs
     E, N = inp["E"], inp["N"]

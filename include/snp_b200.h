@@ -43,7 +43,7 @@ typedef enum snp_status {
 } snp_status;
 
 enum { SNP_F32 = 0, SNP_F64 = 1 };
-enum { SNP_OPT_FULL_PAIR_LOOP = 1 };
+enum { SNP_OPT_FULL_PAIR_LOOP = 1, SNP_OPT_NO_CULLING = 2 };
 
 /* Field order of the structure-of-arrays buffers (each field is a contiguous run of E*N elements). */
 enum { SNP_DYN_PX = 0, SNP_DYN_PY, SNP_DYN_VX, SNP_DYN_VY, SNP_DYN_TH, SNP_DYN_BVX, SNP_DYN_BVY, SNP_DYN_OM,
@@ -144,9 +144,12 @@ int snp_rotate_goal_rows(const snp_crowd *crowd, double *goal_rows_dev, void *cu
  * `others` = [5][M] x,y,vx,vy,r+safety (SoA) of ALL M entities exerting force -- the crowd itself (gathered over ranks
  * when it is sharded by agent) plus, optionally, the robot as last entry; `self_offset` = index of this crowd's agent 0
  * in that view.  Own state is updated in place; when `next_view` is non-NULL the updated x,y,vx,vy,r+safety of the own
- * agents are also written into it (same [5][M] layout, same offset), ready to be all-gathered for the next sub-step. */
+ * agents are also written into it (same [5][M] layout, same offset), ready to be all-gathered for the next sub-step.
+ * `scratch` = device workspace of at least snp_large_scratch_bytes(n_local, M, dtype) bytes (per-chunk partial sums and tile
+ * boxes).  opts->reserved bit 1 (SNP_OPT_NO_CULLING) disables the exact far-tile culling. */
+int64_t snp_large_scratch_bytes(int64_t n_local, int64_t M, int32_t dtype);
 int snp_large_step(const snp_crowd *crowd, const snp_step_opts *opts, const void *others, int64_t M, int64_t self_offset,
-                   void *next_view, void *cuda_stream);
+                   void *next_view, void *scratch, int64_t scratch_bytes, void *cuda_stream);
 /* Writes this crowd's [5][.] entity view (x,y,vx,vy,r+safety; v = R(yaw) bv for headed models) into `view` (field stride
  * `stride` elements, starting at element `offset`). */
 int snp_large_publish(const snp_crowd *crowd, int32_t type, void *view, int64_t stride, int64_t offset, void *cuda_stream);

@@ -1,40 +1,157 @@
-// snp_step_large.cu -- one very large crowd: shared-memory tiled all-pairs (N-body style) social force + the same wall /
-// desired / torque / Euler epilogue as the small-crowd kernel, one sub-step per launch.
+// snp_step_large.cu -- one very large crowd: shared-memory tiled all-pairs (N-body style) social force, then the same wall /
+// desired / torque / Euler epilogue as the small-crowd kernel.  One sub-step = three launches on one stream:
 //
-// Every agent i of this rank's crowd accumulates the force of ALL M entities of the `others` view
-// ([5][M] = x, y, vx, vy, r+safety in SoA, float4-coalesced tile loads) in ascending j -- the accumulation order of the
-// reference's row-major pair loop (social_gym/src/forces.py:145-151), so the fp64 result matches the oracle to rounding.
-// The new (x, y, vx, vy) of the own agents is written straight into `next_view` (double-buffered by the host), which is
-// what the other ranks all-gather when the crowd is sharded by agent; own state is updated in place.
-// Reference: same as snp_step_small.cu (motion_model_manager.py:354-373,424-459; forces.py).
+//   k_tile_boxes   bounding box (+ max r+safety) of every 128-entity tile of the `others` view  [5][M] = x, y, vx, vy, r+s
+//   k_large_pairs  grid (i-blocks of 256 agents, j-chunks of 4096 entities): every agent accumulates the force of the
+//                  chunk's entities in ascending j from shared-memory tiles and writes ONE partial sum per chunk.
+//                  A tile is skipped when its box is farther from the i-block's box than the distance at which the pair
+//                  law is identically zero in the arithmetic in use (exp underflow: r_i+s_i+r_j+s_j + 700 B in fp64,
+//                  + 88 B in fp32 with ex2.approx.ftz) -- an EXACT optimisation, the summed force is unchanged.
+//   k_large_finish per agent: partial sums added in ascending chunk order (fixed, so the result does not depend on how the
+//                  crowd is sharded over GPUs), goal switch, wall force, desired force, torque, Euler; writes the state in
+//                  place and the agent's entry of the NEXT entity view (what the other ranks all-gather).
+//
+// The chunking gives (N/256) x (M/4096) CTAs -- 4096 at 65536 humans on one GPU, 512 per GPU at 8 GPUs -- instead of N/256.
+// Reference: same as snp_step_small.cu (motion_model_manager.py:354-373,424-459; forces.py:63-151).
 #include "snp_kernels.cuh"
 
 namespace snp {
 namespace {
 
-constexpr int kTile = 128;      // entities per shared-memory tile == threads per block
-constexpr int kAgentsPerThread = 2;
+constexpr int kTile = 128;           // entities per shared-memory tile == threads per block
+constexpr int kAgentsPerThread = 2;  // register tiling: every staged entity is used for two agents
+constexpr int kChunk = 4096;         // entities per j-chunk (one partial sum each); fixed so results are sharding-independent
 
 template <typename T> struct LargeArgs {
     KArgs<T> k;
     const T *others;
     long long M, self_offset;
     T *next_view;
+    T *partial;   // [J][2][N_local]
+    T *boxes;     // [n_tiles][5] xmin, xmax, ymin, ymax, max(r+s)
+    int J, n_tiles;
+    T cull_margin;  // distance beyond r+s sums at which the pair law is exactly zero; < 0 disables culling
 };
 
-template <typename T, int SOC, int OBS, int HEADED>
-__global__ void __launch_bounds__(kTile) k_large_step(const LargeArgs<T> la) {
+template <typename T> __device__ __forceinline__ T warp_min(T v) {
+    for (int o = 16; o > 0; o >>= 1) { const T w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
+    return v;
+}
+template <typename T> __device__ __forceinline__ T warp_max(T v) {
+    for (int o = 16; o > 0; o >>= 1) { const T w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    return v;
+}
+
+// Block-wide (128 threads) box of per-thread (xmin, xmax, ymin, ymax, rsmax); result broadcast through `sbox`.
+template <typename T> __device__ __forceinline__ void block_box(T xmin, T xmax, T ymin, T ymax, T rs, T *sbox /*[4][5]*/, T *out /*[5]*/) {
+    xmin = warp_min(xmin); xmax = warp_max(xmax); ymin = warp_min(ymin); ymax = warp_max(ymax); rs = warp_max(rs);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sbox[w * 5 + 0] = xmin; sbox[w * 5 + 1] = xmax; sbox[w * 5 + 2] = ymin; sbox[w * 5 + 3] = ymax; sbox[w * 5 + 4] = rs; }
+    __syncthreads();
+    out[0] = min(min(sbox[0], sbox[5]), min(sbox[10], sbox[15]));
+    out[1] = max(max(sbox[1], sbox[6]), max(sbox[11], sbox[16]));
+    out[2] = min(min(sbox[2], sbox[7]), min(sbox[12], sbox[17]));
+    out[3] = max(max(sbox[3], sbox[8]), max(sbox[13], sbox[18]));
+    out[4] = max(max(sbox[4], sbox[9]), max(sbox[14], sbox[19]));
+    __syncthreads();
+}
+
+template <typename T> __global__ void __launch_bounds__(kTile) k_tile_boxes(const T *others, long long M, T *boxes) {
+    __shared__ T sbox[20];
+    const long long j = (long long)blockIdx.x * kTile + threadIdx.x;
+    const bool ok = j < M;
+    const T big = Real<T>::inf();
+    const T x = ok ? others[j] : T(0), y = ok ? others[M + j] : T(0), rs = ok ? others[4 * M + j] : T(0);
+    T out[5];
+    block_box<T>(ok ? x : big, ok ? x : -big, ok ? y : big, ok ? y : -big, rs, sbox, out);
+    if (threadIdx.x < 5) boxes[(size_t)blockIdx.x * 5 + threadIdx.x] = out[threadIdx.x];
+}
+
+template <typename T, int SOC>
+__global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
+    __shared__ __align__(16) unsigned char tile_raw[sizeof(Ent<T>) * kTile];
+    __shared__ T tile_rs[kTile];
+    __shared__ double exp_tbl_s[64];
+    __shared__ T sbox[20];
+    Ent<T> *tile = reinterpret_cast<Ent<T> *>(tile_raw);
+    const KArgs<T> &a = la.k;
+    if (sizeof(T) == 8) exp_table_init(exp_tbl_s);
+
+    const long long N = a.EN, M = la.M;
+    const Params<T> &P = a.P;
+    T mx[kAgentsPerThread], my[kAgentsPerThread], mvx[kAgentsPerThread], mvy[kAgentsPerThread], mrs[kAgentsPerThread];
+    long long idx[kAgentsPerThread];
+    T fsx[kAgentsPerThread], fsy[kAgentsPerThread];
+    const T big = Real<T>::inf();
+    T bx0 = big, bx1 = -big, by0 = big, by1 = -big, brs = T(0);
+#pragma unroll
+    for (int q = 0; q < kAgentsPerThread; ++q) {
+        idx[q] = ((long long)blockIdx.x * kAgentsPerThread + q) * kTile + threadIdx.x;
+        const bool live = idx[q] < N;
+        const long long o = la.self_offset + (live ? idx[q] : 0);
+        mx[q] = la.others[o]; my[q] = la.others[M + o]; mvx[q] = la.others[2 * M + o]; mvy[q] = la.others[3 * M + o]; mrs[q] = la.others[4 * M + o];
+        fsx[q] = T(0); fsy[q] = T(0);
+        if (live) { bx0 = min(bx0, mx[q]); bx1 = max(bx1, mx[q]); by0 = min(by0, my[q]); by1 = max(by1, my[q]); brs = max(brs, mrs[q]); }
+    }
+    T ibox[5];
+    block_box<T>(bx0, bx1, by0, by1, brs, sbox, ibox);
+
+    const bool sym = a.symmetric != 0;
+    const long long j_begin = (long long)blockIdx.y * kChunk;
+    const long long j_end = min(M, j_begin + kChunk);
+    for (long long j0 = j_begin; j0 < j_end; j0 += kTile) {
+        if (la.cull_margin >= T(0)) {  // uniform across the CTA
+            const T *b = la.boxes + (size_t)(j0 / kTile) * 5;
+            const T gx = max(T(0), max(ibox[0] - b[1], b[0] - ibox[1]));
+            const T gy = max(T(0), max(ibox[2] - b[3], b[2] - ibox[3]));
+            const T reach = ibox[4] + b[4] + la.cull_margin;
+            if (fma_<T>(gx, gx, gy * gy) > reach * reach) continue;
+        }
+        __syncthreads();
+        const long long j = j0 + threadIdx.x;
+        if (j < j_end) {
+            tile[threadIdx.x] = Ent<T>{la.others[j], la.others[M + j], la.others[2 * M + j], la.others[3 * M + j]};
+            tile_rs[threadIdx.x] = la.others[4 * M + j];
+        }
+        __syncthreads();
+        const int cnt = (int)min((long long)kTile, j_end - j0);
+#pragma unroll 2
+        for (int t = 0; t < cnt; ++t) {
+            const Ent<T> o = tile[t];
+            const T rsj = tile_rs[t];
+            const long long jj = j0 + t - la.self_offset;  // index of the entity in this crowd's numbering
+#pragma unroll
+            for (int q = 0; q < kAgentsPerThread; ++q) {
+                T fx, fy;  // the self pair (jj == idx[q]) contributes exactly zero by construction (tiny_ in pair_force)
+                if (SOC == 2) {
+                    const bool sw = sym && jj < idx[q];
+                    pair_force<T, SOC>(P, exp_tbl_s, sw ? o.x : mx[q], sw ? o.y : my[q], sw ? o.vx : mvx[q], sw ? o.vy : mvy[q], sw ? rsj : mrs[q],
+                                       sw ? mx[q] : o.x, sw ? my[q] : o.y, sw ? mvx[q] : o.vx, sw ? mvy[q] : o.vy, sw ? mrs[q] : rsj, fx, fy);
+                    fx = sw ? -fx : fx; fy = sw ? -fy : fy;
+                } else {
+                    pair_force<T, SOC>(P, exp_tbl_s, mx[q], my[q], mvx[q], mvy[q], mrs[q], o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+                }
+                fsx[q] += fx; fsy[q] += fy;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kAgentsPerThread; ++q)
+        if (idx[q] < N) {
+            la.partial[((size_t)blockIdx.y * 2 + 0) * N + idx[q]] = fsx[q];
+            la.partial[((size_t)blockIdx.y * 2 + 1) * N + idx[q]] = fsy[q];
+        }
+}
+
+template <typename T, int OBS, int HEADED>
+__global__ void __launch_bounds__(kTile) k_large_finish(const LargeArgs<T> la) {
     using R = Real<T>;
     const KArgs<T> &a = la.k;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nseg = a.W * a.S;
     double *exp_tbl_s = reinterpret_cast<double *>(smem_raw);
     Seg<T> *segs = reinterpret_cast<Seg<T> *>(smem_raw + 512);
-    size_t off = 512 + ((sizeof(Seg<T>) * (size_t)nseg + 31) & ~size_t(31));
-    Ent<T> *tile = reinterpret_cast<Ent<T> *>(smem_raw + off);
-    T *tile_rs = reinterpret_cast<T *>(smem_raw + off + sizeof(Ent<T>) * kTile);
-    int *seg_cnt = reinterpret_cast<int *>(smem_raw + off + sizeof(Ent<T>) * kTile + sizeof(T) * kTile);
-
+    int *seg_cnt = reinterpret_cast<int *>(smem_raw + 512 + ((sizeof(Seg<T>) * (size_t)nseg + 15) & ~size_t(15)));
     if (sizeof(T) == 8) exp_table_init(exp_tbl_s);
     for (int k = threadIdx.x; k < nseg; k += blockDim.x) {
         const T *w = a.walls + (size_t)k * 4;
@@ -46,100 +163,52 @@ __global__ void __launch_bounds__(kTile) k_large_step(const LargeArgs<T> la) {
         while (c < a.S && segs[(size_t)k * a.S + c].ax == segs[(size_t)k * a.S + c].ax) ++c;
         seg_cnt[k] = c;
     }
-
-    const long long N = a.EN;
-    const long long M = la.M;
+    __syncthreads();
+    const long long N = a.EN, M = la.M;
+    const long long i = (long long)blockIdx.x * kTile + threadIdx.x;
+    if (i >= N) return;
     const Params<T> &P = a.P;
-    Agent<T> me[kAgentsPerThread];
-    long long idx[kAgentsPerThread];
-    bool live[kAgentsPerThread];
-    int gidx[kAgentsPerThread], gcnt[kAgentsPerThread];
-    T fsx[kAgentsPerThread], fsy[kAgentsPerThread];
-#pragma unroll
-    for (int q = 0; q < kAgentsPerThread; ++q) {
-        idx[q] = ((long long)blockIdx.x * kAgentsPerThread + q) * kTile + threadIdx.x;
-        live[q] = idx[q] < N;
-        const long long i = live[q] ? idx[q] : 0;
-        Agent<T> &m = me[q];
-        m.px = a.dyn[SNP_DYN_PX * N + i]; m.py = a.dyn[SNP_DYN_PY * N + i];
-        m.vx = a.dyn[SNP_DYN_VX * N + i]; m.vy = a.dyn[SNP_DYN_VY * N + i];
-        m.dfx = a.dyn[SNP_DYN_DFX * N + i]; m.dfy = a.dyn[SNP_DYN_DFY * N + i];
-        if (HEADED) {
-            m.th = a.dyn[SNP_DYN_TH * N + i]; m.bvx = a.dyn[SNP_DYN_BVX * N + i]; m.bvy = a.dyn[SNP_DYN_BVY * N + i];
-            m.om = a.dyn[SNP_DYN_OM * N + i];
-            R::sincos_(m.th, &m.sn, &m.cs);
-            m.vx = np_mv(m.cs, -m.sn, m.bvx, m.bvy);
-            m.vy = np_mv(m.sn, m.cs, m.bvx, m.bvy);
-        } else { m.th = m.bvx = m.bvy = m.om = T(0); m.cs = T(1); m.sn = T(0); }
-        m.r = a.stat[SNP_STAT_R * N + i]; m.m = a.stat[SNP_STAT_M * N + i]; m.vd = a.stat[SNP_STAT_VD * N + i];
-        m.rs = m.r + a.stat[SNP_STAT_SAFETY * N + i];
-        agent_static<T>(P, m);
-        gidx[q] = a.goal_idx[i]; gcnt[q] = a.goal_cnt[i];
-        m.gx = a.goals[((size_t)gidx[q] * 2 + 0) * N + i]; m.gy = a.goals[((size_t)gidx[q] * 2 + 1) * N + i];
-        fsx[q] = T(0); fsy[q] = T(0);
-    }
+    Agent<T> m;
+    m.px = a.dyn[SNP_DYN_PX * N + i]; m.py = a.dyn[SNP_DYN_PY * N + i];
+    m.vx = a.dyn[SNP_DYN_VX * N + i]; m.vy = a.dyn[SNP_DYN_VY * N + i];
+    m.dfx = a.dyn[SNP_DYN_DFX * N + i]; m.dfy = a.dyn[SNP_DYN_DFY * N + i];
+    if (HEADED) {
+        m.th = a.dyn[SNP_DYN_TH * N + i]; m.bvx = a.dyn[SNP_DYN_BVX * N + i]; m.bvy = a.dyn[SNP_DYN_BVY * N + i];
+        m.om = a.dyn[SNP_DYN_OM * N + i];
+        R::sincos_(m.th, &m.sn, &m.cs);
+        m.vx = np_mv(m.cs, -m.sn, m.bvx, m.bvy);  // mmm:448; the same value k_large_publish / the previous step put in the view
+        m.vy = np_mv(m.sn, m.cs, m.bvx, m.bvy);
+    } else { m.th = m.bvx = m.bvy = m.om = T(0); m.cs = T(1); m.sn = T(0); }
+    m.r = a.stat[SNP_STAT_R * N + i]; m.m = a.stat[SNP_STAT_M * N + i]; m.vd = a.stat[SNP_STAT_VD * N + i];
+    m.rs = m.r + a.stat[SNP_STAT_SAFETY * N + i];
+    agent_static<T>(P, m);
+    int gidx = a.goal_idx[i];
+    const int gcnt = a.goal_cnt[i];
+    m.gx = a.goals[((size_t)gidx * 2 + 0) * N + i]; m.gy = a.goals[((size_t)gidx * 2 + 1) * N + i];
+    T fsx = T(0), fsy = T(0);
+    for (int p = 0; p < la.J; ++p) { fsx += la.partial[((size_t)p * 2 + 0) * N + i]; fsy += la.partial[((size_t)p * 2 + 1) * N + i]; }
 
-    // ---- tiled all-pairs ----
-    const bool sym = a.symmetric != 0;
-    for (long long j0 = 0; j0 < M; j0 += kTile) {
-        __syncthreads();
-        const long long j = j0 + threadIdx.x;
-        if (j < M) {
-            tile[threadIdx.x] = Ent<T>{la.others[j], la.others[M + j], la.others[2 * M + j], la.others[3 * M + j]};
-            tile_rs[threadIdx.x] = la.others[4 * M + j];
-        }
-        __syncthreads();
-        const int cnt = (int)min((long long)kTile, M - j0);
-#pragma unroll 4
-        for (int t = 0; t < cnt; ++t) {
-            const Ent<T> o = tile[t];
-            const T rsj = tile_rs[t];
-            const long long jj = j0 + t - la.self_offset;  // index of the entity in this crowd's numbering
-#pragma unroll
-            for (int q = 0; q < kAgentsPerThread; ++q) {
-                Agent<T> &m = me[q];
-                T fx, fy;  // the self pair (jj == idx[q]) contributes exactly zero by construction (tiny_ in pair_force)
-                if (SOC == 2) {
-                    const bool sw = sym && jj < idx[q];
-                    pair_force<T, SOC>(P, exp_tbl_s, sw ? o.x : m.px, sw ? o.y : m.py, sw ? o.vx : m.vx, sw ? o.vy : m.vy, sw ? rsj : m.rs,
-                                       sw ? m.px : o.x, sw ? m.py : o.y, sw ? m.vx : o.vx, sw ? m.vy : o.vy, sw ? m.rs : rsj, fx, fy);
-                    fx = sw ? -fx : fx; fy = sw ? -fy : fy;
-                } else {
-                    pair_force<T, SOC>(P, exp_tbl_s, m.px, m.py, m.vx, m.vy, m.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
-                }
-                fsx[q] += fx; fsy[q] += fy;
-            }
-        }
+    const T dg = np_norm(m.gx - m.px, m.gy - m.py);
+    if (a.numba ? (dg <= m.r) : (dg < m.r)) {
+        gidx = (gidx + 1 >= gcnt) ? 0 : gidx + 1;
+        m.gx = a.goals[((size_t)gidx * 2 + 0) * N + i]; m.gy = a.goals[((size_t)gidx * 2 + 1) * N + i];
     }
-
-    // ---- epilogue per agent ----
-#pragma unroll
-    for (int q = 0; q < kAgentsPerThread; ++q) {
-        if (!live[q]) continue;
-        Agent<T> &m = me[q];
-        const long long i = idx[q];
-        const T dg = np_norm(m.gx - m.px, m.gy - m.py);
-        if (a.numba ? (dg <= m.r) : (dg < m.r)) {
-            gidx[q] = (gidx[q] + 1 >= gcnt[q]) ? 0 : gidx[q] + 1;
-            m.gx = a.goals[((size_t)gidx[q] * 2 + 0) * N + i]; m.gy = a.goals[((size_t)gidx[q] * 2 + 1) * N + i];
-        }
-        T fox = T(0), foy = T(0);
-        if (a.W > 0) obstacle_force<T, OBS>(P, exp_tbl_s, segs, seg_cnt, a.W, a.S, a.numba != 0, m.px, m.py, m.vx, m.vy, m.rs, fox, foy);
-        desired_force<T>(P, m, a.numba != 0);
-        integrate<T, HEADED>(P, m, fox, foy, fsx[q], fsy[q], a.dt);
-        a.dyn[SNP_DYN_PX * N + i] = m.px; a.dyn[SNP_DYN_PY * N + i] = m.py;
-        a.dyn[SNP_DYN_VX * N + i] = m.vx; a.dyn[SNP_DYN_VY * N + i] = m.vy;
-        a.dyn[SNP_DYN_DFX * N + i] = m.dfx; a.dyn[SNP_DYN_DFY * N + i] = m.dfy;
-        if (HEADED) {
-            a.dyn[SNP_DYN_TH * N + i] = m.th; a.dyn[SNP_DYN_BVX * N + i] = m.bvx; a.dyn[SNP_DYN_BVY * N + i] = m.bvy;
-            a.dyn[SNP_DYN_OM * N + i] = m.om;
-        }
-        a.goal_idx[i] = gidx[q];
-        if (la.next_view) {
-            const long long o = la.self_offset + i;
-            la.next_view[o] = m.px; la.next_view[M + o] = m.py; la.next_view[2 * M + o] = m.vx; la.next_view[3 * M + o] = m.vy;
-            la.next_view[4 * M + o] = m.rs;
-        }
+    T fox = T(0), foy = T(0);
+    if (a.W > 0) obstacle_force<T, OBS>(P, exp_tbl_s, segs, seg_cnt, a.W, a.S, a.numba != 0, m.px, m.py, m.vx, m.vy, m.rs, fox, foy);
+    desired_force<T>(P, m, a.numba != 0);
+    integrate<T, HEADED>(P, m, fox, foy, fsx, fsy, a.dt);
+    a.dyn[SNP_DYN_PX * N + i] = m.px; a.dyn[SNP_DYN_PY * N + i] = m.py;
+    a.dyn[SNP_DYN_VX * N + i] = m.vx; a.dyn[SNP_DYN_VY * N + i] = m.vy;
+    a.dyn[SNP_DYN_DFX * N + i] = m.dfx; a.dyn[SNP_DYN_DFY * N + i] = m.dfy;
+    if (HEADED) {
+        a.dyn[SNP_DYN_TH * N + i] = m.th; a.dyn[SNP_DYN_BVX * N + i] = m.bvx; a.dyn[SNP_DYN_BVY * N + i] = m.bvy;
+        a.dyn[SNP_DYN_OM * N + i] = m.om;
+    }
+    a.goal_idx[i] = gidx;
+    if (la.next_view) {
+        const long long o = la.self_offset + i;
+        la.next_view[o] = m.px; la.next_view[M + o] = m.py; la.next_view[2 * M + o] = m.vx; la.next_view[3 * M + o] = m.vy;
+        la.next_view[4 * M + o] = m.rs;
     }
 }
 
@@ -163,19 +232,24 @@ template <typename T> __global__ void k_large_publish(const T *dyn, const T *sta
 template <typename T, int SOC, int OBS, int HEADED> int launch_large(const LargeArgs<T> &la, cudaStream_t st) {
     const long long N = la.k.EN;
     const int nseg = la.k.W * la.k.S;
-    const size_t smem = 512 + ((sizeof(Seg<T>) * (size_t)nseg + 31) & ~size_t(31)) + sizeof(Ent<T>) * kTile + sizeof(T) * kTile + sizeof(int) * (la.k.W + 1) + 16;
+    k_tile_boxes<T><<<(unsigned)la.n_tiles, kTile, 0, st>>>(la.others, la.M, la.boxes);
     const long long per_block = (long long)kTile * kAgentsPerThread;
-    const unsigned blocks = (unsigned)((N + per_block - 1) / per_block);
-    auto kern = k_large_step<T, SOC, OBS, HEADED>;
-    if (smem > 48 * 1024) SNP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<blocks, kTile, smem, st>>>(la);
-    count_launch();
+    dim3 grid((unsigned)((N + per_block - 1) / per_block), (unsigned)la.J);
+    k_large_pairs<T, SOC><<<grid, kTile, 0, st>>>(la);
+    const size_t smem = 512 + ((sizeof(Seg<T>) * (size_t)nseg + 15) & ~size_t(15)) + sizeof(int) * (la.k.W + 1) + 16;
+    auto fin = k_large_finish<T, OBS, HEADED>;
+    if (smem > 48 * 1024) SNP_CUDA_OK(cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fin<<<(unsigned)((N + kTile - 1) / kTile), kTile, smem, st>>>(la);
+    count_launch(3);
     SNP_CUDA_OK(cudaGetLastError());
     return SNP_OK;
 }
 
+inline long long large_J(long long M) { return (M + kChunk - 1) / kChunk; }
+inline long long large_tiles(long long M) { return (M + kTile - 1) / kTile; }
+
 template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, const void *others, long long M, long long self_offset,
-                                    void *next_view, cudaStream_t st) {
+                                    void *next_view, void *scratch, long long scratch_bytes, cudaStream_t st) {
     LargeArgs<T> la;
     KArgs<T> &a = la.k;
     a.E = 1; a.N = 0; a.G = c->G; a.EN = (long long)c->E * c->N;
@@ -186,6 +260,20 @@ template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, 
     a.dt = (T)o->dt; a.dt_d = o->dt; a.action = nullptr; a.pre_checks = a.post_checks = a.track_touch = 0;
     a.time_now = nullptr; a.flags = nullptr; a.checks = nullptr; a.epw = 1; a.full_pair_loop = 1;
     la.others = (const T *)others; la.M = M; la.self_offset = self_offset; la.next_view = (T *)next_view;
+    la.J = (int)large_J(M); la.n_tiles = (int)large_tiles(M);
+    const long long need = (long long)sizeof(T) * ((long long)la.J * 2 * a.EN + (long long)la.n_tiles * 5);
+    if (!scratch || scratch_bytes < need) { set_error("snp_large_step: scratch of %lld bytes needed, %lld given", need, scratch_bytes); return SNP_ERR_INVALID; }
+    la.partial = (T *)scratch;
+    la.boxes = la.partial + (size_t)la.J * 2 * a.EN;
+    // exact culling distance beyond the r+s sums: where exp(rd/B) is identically zero in the arithmetic in use
+    const int soc = o->type % 3;
+    const double under = sizeof(T) == 8 ? 700.0 : 88.0;
+    double margin = -1.0;
+    if (!(o->reserved & 2)) {
+        if (soc == 0 && c->params[3] > 0) margin = under * c->params[3];
+        else if (soc == 1 && c->params[3] > 0 && c->params[7] > 0) margin = under * (c->params[3] > c->params[7] ? c->params[3] : c->params[7]);
+    }
+    la.cull_margin = (T)margin;
     switch (o->type) {
         case 0: return launch_large<T, 0, 0, 0>(la, st);
         case 1: return launch_large<T, 1, 1, 0>(la, st);
@@ -208,16 +296,21 @@ using namespace snp;
 
 extern "C" {
 
+int64_t snp_large_scratch_bytes(int64_t n_local, int64_t M, int32_t dtype) {
+    const long long w = dtype == SNP_F64 ? 8 : 4;
+    return w * (large_J(M) * 2 * n_local + large_tiles(M) * 5) + 64;
+}
+
 int snp_large_step(const snp_crowd *c, const snp_step_opts *o, const void *others, int64_t M, int64_t self_offset, void *next_view,
-                   void *stream) {
+                   void *scratch, int64_t scratch_bytes, void *stream) {
     if (!c || !o || !others) { set_error("snp_large_step: null argument"); return SNP_ERR_INVALID; }
     if (!c->dyn || !c->stat || !c->goals || !c->goal_idx || !c->goal_cnt) { set_error("snp_large_step: crowd arrays missing"); return SNP_ERR_INVALID; }
     if (c->agent_params) { set_error("snp_large_step: per-agent parameter rows are not supported"); return SNP_ERR_UNSUPPORTED; }
     if (c->walls_per_env) { set_error("snp_large_step: one wall set per crowd"); return SNP_ERR_INVALID; }
     const long long N = (long long)c->E * c->N;
     if (M < N || self_offset < 0 || self_offset + N > M + 1) { set_error("snp_large_step: M=%lld offset=%lld N=%lld", (long long)M, (long long)self_offset, N); return SNP_ERR_INVALID; }
-    if (c->dtype == SNP_F64) return run_large<double>(c, o, others, M, self_offset, next_view, (cudaStream_t)stream);
-    if (c->dtype == SNP_F32) return run_large<float>(c, o, others, M, self_offset, next_view, (cudaStream_t)stream);
+    if (c->dtype == SNP_F64) return run_large<double>(c, o, others, M, self_offset, next_view, scratch, scratch_bytes, (cudaStream_t)stream);
+    if (c->dtype == SNP_F32) return run_large<float>(c, o, others, M, self_offset, next_view, scratch, scratch_bytes, (cudaStream_t)stream);
     set_error("bad dtype %d", c->dtype);
     return SNP_ERR_INVALID;
 }

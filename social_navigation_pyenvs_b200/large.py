@@ -30,6 +30,9 @@ class LargeCrowd:
                                                      all_params_equal=symmetric, numba_compat=numba_compat, dtype=dtype, device=device)
         self.type = SFMS.index(model)
         self.view = [torch.zeros((5, self.n_total), dtype=dtype, device=self.eng.device) for _ in range(2)]
+        nbytes = int(self.eng.lib.snp_large_scratch_bytes(self.n_local, self.n_total, L.SNP_F64 if dtype == torch.float64 else L.SNP_F32))
+        self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.eng.device)
+        self.culling = True
         self.cur = 0
         self._publish()
 
@@ -48,10 +51,12 @@ class LargeCrowd:
     def step(self, dt=0.0125, n_substeps=1):
         c = self.eng._crowd()
         o = self.eng._opts(dt, 1)
+        o.reserved = 0 if self.culling else 2  # SNP_OPT_NO_CULLING
         for _ in range(n_substeps):
             cur, nxt = self.view[self.cur], self.view[self.cur ^ 1]
             L.check(self.eng.lib.snp_large_step(ctypes.byref(c), ctypes.byref(o), ctypes.c_void_p(cur.data_ptr()), self.n_total, self.offset,
-                                                ctypes.c_void_p(nxt.data_ptr()), self._stream()))
+                                                ctypes.c_void_p(nxt.data_ptr()), ctypes.c_void_p(self.scratch.data_ptr()), self.scratch.numel(),
+                                                self._stream()))
             self._gather(nxt)
             self.cur ^= 1
 

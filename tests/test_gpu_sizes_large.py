@@ -126,3 +126,30 @@ def test_large_crowd_tiled_kernel_vs_oracle():
         got = crowd.local_rows(S[0])
         tol = 1e-9 if "moussaid" not in model else 1e-6
         assert rel_err(got[:, :8], ref[0, :, :8]).max() < tol, model
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_large_crowd_chunked_sums_and_exact_culling(dtype):
+    """5184 humans (two j-chunks, 41 tiles, a 72 m wide crowd): the chunked partial sums stay within 1e-9 of the oracle's single
+    j-ascending sum, and skipping tiles beyond the exp-underflow distance changes NOTHING (bit-identical on/off)."""
+    from social_navigation_pyenvs_b200 import scenarios
+    from social_navigation_pyenvs_b200.large import LargeCrowd
+    sc = scenarios.jittered_grid_crowd(72, pitch=1.0, jitter=0.3, seed=3)
+    S, G = sc["states"], sc["goals"]
+    n = S.shape[1]
+    rng = np.random.RandomState(1)
+    S[0, :, 5:7] = rng.uniform(-0.6, 0.6, (n, 2))
+    if dtype == torch.float32:
+        S = S.astype(np.float32).astype(np.float64)
+    out = {}
+    for cull in (True, False):
+        crowd = LargeCrowd("hsfm_farina", S[0], G[0], dtype=dtype, symmetric=True)
+        crowd.culling = cull
+        crowd.step(0.0125, n_substeps=2)
+        out[cull] = crowd.local_rows(S[0])
+    assert np.array_equal(out[True], out[False])
+    cfg = OracleConfig(oracle.type_code("hsfm_farina"), False, True, False)
+    params = np.tile(oracle.default_params("hsfm_farina"), (1, n, 1))
+    ref, _, _ = oracle.update_humans(cfg, S, G, None, params, np.zeros((1, n)), np.zeros((1, n, 2)), 0.0125, 2)
+    tol = 1e-9 if dtype == torch.float64 else 1e-4
+    assert rel_err(out[True][:, :8], ref[0, :, :8]).max() < tol
