@@ -34,6 +34,8 @@ WORKLOADS = {
     "4096x5_sfm_helbing_cc": ("sfm_helbing", 4096, 5, False, False),
     # BASELINE configs[4]: ONE crowd of 65536 humans, sharded by agent across the GPUs (strong scaling, all-gather per sub-step)
     "65536_hsfm_single_crowd": ("hsfm_farina", 1, 65536, False, False),
+    # BASELINE configs[3]: 4096 envs x 360-ray laser over 25 humans + 14 wall segments (metric: rays/s)
+    "laser_4096x360": ("hsfm_farina", 4096, 25, True, True),
 }
 
 
@@ -111,6 +113,15 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(n for b, n in self.REASONS.items() if self.bits & b), "samples": len(self.sm)}
+
+
+def measured_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE k_step launch from the committed `ncu --set full` capture of this
+    exact workload / dtype (profiles/traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[f"{args.workload}:{args.dtype}"]
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def oracle_rate(inp, n_envs, threads, substeps, repeats=1):
@@ -245,6 +256,79 @@ def run_large_crowd(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_laser(args, rank, world, local_rank):
+    """Config 4: LaserSensor.get_laser_measurements for 4096 sensors x 360 rays (range 2 pi, max 10 m) over the 25 humans and the
+    3 wall polygons (14 segments) of workload 3b; a step = one scan of every env = one launch.  Env-sharded (weak scaling)."""
+    import ctypes
+    inp = build_inputs("4096x25_hsfm_ccso_walls_robot", 2000 + rank * 4096)
+    import torch
+    import torch.distributed as dist
+    from social_navigation_pyenvs_b200 import CrowdEngine, _lib, sensors
+    from social_navigation_pyenvs_b200.parallel import max_over_ranks
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.lib()
+    tdtype = torch.float64 if args.dtype == "f64" else torch.float32
+    E, N, samples = inp["E"], inp["N"], 360
+    eng = CrowdEngine.from_reference_arrays(inp["model"], inp["states"], inp["goals"], walls=inp["walls"], safety=inp["safety"],
+                                            consider_robot=True, all_params_equal=True, dtype=tdtype)
+    pose = torch.stack([eng.robot[_lib.ROBOT_PX], eng.robot[_lib.ROBOT_PY], torch.full((E,), float(np.pi / 2), dtype=tdtype, device="cuda")])
+    pose = pose.contiguous()
+    scanner = sensors.EngineScanner(eng, 2 * np.pi, samples, 10.0, robot_radius=0.3)
+    for _ in range(args.warmup):
+        scanner.scan(pose)
+    torch.cuda.synchronize()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    lib.snp_launch_count(1)
+    with ClockSampler(local_rank) as clocks:
+        for s in range(args.steps):
+            flush.fill_(s & 0xFF)
+            ev[s][0].record(stream)
+            ranges, hits = scanner.scan(pose)
+            ev[s][1].record(stream)
+        torch.cuda.synchronize()
+    launches = int(lib.snp_launch_count(0))
+    total_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), "cuda", world)
+    # end to end with host arrays through the reference-shaped call (humans [E,N,3], walls, pose [E,3] -> ranges, hits)
+    humans = inp["states"][:, :N][:, :, [0, 1, 8]].copy()
+    pose_h = np.concatenate([inp["robot"][:, 0:2], np.full((E, 1), np.pi / 2)], 1)
+    sensors.scan_batch(humans, inp["walls"], pose_h, 2 * np.pi, samples, 10.0, 0.3, dtype="float64" if args.dtype == "f64" else "float32")
+    reps = 10
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        sensors.scan_batch(humans, inp["walls"], pose_h, 2 * np.pi, samples, 10.0, 0.3, dtype="float64" if args.dtype == "f64" else "float32")
+    e2e_s = max_over_ranks(time.perf_counter() - t0, "cuda", world)
+    if rank == 0:
+        pipe = ctypes.c_double()
+        _lib.check(lib.snp_measure_pipe_peak(1 if args.dtype == "f64" else 0, ctypes.byref(pipe)))
+        nseg = int((~np.isnan(inp["walls"][:, :, 0, 0])).sum())
+        flops_per_ray = 12 * N + 25 * nseg  # SURVEY 8(d)
+        per_s = total_ms / args.steps * 1e-3
+        ach = E * samples * flops_per_ray / per_s / 1e12
+        w = 8 if args.dtype == "f64" else 4
+        bytes_per_launch = E * ((3 * N + 3) * w + samples * (w + 4)) + 4 * nseg * w
+        line = {"metric": "laser rays/sec (envs x rays)", "value": world * E * samples * args.steps / (total_ms * 1e-3), "unit": "rays/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": args.workload, "envs_per_gpu": E, "rays": samples, "humans": N, "wall_segments": nseg,
+                           "l2": "256 MiB flush write between timed steps"},
+                "clocks": clocks.summary(), "gpu_launches": launches,
+                "e2e": {"value": world * E * samples * reps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": int(humans.nbytes + pose_h.nbytes),
+                        "d2h_bytes_per_step": int(E * samples * 12), "api": "sensors.scan_batch (snp_laser_host)", "steps": reps},
+                "roofline": {"bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": ach, "peak": pipe.value, "unit": "TFLOP/s",
+                             "frac": ach / pipe.value, "traffic": None, "kernel": "snp::k_laser_rays", "flops_per_ray": flops_per_ray,
+                             "hbm": {"achieved_gbs": bytes_per_launch / per_s / 1e9, "bytes_per_ray": bytes_per_launch / (E * samples)}}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -266,6 +350,9 @@ def main():
 
     if args.workload == "65536_hsfm_single_crowd":
         run_large_crowd(args, rank, world, local_rank)
+        return
+    if args.workload == "laser_4096x360":
+        run_laser(args, rank, world, local_rank)
         return
     # host-side scenario generation forks worker processes: do it before CUDA is initialised in this process
     inp = build_inputs(args.workload, 2000 + rank * 4096)  # every rank owns different envs
@@ -384,7 +471,7 @@ def main():
     ach_gbs = launch_bytes / per_launch_s / 1e9
     ach_sfu = E * N * SUBSTEPS * cost["sfu"] / per_launch_s / 1e9
     roofline = {"bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": ach_tflops, "peak": pipe.value, "unit": "TFLOP/s",
-                "frac": ach_tflops / pipe.value, "traffic": None,
+                "frac": ach_tflops / pipe.value, "traffic": measured_traffic(args),
                 "peak_source": "measured in this run: register-resident FMA loop on all SMs (snp_measure_pipe_peak)",
                 "kernel": "snp::k_step (fused 20 sub-steps)", "flops_per_agent_substep": cost["flops"],
                 "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": hbm_peak, "frac": ach_gbs / hbm_peak, "peak_source": hbm_src,

@@ -8,6 +8,16 @@ namespace snp {
 
 template <typename T> struct alignas(16) Ent { T x, y, vx, vy; };  // float4 / double4-sized entity record staged in shared memory
 
+// Entities of one env group in shared memory as two arrays of (x,y) and (vx,vy) pairs.  With one lane per entity (the halved
+// pair loop reads ents[(i+k) mod N]) consecutive lanes then touch consecutive 8/16-byte words -> no bank conflicts, where a
+// 32-byte double4 record per lane gave a 2-way conflict on every LDS.128 (profiles/r01: 11.3 M conflicts per launch).
+template <typename T> struct alignas(2 * sizeof(T)) Vec2 { T a, b; };
+template <typename T> struct EntView {
+    Vec2<T> *pos, *vel;
+    __device__ __forceinline__ Ent<T> get(int j) const { const Vec2<T> p = pos[j], v = vel[j]; return Ent<T>{p.a, p.b, v.a, v.b}; }
+    __device__ __forceinline__ void put(int j, T x, T y, T vx, T vy) const { pos[j] = Vec2<T>{x, y}; vel[j] = Vec2<T>{vx, vy}; }
+};
+
 template <typename T> struct KArgs {
     int E, N, G;
     long long EN;

@@ -16,8 +16,6 @@ namespace snp {
 namespace {
 
 template <typename T> struct Circ { T sx, sy, cc; };       // s = sensor - centre, cc = s.s - r^2
-template <typename T> struct RaySeg { T x1, y1, x2, y2; };
-
 // Exact-formula arithmetic for double (matches the oracle bit for bit given the same ray direction); plain for float.
 template <typename T> struct Ops;
 template <> struct Ops<double> {
@@ -37,6 +35,20 @@ template <> struct Ops<float> {
     static __device__ __forceinline__ void sincos(float a, float *s, float *c) { sincosf(a, s, c); }
 };
 
+// One wall segment as the ray loop wants it.  Everything that does not depend on the ray direction is evaluated once per env
+// with the reference's own operations (sensors.py:36-47): a = x1-x2, b = y1-y2, e = x1-x3, f = y1-y3 (x3,y3 = sensor),
+// un = -((x1-x2)*(y1-y3) - (y1-y2)*(x1-x3)) = the numerator of u.
+template <typename T> struct RaySeg { T x1, y1, x2, y2, a, b, e, f, un; };
+
+template <typename T> __device__ __forceinline__ RaySeg<T> make_rayseg(T x1, T y1, T x2, T y2, T x3, T y3) {
+    using O = Ops<T>;
+    RaySeg<T> s;
+    s.x1 = x1; s.y1 = y1; s.x2 = x2; s.y2 = y2;
+    s.a = O::sub(x1, x2); s.b = O::sub(y1, y2); s.e = O::sub(x1, x3); s.f = O::sub(y1, y3);
+    s.un = -O::sub(O::mul(s.a, s.f), O::mul(s.b, s.e));
+    return s;
+}
+
 template <typename T> __device__ __forceinline__ Circ<T> make_circ(T ox, T oy, T cx, T cy, T r) {
     using O = Ops<T>;
     Circ<T> c;
@@ -50,28 +62,28 @@ template <typename T> __device__ __forceinline__ T circle_hit(const Circ<T> &c, 
     const T b = O::fma(c.sy, dy, O::mul(c.sx, dx));  // np.dot(s, dir)
     T h = O::sub(O::mul(b, b), c.cc);
     if (h < T(0)) return maxd;
-    h = Real<T>::sqrt_(h);
+    h = Real<T>::sqrt_exact(h);
     const T t = O::sub(-b, h);
     if (t < T(0)) return maxd;
     return t < maxd ? t : maxd;
 }
 
-template <typename T> __device__ __forceinline__ T segment_hit(const RaySeg<T> &s, T x3, T y3, T dx, T dy, T maxd) {  // sensors.py:35-51
+// sensors.py:35-51 for one (ray, segment): (c, d) = (y3 - y4, x3 - x4) are per-ray constants.  The two divisions of the
+// reference (t and u) are only needed to LOCATE a hit: den > 0, 0 < t and u > 0 are decided exactly by the numerators' signs,
+// and t < 1 implies nt < den, so the division (and the reference's own `t < 1` test on the rounded quotient) runs only for
+// the few candidate hits.  Same hit/miss decisions and the same range bits as the division-first form.
+template <typename T> __device__ __forceinline__ T segment_hit(const RaySeg<T> &s, T x3, T y3, T c, T d, T maxd) {
     using O = Ops<T>;
-    const T x4 = O::add(x3, dx), y4 = O::add(y3, dy);
-    const T a = O::sub(s.x1, s.x2), b = O::sub(s.y1, s.y2), c = O::sub(y3, y4), d = O::sub(x3, x4);
-    const T den = O::sub(O::mul(a, c), O::mul(b, d));
-    if (den <= T(0)) return maxd;
-    const T e = O::sub(s.x1, x3), f = O::sub(s.y1, y3);
-    const T t = O::div(O::sub(O::mul(e, c), O::mul(f, d)), den);
-    const T u = -O::div(O::sub(O::mul(a, f), O::mul(b, e)), den);
-    if (t > T(0) && t < T(1) && u > T(0)) {
-        const T ix = O::add(s.x1, O::mul(t, O::sub(s.x2, s.x1))), iy = O::add(s.y1, O::mul(t, O::sub(s.y2, s.y1)));
-        const T ex = O::sub(x3, ix), ey = O::sub(y3, iy);
-        const T dist = Real<T>::sqrt_(O::fma(ey, ey, O::mul(ex, ex)));  // np.linalg.norm
-        return dist < maxd ? dist : maxd;
-    }
-    return maxd;
+    const T den = O::sub(O::mul(s.a, c), O::mul(s.b, d));
+    if (!(den > T(0))) return maxd;
+    const T nt = O::sub(O::mul(s.e, c), O::mul(s.f, d));
+    if (!(nt > T(0) && nt < den && s.un > T(0))) return maxd;
+    const T t = O::div(nt, den);
+    if (!(t < T(1))) return maxd;
+    const T ix = O::add(s.x1, O::mul(t, O::sub(s.x2, s.x1))), iy = O::add(s.y1, O::mul(t, O::sub(s.y2, s.y1)));
+    const T ex = O::sub(x3, ix), ey = O::sub(y3, iy);
+    const T dist = Real<T>::sqrt_exact(O::fma(ey, ey, O::mul(ex, ex)));  // np.linalg.norm
+    return dist < maxd ? dist : maxd;
 }
 
 template <typename T> __device__ __forceinline__ void ray_direction(T yaw, T range, int samples, int k, T &dx, T &dy) {
@@ -108,12 +120,13 @@ template <typename T> __global__ void __launch_bounds__(128) k_laser_rays(const 
         circ[k] = make_circ<T>(ox, oy, a.px[idx], a.py[idx], a.radius[idx]);
     }
     const T *w = a.walls + (a.walls_per_env ? (size_t)e * nseg * 4 : 0);
-    for (int k = threadIdx.x; k < nseg; k += blockDim.x) segs[k] = RaySeg<T>{w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]};
+    for (int k = threadIdx.x; k < nseg; k += blockDim.x) segs[k] = make_rayseg<T>(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3], ox, oy);
     __syncthreads();
     const int ray = blockIdx.x * blockDim.x + threadIdx.x;
     if (ray >= a.samples) return;
     T dx, dy;
     ray_direction<T>(yaw, a.range, a.samples, ray, dx, dy);
+    const T rc_c = Ops<T>::sub(oy, Ops<T>::add(oy, dy)), rc_d = Ops<T>::sub(ox, Ops<T>::add(ox, dx));  // y3 - y4, x3 - x4 (sensors.py:42-44)
     T best = a.maxd;
     int hit = -1;
     for (int k = 0; k < a.N; ++k) {
@@ -122,9 +135,9 @@ template <typename T> __global__ void __launch_bounds__(128) k_laser_rays(const 
     }
     int ord = a.N;
     for (int k = 0; k < nseg; ++k) {
-        const RaySeg<T> s = segs[k];
+        const RaySeg<T> &s = segs[k];
         if (s.x1 != s.x1) continue;  // NaN padding slot
-        const T rc = segment_hit<T>(s, ox, oy, dx, dy, a.maxd);
+        const T rc = segment_hit<T>(s, ox, oy, rc_c, rc_d, a.maxd);
         if (rc < best) { best = rc; hit = ord; }
         ++ord;
     }
@@ -153,6 +166,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_laser_warp(const 
     const T ox = a.pose[e], oy = a.pose[(size_t)a.E + e], yaw = a.pose[2 * (size_t)a.E + e];
     T dx, dy;
     ray_direction<T>(yaw, a.range, a.samples, ray, dx, dy);
+    const T rc_c = Ops<T>::sub(oy, Ops<T>::add(oy, dy)), rc_d = Ops<T>::sub(ox, Ops<T>::add(ox, dx));
     T best = a.maxd;
     int hit = 0x7fffffff;
     for (int k = lane; k < a.N; k += 32) {
@@ -162,10 +176,10 @@ template <typename T> __global__ void __launch_bounds__(256) k_laser_warp(const 
         if (rc < best) { best = rc; hit = k; }
     }
     for (int k = lane; k < nseg; k += 32) {
-        const RaySeg<T> s{w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]};
+        const RaySeg<T> s = make_rayseg<T>(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3], ox, oy);
         if (s.x1 != s.x1) continue;
         const int wi = k / a.S;
-        const T rc = segment_hit<T>(s, ox, oy, dx, dy, a.maxd);
+        const T rc = segment_hit<T>(s, ox, oy, rc_c, rc_d, a.maxd);
         if (rc < best) { best = rc; hit = a.N + wall_base[wi] + (k - wi * a.S); }
     }
     // (value, index) min-reduction; ties -> lowest index == the reference's first strict-'<' winner

@@ -93,14 +93,14 @@ __device__ __forceinline__ double seg_min(double v, int i, int n, unsigned mask)
 // law is antisymmetric: uniform parameters, and for Moussaid the reference's symmetric path (lower index is agent 1,
 // forces.py:145-151).  Accumulation order differs from the reference's j-ascending order (rounding-level effect only).
 template <typename T, int SOC>
-__device__ __forceinline__ void social_force_halved(const Params<T> &P, const double *tbl, const Ent<T> *ents, const T *rs_g, const Agent<T> &me,
+__device__ __forceinline__ void social_force_halved(const Params<T> &P, const double *tbl, const EntView<T> ents, const T *rs_g, const Agent<T> &me,
                                                     int i, int N, bool with_robot, unsigned wmask, int gbase, T &fsx, T &fsy) {
     int p = i, q = i;
     const int rounds = (N - 1) >> 1;
     for (int k = 1; k <= rounds; ++k) {
         p = (p + 1 == N) ? 0 : p + 1;  // partner (i + k) mod N
         q = (q == 0) ? N - 1 : q - 1;  // the lane whose partner in this round is me: (i - k) mod N
-        const Ent<T> o = ents[p];
+        const Ent<T> o = ents.get(p);
         const T rsj = rs_g[p];
         T fx, fy;
         if (SOC == 2) {
@@ -116,7 +116,7 @@ __device__ __forceinline__ void social_force_halved(const Params<T> &P, const do
     }
     if (!(N & 1)) {  // antipodal pair: both ends evaluate it
         p = (p + 1 == N) ? 0 : p + 1;
-        const Ent<T> o = ents[p];
+        const Ent<T> o = ents.get(p);
         const T rsj = rs_g[p];
         T fx, fy;
         if (SOC == 2) {
@@ -130,7 +130,7 @@ __device__ __forceinline__ void social_force_halved(const Params<T> &P, const do
         fsx += fx; fsy += fy;
     }
     if (with_robot) {  // the robot exerts force but feels none (forces.py:146,151)
-        const Ent<T> o = ents[N];
+        const Ent<T> o = ents.get(N);
         T fx, fy;
         pair_force<T, SOC>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rs_g[N], fx, fy);
         fsx += fx; fsy += fy;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
     Seg<T> *segs_all = reinterpret_cast<Seg<T> *>(smem_raw + lay.segs);
     int *seg_cnt_all = reinterpret_cast<int *>(smem_raw + lay.seg_cnt);
     const int slots = lay.slots;
-    Ent<T> *ents0 = reinterpret_cast<Ent<T> *>(smem_raw + lay.ents);
+    Vec2<T> *ents0 = reinterpret_cast<Vec2<T> *>(smem_raw + lay.ents);  // [2 buffers][pos | vel][slots]
     T *rs_all = reinterpret_cast<T *>(smem_raw + lay.rs);
     double *red = reinterpret_cast<double *>(smem_raw + lay.red);  // CTA mode only: [N] doubles
 
@@ -298,14 +298,14 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
     bool touched = false;
     const T dt = a.dt;
     for (int s = 0; s < a.n_substeps; ++s) {
-        Ent<T> *ents = ents0 + (size_t)(s & 1) * slots + gslot;
+        const EntView<T> ents{ents0 + (size_t)(s & 1) * 2 * slots + gslot, ents0 + (size_t)(s & 1) * 2 * slots + slots + gslot};
         if (a.robot_mode == 1 && has_robot) {  // robot_agent.py:126-131 (holonomic): p = p + a*dt ; v = a
             if (sizeof(T) == 8) { rpx = (T)__dadd_rn((double)rpx, __dmul_rn((double)ax, (double)dt)); rpy = (T)__dadd_rn((double)rpy, __dmul_rn((double)ay, (double)dt)); }
             else { rpx = rpx + ax * dt; rpy = rpy + ay * dt; }
             rvx = ax; rvy = ay;
         }
-        if (live) { ents[i] = Ent<T>{me.px, me.py, me.vx, me.vy}; }
-        if (leader && a.consider_robot) ents[N] = Ent<T>{rpx, rpy, rvx, rvy};
+        if (live) ents.put(i, me.px, me.py, me.vx, me.vy);
+        if (leader && a.consider_robot) ents.put(N, rpx, rpy, rvx, rvy);
         if constexpr (CTA) __syncthreads(); else __syncwarp(wmask);
 
         if (live) {
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
                 const bool sym = a.symmetric != 0;
 #pragma unroll 2
                 for (int j = 0; j < M; ++j) {
-                    const Ent<T> o = ents[j];
+                    const Ent<T> o = ents.get(j);
                     const T rsj = rs_g[j];
                     T fx, fy;
                     if (SOC == 2) {

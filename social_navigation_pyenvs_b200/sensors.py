@@ -97,23 +97,38 @@ class LaserSensor:
         return dict(zip(angles, meas))
 
 
+class EngineScanner:
+    """Device-resident scans over a CrowdEngine's humans and walls with preallocated outputs and a cached argument block, so a
+    scan costs one C call: `ranges, hits = scanner.scan(pose)` with pose a [3,E] device tensor (x, y, yaw) of the engine's dtype.
+    The returned tensors are reused by the next scan."""
+
+    def __init__(self, engine, range_, samples, max_distance, robot_radius=0.0, want_hits=True):
+        import torch
+        if max_distance > 10:
+            raise ValueError("Maxium distance for laser is 10 meters")
+        self.engine, self.torch = engine, torch
+        self.ranges = torch.empty((engine.E, samples), dtype=engine.dtype, device=engine.device)
+        self.hits = torch.empty((engine.E, samples), dtype=torch.int32, device=engine.device) if want_hits else None
+        a = L.SnpLaserArgs()
+        a.E, a.N, a.samples = engine.E, engine.N, int(samples)
+        a.dtype = L.SNP_F64 if engine.dtype == torch.float64 else L.SNP_F32
+        a.px, a.py = engine.dyn[L.DYN_PX].data_ptr(), engine.dyn[L.DYN_PY].data_ptr()
+        a.radius = engine.stat[L.STAT_R].data_ptr()
+        a.walls = None if engine.walls is None else engine.walls.data_ptr()
+        a.W, a.S, a.walls_per_env = engine.W, engine.S, engine.walls_per_env
+        a.range, a.max_distance, a.robot_radius = float(range_), float(max_distance), float(robot_radius)
+        a.ranges = self.ranges.data_ptr()
+        a.hits = None if self.hits is None else self.hits.data_ptr()
+        self.args, self.fn = a, L.lib().snp_laser
+
+    def scan(self, pose):
+        assert pose.is_contiguous() and pose.dtype == self.engine.dtype and pose.shape == (3, self.engine.E)
+        self.args.pose = pose.data_ptr()
+        L.check(self.fn(ctypes.byref(self.args), ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)))
+        return self.ranges, self.hits
+
+
 def scan_engine(engine, pose, range_, samples, max_distance, robot_radius=0.0, want_hits=True):
-    """Device-resident scan over a CrowdEngine's humans and walls: pose [3,E] tensor (x,y,yaw) of the engine's dtype.
-    Returns (ranges [E,samples] tensor, hits [E,samples] int32 tensor or None) on the device, no host round trip."""
-    import torch
-    a = L.SnpLaserArgs()
-    a.E, a.N, a.samples = engine.E, engine.N, int(samples)
-    a.dtype = L.SNP_F64 if engine.dtype == torch.float64 else L.SNP_F32
-    a.px, a.py = engine.dyn[L.DYN_PX].data_ptr(), engine.dyn[L.DYN_PY].data_ptr()
-    a.radius = engine.stat[L.STAT_R].data_ptr()
-    a.walls = None if engine.walls is None else engine.walls.data_ptr()
-    a.W, a.S, a.walls_per_env = engine.W, engine.S, engine.walls_per_env
+    """One-off device-resident scan (see EngineScanner): pose [3,E] tensor (x,y,yaw).  Returns (ranges, hits) device tensors."""
     pose = pose.to(device=engine.device, dtype=engine.dtype).contiguous()
-    a.pose = pose.data_ptr()
-    a.range, a.max_distance, a.robot_radius = float(range_), float(max_distance), float(robot_radius)
-    ranges = torch.empty((engine.E, samples), dtype=engine.dtype, device=engine.device)
-    hits = torch.empty((engine.E, samples), dtype=torch.int32, device=engine.device) if want_hits else None
-    a.ranges = ranges.data_ptr()
-    a.hits = None if hits is None else hits.data_ptr()
-    L.check(L.lib().snp_laser(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-    return ranges, hits
+    return EngineScanner(engine, range_, samples, max_distance, robot_radius, want_hits).scan(pose)
