@@ -29,25 +29,37 @@ template <typename T> __host__ __device__ inline Params<T> make_params(const dou
 
 // Force exerted on agent 1 by agent 2 (forces.py:63-128).  rs = radius + safety_space.
 // SOC: 0 Helbing, 1 Guo, 2 Moussaid.
+// `vote_mask`: lanes of the warp executing this call together.  The body-compression and sliding-friction terms
+// (k1 max(0,rd), k2 max(0,rd) dv) are identically zero unless the two bodies overlap, which is rare; the warp votes and skips
+// them (and the relative-velocity projection they need) when no lane has a contact.  The result is bit-identical to the
+// always-evaluated form (the skipped terms are exact zeros added to / multiplied into the rest).
 template <typename T, int SOC>
-__device__ __forceinline__ void pair_force(const Params<T> &P, const double *tbl, T x1, T y1, T vx1, T vy1, T rs1, T x2, T y2, T vx2,
-                                           T vy2, T rs2, T &fx, T &fy) {
+__device__ __forceinline__ void pair_force(const Params<T> &P, const double *tbl, unsigned vote_mask, T x1, T y1, T vx1, T vy1, T rs1, T x2,
+                                           T y2, T vx2, T vy2, T rs2, T &fx, T &fy) {
     using R = Real<T>;
     const T dx = x1 - x2, dy = y1 - y2;
-    const T d2 = np_sq(dx, dy) + tiny_<T>();  // self pair: n = (0,0) -> zero force, no branch (see tiny_)
+    const T d2 = fma_<T>(dy, dy, fma_<T>(dx, dx, tiny_<T>()));  // self pair: n = (0,0) -> zero force, no branch (see tiny_)
     const T inv = R::rsqrt_(d2);
     const T dist = d2 * inv;
     const T nx = dx * inv, ny = dy * inv;
     const T rd = (rs1 + rs2) - dist;
-    const T prd = max0(rd);
+    const bool contact = __any_sync(vote_mask, rd > T(0));
     if (SOC < 2) {
-        // t = (-ny, nx); dv = (v2 - v1) . t
-        const T dv = np_dot(vx2 - vx1, vy2 - vy1, -ny, nx);
-        const T cn = fma_<T>(P.Ai, R::exp_(rd * P.inv_Bi, tbl), P.k1 * prd);
-        T ct = P.k2 * prd * dv;
+        T cn = P.Ai * R::exp_(rd * P.inv_Bi, tbl);
+        T ct = T(0);
+        if (contact) {
+            const T prd = max0(rd);
+            const T dv = np_dot(vx2 - vx1, vy2 - vy1, -ny, nx);  // t = (-ny, nx); dv = (v2 - v1) . t
+            cn = fma_<T>(P.k1, prd, cn);
+            ct = P.k2 * prd * dv;
+        }
         if (SOC == 1) ct = fma_<T>(P.Ci, R::exp_(rd * P.inv_Di, tbl), ct);
-        fx = fma_<T>(cn, nx, ct * -ny);
-        fy = fma_<T>(cn, ny, ct * nx);
+        if (SOC == 1 || contact) {
+            fx = fma_<T>(cn, nx, ct * -ny);
+            fy = fma_<T>(cn, ny, ct * nx);
+        } else {
+            fx = cn * nx; fy = cn * ny;
+        }
     } else {
         const T ivx = fma_<T>(P.lambda, vx1 - vx2, -nx);
         const T ivy = fma_<T>(P.lambda, vy1 - vy2, -ny);
@@ -58,12 +70,16 @@ __device__ __forceinline__ void pair_force(const Params<T> &P, const double *tbl
         const T theta = bound_angle<T>(R::atan2_(ny, nx) - R::atan2_(iy, ix) + R::pi());
         const T k = sign_(theta);
         const T F = P.gamma * inorm;
-        const T dvh = np_dot(vx2 - vx1, vy2 - vy1, -iy, ix);
         const T e0 = P.Ei * R::exp_(-dist * R::rcp_(F), tbl);
         const T a = P.ns1 * F * theta, b = P.ns * F * theta;
         const T ea = R::exp_(-(a * a), tbl), eb = k * R::exp_(-(b * b), tbl);
-        const T ci = fma_<T>(e0, ea, P.k1 * prd);       // coefficient of i_ij
-        const T ch = fma_<T>(e0, eb, P.k2 * prd * dvh);  // coefficient of h_ij = (-iy, ix)
+        T ci = e0 * ea, ch = e0 * eb;  // coefficients of i_ij and h_ij = (-iy, ix)
+        if (contact) {
+            const T prd = max0(rd);
+            const T dvh = np_dot(vx2 - vx1, vy2 - vy1, -iy, ix);
+            ci = fma_<T>(P.k1, prd, ci);
+            ch = fma_<T>(P.k2 * prd, dvh, ch);
+        }
         fx = -fma_<T>(ci, ix, ch * -iy);
         fy = -fma_<T>(ci, iy, ch * ix);
     }
@@ -103,8 +119,8 @@ __device__ __forceinline__ void closest_point(const Seg<T> *segs, int cnt, T px,
 
 // Wall force of all W polygons on one agent (forces.py:27-53).  OBS: 0 Helbing (mean over walls), 1 Guo (sum; mean in Numba).
 template <typename T, int OBS>
-__device__ __forceinline__ void obstacle_force(const Params<T> &P, const double *tbl, const Seg<T> *segs, const int *seg_cnt, int W, int S,
-                                               bool numba, T px, T py, T vx, T vy, T rs, T &fx, T &fy) {
+__device__ __forceinline__ void obstacle_force(const Params<T> &P, const double *tbl, unsigned vote_mask, const Seg<T> *segs, const int *seg_cnt,
+                                               int W, int S, bool numba, T px, T py, T vx, T vy, T rs, T &fx, T &fy) {
     using R = Real<T>;
     fx = T(0); fy = T(0);
     for (int w = 0; w < W; ++w) {
@@ -114,15 +130,21 @@ __device__ __forceinline__ void obstacle_force(const Params<T> &P, const double 
         const T inv = R::rsqrt_(d2);
         const T dist = d2 * inv;
         const T nx = dx * inv, ny = dy * inv;
-        const T dv = -np_dot(vx, vy, -ny, nx);
         const T rd = rs - dist;
-        const T prd = max0(rd);
-        const T cn = fma_<T>(P.Aw, R::exp_(rd * P.inv_Bw, tbl), P.k1 * prd);
-        T ct;
-        if (OBS == 0) ct = -(P.k2 * prd * dv);
-        else ct = (-P.Cw * R::exp_(rd * P.inv_Dw, tbl) - P.k2 * prd) * dv;
-        fx += fma_<T>(cn, nx, ct * -ny);
-        fy += fma_<T>(cn, ny, ct * nx);
+        const bool contact = __any_sync(vote_mask, rd > T(0));  // compression / friction terms only when some lane touches the wall
+        T cn = P.Aw * R::exp_(rd * P.inv_Bw, tbl);
+        if (OBS == 0 && !contact) {
+            fx = fma_<T>(cn, nx, fx); fy = fma_<T>(cn, ny, fy);
+        } else {
+            const T prd = contact ? max0(rd) : T(0);
+            const T dv = -np_dot(vx, vy, -ny, nx);
+            cn = fma_<T>(P.k1, prd, cn);
+            T ct;
+            if (OBS == 0) ct = -(P.k2 * prd * dv);
+            else ct = (-P.Cw * R::exp_(rd * P.inv_Dw, tbl) - P.k2 * prd) * dv;
+            fx += fma_<T>(cn, nx, ct * -ny);
+            fy += fma_<T>(cn, ny, ct * nx);
+        }
     }
     if (W > 0 && (OBS == 0 || numba)) { const T iw = R::rcp_(T(W)); fx *= iw; fy *= iw; }
 }

@@ -125,11 +125,11 @@ __global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
                 T fx, fy;  // the self pair (jj == idx[q]) contributes exactly zero by construction (tiny_ in pair_force)
                 if (SOC == 2) {
                     const bool sw = sym && jj < idx[q];
-                    pair_force<T, SOC>(P, exp_tbl_s, sw ? o.x : mx[q], sw ? o.y : my[q], sw ? o.vx : mvx[q], sw ? o.vy : mvy[q], sw ? rsj : mrs[q],
+                    pair_force<T, SOC>(P, exp_tbl_s, 0xffffffffu, sw ? o.x : mx[q], sw ? o.y : my[q], sw ? o.vx : mvx[q], sw ? o.vy : mvy[q], sw ? rsj : mrs[q],
                                        sw ? mx[q] : o.x, sw ? my[q] : o.y, sw ? mvx[q] : o.vx, sw ? mvy[q] : o.vy, sw ? mrs[q] : rsj, fx, fy);
                     fx = sw ? -fx : fx; fy = sw ? -fy : fy;
                 } else {
-                    pair_force<T, SOC>(P, exp_tbl_s, mx[q], my[q], mvx[q], mvy[q], mrs[q], o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+                    pair_force<T, SOC>(P, exp_tbl_s, 0xffffffffu, mx[q], my[q], mvx[q], mvy[q], mrs[q], o.x, o.y, o.vx, o.vy, rsj, fx, fy);
                 }
                 fsx[q] += fx; fsy[q] += fy;
             }
@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(kTile) k_large_finish(const LargeArgs<T> la) {
     const long long N = a.EN, M = la.M;
     const long long i = (long long)blockIdx.x * kTile + threadIdx.x;
     if (i >= N) return;
+    const unsigned vote_mask = __activemask();  // the lanes that own an agent (the tail warp is partial)
     const Params<T> &P = a.P;
     Agent<T> m;
     m.px = a.dyn[SNP_DYN_PX * N + i]; m.py = a.dyn[SNP_DYN_PY * N + i];
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(kTile) k_large_finish(const LargeArgs<T> la) {
         m.gx = a.goals[((size_t)gidx * 2 + 0) * N + i]; m.gy = a.goals[((size_t)gidx * 2 + 1) * N + i];
     }
     T fox = T(0), foy = T(0);
-    if (a.W > 0) obstacle_force<T, OBS>(P, exp_tbl_s, segs, seg_cnt, a.W, a.S, a.numba != 0, m.px, m.py, m.vx, m.vy, m.rs, fox, foy);
+    if (a.W > 0) obstacle_force<T, OBS>(P, exp_tbl_s, vote_mask, segs, seg_cnt, a.W, a.S, a.numba != 0, m.px, m.py, m.vx, m.vy, m.rs, fox, foy);
     desired_force<T>(P, m, a.numba != 0);
     integrate<T, HEADED>(P, m, fox, foy, fsx, fsy, a.dt);
     a.dyn[SNP_DYN_PX * N + i] = m.px; a.dyn[SNP_DYN_PY * N + i] = m.py;

@@ -105,11 +105,11 @@ __device__ __forceinline__ void social_force_halved(const Params<T> &P, const do
         T fx, fy;
         if (SOC == 2) {
             const bool sw = p < i;  // the lower index is agent 1
-            pair_force<T, SOC>(P, tbl, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
+            pair_force<T, SOC>(P, tbl, wmask, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
                                sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
             fx = sw ? -fx : fx; fy = sw ? -fy : fy;
         } else {
-            pair_force<T, SOC>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+            pair_force<T, SOC>(P, tbl, wmask, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
         }
         const T rx = __shfl_sync(wmask, fx, gbase + q), ry = __shfl_sync(wmask, fy, gbase + q);
         fsx += fx - rx; fsy += fy - ry;
@@ -121,18 +121,18 @@ __device__ __forceinline__ void social_force_halved(const Params<T> &P, const do
         T fx, fy;
         if (SOC == 2) {
             const bool sw = p < i;
-            pair_force<T, SOC>(P, tbl, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
+            pair_force<T, SOC>(P, tbl, wmask, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
                                sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
             fx = sw ? -fx : fx; fy = sw ? -fy : fy;
         } else {
-            pair_force<T, SOC>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+            pair_force<T, SOC>(P, tbl, wmask, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
         }
         fsx += fx; fsy += fy;
     }
     if (with_robot) {  // the robot exerts force but feels none (forces.py:146,151)
         const Ent<T> o = ents.get(N);
         T fx, fy;
-        pair_force<T, SOC>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rs_g[N], fx, fy);
+        pair_force<T, SOC>(P, tbl, wmask, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rs_g[N], fx, fy);
         fsx += fx; fsy += fy;
     }
 }
@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
     unsigned wmask = 0xffffffffu;
     if constexpr (CTA) {
         i = threadIdx.x; g = 0; env = blockIdx.x; live = i < N;
+        wmask = __ballot_sync(0xffffffffu, live);  // lanes of this warp that take part in votes
     } else {
         const int warp = threadIdx.x >> 5;
         const int gw = lane / N;  // group within the warp
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             }
             // wall force
             T fox = T(0), foy = T(0);
-            if (a.W > 0) obstacle_force<T, OBS>(P, exp_tbl_s, segs, seg_cnt, a.W, a.S, a.numba != 0, me.px, me.py, me.vx, me.vy, me.rs, fox, foy);
+            if (a.W > 0) obstacle_force<T, OBS>(P, exp_tbl_s, wmask, segs, seg_cnt, a.W, a.S, a.numba != 0, me.px, me.py, me.vx, me.vy, me.rs, fox, foy);
             T fsx = T(0), fsy = T(0);
             if constexpr (HALF) {
                 social_force_halved<T, SOC>(P, exp_tbl_s, ents, rs_g, me, i, N, a.consider_robot != 0, wmask, lane - i, fsx, fsy);
@@ -336,11 +337,11 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
                         // symmetric path: the pair is evaluated once with the LOWER index as agent 1 and applied with a minus
                         // sign to the other (forces.py:149-151); only Moussaid's sign(theta) makes that differ from f(i,j).
                         const bool sw = sym && j < i;
-                        pair_force<T, SOC>(P, exp_tbl_s, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
+                        pair_force<T, SOC>(P, exp_tbl_s, wmask, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
                                            sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
                         fx = sw ? -fx : fx; fy = sw ? -fy : fy;
                     } else {
-                        pair_force<T, SOC>(P, exp_tbl_s, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+                        pair_force<T, SOC>(P, exp_tbl_s, wmask, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
                     }
                     fsx += fx; fsy += fy;
                 }
