@@ -43,7 +43,7 @@ typedef enum snp_status {
 } snp_status;
 
 enum { SNP_F32 = 0, SNP_F64 = 1 };
-enum { SNP_OPT_FULL_PAIR_LOOP = 1, SNP_OPT_NO_CULLING = 2 };
+enum { SNP_OPT_FULL_PAIR_LOOP = 1, SNP_OPT_NO_CULLING = 2, SNP_OPT_MAP_WARP = 4, SNP_OPT_MAP_BLOCK = 8 };
 
 /* Field order of the structure-of-arrays buffers (each field is a contiguous run of E*N elements). */
 enum { SNP_DYN_PX = 0, SNP_DYN_PY, SNP_DYN_VX, SNP_DYN_VY, SNP_DYN_TH, SNP_DYN_BVX, SNP_DYN_BVY, SNP_DYN_OM,
@@ -100,7 +100,8 @@ typedef struct snp_step_opts {
     int32_t post_checks;      /* actual collision / goal on the POST-step state (social_nav_gym.py:269) */
     int32_t track_touch;      /* OR of the run_k_steps collision test after every sub-step */
     int32_t reserved;         /* bit 0 (SNP_OPT_FULL_PAIR_LOOP): evaluate every ordered pair in j-ascending order (the reference's
-                                 accumulation order) instead of each unordered pair once per warp */
+                                 accumulation order) instead of each unordered pair once per warp;
+                                 bits 2-3 (SNP_OPT_MAP_WARP / SNP_OPT_MAP_BLOCK): force the warp-packed / block-packed thread mapping */
     double consts[6];         /* time_limit, collision_penalty, success_reward, discomfort_dist,
                                  discomfort_penalty_factor, robot_time_step */
     double *time_now;         /* optional [E] global_time; read by the reward, advanced by dt per sub-step */

@@ -6,8 +6,9 @@
 // Two mappings of the same body:
 //   warp-packed (CTA = false): N <= 32 humans per env; floor(32/N) envs share a warp, one lane per human; the only
 //       synchronisation is __syncwarp; flag reductions are segmented warp shuffles.
-//   CTA-per-env (CTA = true): 32 < N <= 512; one thread per human, __syncthreads per sub-step, reductions through
-//       shared memory.
+//   block-packed (BLOCK = true): floor(128/N) envs share a 128-thread CTA regardless of warp boundaries (N = 25: 5 envs on
+//       125 of 128 lanes instead of 25 of 32), or one env per CTA for 128 < N <= 512; synchronisation is __syncthreads
+//       (two per sub-step), reductions and the pair exchange go through shared memory.
 // Reference: social_gym/src/motion_model_manager.py:354-373,424-459 (serial path), src/forces.py, src/forces_parallel.py:184-284,
 // social_gym/social_nav_gym.py:227-250 (sub-step loop), social_nav_sim.py:949-1029 and social_nav_gym.py:107-118 (checks).
 #include <cstdio>
@@ -31,9 +32,9 @@ constexpr int kSlotsPerWarp = 64;  // >= epw * (N + 1) for every N <= 32
 
 // Byte offsets of the dynamic shared-memory regions (same arithmetic on host and device).
 template <typename T> struct SmemLayout {
-    size_t segs, seg_cnt, ents, rs, red, total;
+    size_t segs, seg_cnt, ents, rs, red, xchg, tflag, total;
     int slots;
-    __host__ __device__ SmemLayout(int nseg, int seg_groups, int W, int slots_, int red_doubles) : slots(slots_) {
+    __host__ __device__ SmemLayout(int nseg, int seg_groups, int W, int slots_, int red_doubles, int xchg_vec2 = 0, int groups = 0) : slots(slots_) {
         size_t off = sizeof(T) == 8 ? 64 * sizeof(double) : 0;  // exp table (fp64 only)
         segs = off; off += sizeof(Seg<T>) * (size_t)nseg * seg_groups;
         off = (off + 15) & ~size_t(15);
@@ -43,6 +44,9 @@ template <typename T> struct SmemLayout {
         rs = off; off += sizeof(T) * (size_t)slots;
         off = (off + 15) & ~size_t(15);
         red = off; off += sizeof(double) * (size_t)red_doubles;
+        off = (off + 15) & ~size_t(15);
+        xchg = off; off += sizeof(Vec2<T>) * (size_t)xchg_vec2;   // block-packed halved pair loop: [rounds][lanes] of (fx, fy)
+        tflag = off; off += sizeof(int) * (size_t)groups;
         total = off + 16;
     }
 };
@@ -139,6 +143,7 @@ __device__ __forceinline__ void social_force_halved(const Params<T> &P, const do
 
 template <typename T, int SOC, int OBS, int HEADED, bool CTA, bool PER_AGENT, bool HALF>
 __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (sizeof(T) == 4 ? SNP_MINB_F32 : SNP_MINB_F64)) k_step(const KArgs<T> a) {
+    // CTA == true is the block-packed mapping (a.gpb env groups per CTA), CTA == false the warp-packed one (a.epw per warp).
     using R = Real<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -150,7 +155,10 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
     bool live;
     unsigned wmask = 0xffffffffu;
     if constexpr (CTA) {
-        i = threadIdx.x; g = 0; env = blockIdx.x; live = i < N;
+        g = threadIdx.x / N;
+        i = threadIdx.x - g * N;
+        env = (long long)blockIdx.x * a.gpb + g;
+        live = g < a.gpb && env < a.E;
         wmask = __ballot_sync(0xffffffffu, live);  // lanes of this warp that take part in votes
     } else {
         const int warp = threadIdx.x >> 5;
@@ -162,19 +170,23 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
         wmask = __ballot_sync(0xffffffffu, live);
     }
     const int M = N + (a.consider_robot ? 1 : 0);  // entities exerting force
-    const int groups = CTA ? 1 : kWarpsPerBlock * a.epw;
+    const int groups = CTA ? a.gpb : kWarpsPerBlock * a.epw;
+    const int rounds = (N - 1) >> 1;  // halved pair loop
 
     // ---- shared memory carve-up: [exp table][segments][segment counts][entities x2][r+safety][reduction scratch] ----
     const int nseg = a.W * a.S;
     const int seg_groups = a.walls_per_env ? groups : 1;
-    const SmemLayout<T> lay(nseg, seg_groups, a.W, CTA ? (N + 1) : kWarpsPerBlock * kSlotsPerWarp, CTA ? N : 0);
+    const SmemLayout<T> lay(nseg, seg_groups, a.W, CTA ? a.gpb * (N + 1) : kWarpsPerBlock * kSlotsPerWarp, CTA ? a.gpb * N : 0,
+                            (CTA && HALF) ? rounds * a.gpb * N : 0, CTA ? a.gpb : 0);
     double *exp_tbl_s = reinterpret_cast<double *>(smem_raw);
     Seg<T> *segs_all = reinterpret_cast<Seg<T> *>(smem_raw + lay.segs);
     int *seg_cnt_all = reinterpret_cast<int *>(smem_raw + lay.seg_cnt);
     const int slots = lay.slots;
     Vec2<T> *ents0 = reinterpret_cast<Vec2<T> *>(smem_raw + lay.ents);  // [2 buffers][pos | vel][slots]
     T *rs_all = reinterpret_cast<T *>(smem_raw + lay.rs);
-    double *red = reinterpret_cast<double *>(smem_raw + lay.red);  // CTA mode only: [N] doubles
+    double *red = reinterpret_cast<double *>(smem_raw + lay.red) + (CTA ? g * N : 0);  // block-packed only: this group's [N] doubles
+    Vec2<T> *xchg = reinterpret_cast<Vec2<T> *>(smem_raw + lay.xchg) + (CTA ? g * N : 0);
+    int *tflag = reinterpret_cast<int *>(smem_raw + lay.tflag);
 
     if (sizeof(T) == 8) exp_table_init(exp_tbl_s);
     // walls -> shared memory (whole block cooperates, before anyone leaves)
@@ -184,7 +196,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             const int sg = k / nseg, s = k - sg * nseg;
             long long wenv = 0;
             if (a.walls_per_env) {
-                wenv = CTA ? (long long)blockIdx.x : ((long long)blockIdx.x * kWarpsPerBlock * a.epw + sg);
+                wenv = CTA ? ((long long)blockIdx.x * a.gpb + sg) : ((long long)blockIdx.x * kWarpsPerBlock * a.epw + sg);
                 if (wenv >= a.E) wenv = a.E - 1;
             }
             const T *w = a.walls + ((size_t)wenv * nseg + s) * 4;
@@ -201,7 +213,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
     __syncthreads();
     if constexpr (!CTA) { if (!live) return; }
 
-    const int gslot = CTA ? 0 : ((threadIdx.x >> 5) * kSlotsPerWarp + (g - (threadIdx.x >> 5) * a.epw) * (N + 1));
+    const int gslot = CTA ? g * (N + 1) : ((threadIdx.x >> 5) * kSlotsPerWarp + (g - (threadIdx.x >> 5) * a.epw) * (N + 1));
     const Seg<T> *segs = segs_all + (a.walls_per_env ? (size_t)g * nseg : 0);
     const int *seg_cnt = seg_cnt_all + (a.walls_per_env ? g * a.W : 0);
     T *rs_g = rs_all + gslot;
@@ -309,6 +321,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
         if (leader && a.consider_robot) ents.put(N, rpx, rpy, rvx, rvy);
         if constexpr (CTA) __syncthreads(); else __syncwarp(wmask);
 
+        T fox = T(0), foy = T(0), fsx = T(0), fsy = T(0);
         if (live) {
             // goal switching (mmm:66-70 '<', fp:226 '<=')
             {
@@ -319,11 +332,52 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
                 }
             }
             // wall force
-            T fox = T(0), foy = T(0);
             if (a.W > 0) obstacle_force<T, OBS>(P, exp_tbl_s, wmask, segs, seg_cnt, a.W, a.S, a.numba != 0, me.px, me.py, me.vx, me.vy, me.rs, fox, foy);
-            T fsx = T(0), fsy = T(0);
-            if constexpr (HALF) {
+            if constexpr (HALF && !CTA) {
                 social_force_halved<T, SOC>(P, exp_tbl_s, ents, rs_g, me, i, N, a.consider_robot != 0, wmask, lane - i, fsx, fsy);
+            } else if constexpr (HALF && CTA) {
+                // Block-packed halved loop, phase 1: lane i evaluates the pairs {i, (i+k) mod N}, k = 1..rounds, keeps +f and
+                // leaves -f for the partner in plane k of the exchange buffer (written at the PARTNER's slot: conflict-free).
+                const int L = a.gpb * N;
+                int pidx = i;
+#pragma unroll 2
+                for (int k = 0; k < rounds; ++k) {
+                    pidx = (pidx + 1 == N) ? 0 : pidx + 1;
+                    const Ent<T> o = ents.get(pidx);
+                    const T rsj = rs_g[pidx];
+                    T fx, fy;
+                    if (SOC == 2) {
+                        const bool sw = pidx < i;  // the lower index is agent 1 (forces.py:145-151)
+                        pair_force<T, SOC>(P, exp_tbl_s, wmask, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
+                                           sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
+                        fx = sw ? -fx : fx; fy = sw ? -fy : fy;
+                    } else {
+                        pair_force<T, SOC>(P, exp_tbl_s, wmask, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+                    }
+                    fsx += fx; fsy += fy;
+                    xchg[(size_t)k * L + pidx] = Vec2<T>{fx, fy};
+                }
+                if (!(N & 1)) {  // antipodal pair: both ends evaluate it
+                    pidx = (pidx + 1 == N) ? 0 : pidx + 1;
+                    const Ent<T> o = ents.get(pidx);
+                    const T rsj = rs_g[pidx];
+                    T fx, fy;
+                    if (SOC == 2) {
+                        const bool sw = pidx < i;
+                        pair_force<T, SOC>(P, exp_tbl_s, wmask, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
+                                           sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
+                        fx = sw ? -fx : fx; fy = sw ? -fy : fy;
+                    } else {
+                        pair_force<T, SOC>(P, exp_tbl_s, wmask, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+                    }
+                    fsx += fx; fsy += fy;
+                }
+                if (a.consider_robot) {
+                    const Ent<T> o = ents.get(N);
+                    T fx, fy;
+                    pair_force<T, SOC>(P, exp_tbl_s, wmask, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rs_g[N], fx, fy);
+                    fsx += fx; fsy += fy;
+                }
             } else {
                 // j ascending: exactly the accumulation order of forces.py:145-151.  Branch-free body: the self pair contributes
                 // an exactly zero force by construction (tiny_ in pair_force), so consecutive pairs interleave in the pipes.
@@ -346,6 +400,20 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
                     fsx += fx; fsy += fy;
                 }
             }
+        }
+        if constexpr (HALF && CTA) {
+            // phase 2: one barrier, then every lane collects what its partners left for it (own slot of every plane)
+            __syncthreads();
+            if (live) {
+                const int L = a.gpb * N;
+#pragma unroll 4
+                for (int k = 0; k < rounds; ++k) {
+                    const Vec2<T> r = xchg[(size_t)k * L + i];
+                    fsx -= r.a; fsy -= r.b;
+                }
+            }
+        }
+        if (live) {
             desired_force<T>(P, me, a.numba != 0);
             integrate<T, HEADED>(P, me, fox, foy, fsx, fsy, dt);
             if (a.track_touch && has_robot)
@@ -363,12 +431,14 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
         }
         double admin; bool any_touch;
         if constexpr (CTA) {
+            if (threadIdx.x < a.gpb) tflag[threadIdx.x] = 0;
             __syncthreads();
             if (live) red[i] = d;
+            if (live && touched) tflag[g] = 1;
             __syncthreads();
             admin = 10000.0;
             if (leader) for (int k = 0; k < N; ++k) admin = red[k] < admin ? red[k] : admin;
-            any_touch = __syncthreads_or(touched ? 1 : 0) != 0;
+            any_touch = leader && tflag[g] != 0;
         } else {
             const int gbase = lane - i;
             const unsigned gm = (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) << gbase;
@@ -416,9 +486,19 @@ template <typename T, int SOC, int OBS, int HEADED>
 int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
     KArgs<T> a = a_in;
     const int nseg = a.W * a.S;
-    const bool cta = a.N > 32;
     if (a.N > 512) { set_error("snp_step handles N <= 512 humans per env (got %d); use snp_large_step", a.N); return SNP_ERR_UNSUPPORTED; }
     const bool per_agent = a.agent_params != nullptr;
+    // pairs evaluated once per warp / block whenever the law is antisymmetric (see social_force_halved)
+    bool half = !per_agent && !a.full_pair_loop && (SOC != 2 || a.symmetric);
+    // Mapping: warp-packed for N <= 32 (envs tile a warp; __syncwarp and shuffles only), block-packed above (envs tile a 128-thread
+    // CTA).  Block-packing small crowds fills more lanes (N = 25: 125/128 instead of 25/32) but measured SLOWER on B200 (fp64
+    // 0.315 vs 0.281 ms, fp32 0.192 vs 0.178 ms per 20-sub-step launch at 4096 x 25): two __syncthreads per sub-step and the
+    // shared-memory exchange cost more than the idle lanes.  a.mapping: 0 auto, 1 force warp-packed, 2 force block-packed.
+    const int gpb = a.N <= 128 ? 128 / a.N : 1;
+    const int block_threads = a.N <= 128 ? 128 : (a.N + 31) / 32 * 32;
+    bool cta = a.N > 32;
+    if (a.mapping == 1 && a.N <= 32) cta = false;
+    if (a.mapping == 2) cta = true;
     dim3 grid, block;
     size_t smem;
     if (!cta) {
@@ -429,9 +509,12 @@ int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
         smem = SmemLayout<T>(nseg, a.walls_per_env ? epb : 1, a.W, kWarpsPerBlock * kSlotsPerWarp, 0).total;
     } else {
         a.epw = 1;
-        grid = dim3((unsigned)a.E);
-        block = dim3((unsigned)((a.N + 31) / 32 * 32));
-        smem = SmemLayout<T>(nseg, 1, a.W, a.N + 1, a.N).total;
+        a.gpb = gpb;
+        grid = dim3((unsigned)((a.E + gpb - 1) / gpb));
+        block = dim3((unsigned)block_threads);
+        const int rounds = (a.N - 1) >> 1;
+        if (half && sizeof(Vec2<T>) * (size_t)rounds * gpb * a.N > 64 * 1024) half = false;  // exchange planes would not fit: ordered loop
+        smem = SmemLayout<T>(nseg, a.walls_per_env ? gpb : 1, a.W, gpb * (a.N + 1), gpb * a.N, half ? rounds * gpb * a.N : 0, gpb).total;
     }
     if (smem > 200 * 1024) { set_error("wall/segment tables need %zu bytes of shared memory (limit 200 KiB)", smem); return SNP_ERR_UNSUPPORTED; }
 #define SNP_LAUNCH(CTA_, PA_, HALF_)                                                                                   \
@@ -440,10 +523,11 @@ int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
         if (smem > 48 * 1024) SNP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, block, smem, st>>>(a);                                                                            \
     } while (0)
-    // pairs evaluated once per warp whenever the law is antisymmetric (see social_force_halved)
-    const bool half = !cta && !per_agent && !a.full_pair_loop && (SOC != 2 || a.symmetric);
-    if (cta) { if (per_agent) SNP_LAUNCH(true, true, false); else SNP_LAUNCH(true, false, false); }
-    else if (per_agent) SNP_LAUNCH(false, true, false);
+    if (cta) {
+        if (per_agent) SNP_LAUNCH(true, true, false);
+        else if (half) SNP_LAUNCH(true, false, true);
+        else SNP_LAUNCH(true, false, false);
+    } else if (per_agent) SNP_LAUNCH(false, true, false);
     else if (half) SNP_LAUNCH(false, false, true);
     else SNP_LAUNCH(false, false, false);
 #undef SNP_LAUNCH

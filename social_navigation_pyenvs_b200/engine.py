@@ -68,6 +68,7 @@ class CrowdEngine:
         # False (default): every unordered pair is evaluated once per warp (Newton's third law); True: every ordered pair in
         # j-ascending order, the reference's own accumulation order (forces.py:145-151).  Same result up to rounding.
         self.full_pair_loop = bool(full_pair_loop)
+        self.mapping = 0  # 0 auto, 1 force warp-packed, 2 force block-packed thread mapping (tests / tuning)
         self.params = model_parameters(model) if params is None else np.asarray(params, np.float64).reshape(20)
         kw = dict(dtype=dtype, device=self.device)
         self.dyn = torch.zeros((L.DYN_FIELDS, E, N), **kw)
@@ -144,7 +145,7 @@ class CrowdEngine:
         o.n_substeps, o.robot_mode, o.dt = int(n_substeps), int(robot_mode), float(dt)
         o.action = self.action.data_ptr()
         o.pre_checks, o.post_checks, o.track_touch = int(pre_checks), int(post_checks), int(track_touch)
-        o.reserved = 1 if self.full_pair_loop else 0
+        o.reserved = (1 if self.full_pair_loop else 0) | (self.mapping << 2)
         o.consts = (ctypes.c_double * 6)(*self.consts)
         o.time_now = self.time_now.data_ptr() if (advance_time or pre_checks) else None
         o.flags, o.checks = self.flags.data_ptr(), self.checks.data_ptr()

@@ -58,6 +58,37 @@ def test_shapes_vs_oracle(model, N, E):
     assert rel_err(eng.desired_force(), Dr, scale=100.0).max() < 1e-9
 
 
+@pytest.mark.parametrize("N,E", [(5, 203), (25, 37), (12, 50), (32, 11)])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_warp_packed_and_block_packed_mappings_agree(N, E, dtype):
+    """The same crowd through both thread mappings (envs tiling warps vs envs tiling a 128-thread CTA), with walls, robot, checks
+    and 10 fused sub-steps: states within rounding of each other and of the oracle, flags identical."""
+    from social_navigation_pyenvs_b200 import CrowdEngine, scenarios
+    S, G = _random_crowd(E, N, seed=N + E, spread=2.0)  # roomy crowd: 10 fused sub-steps must not amplify rounding chaotically
+    rob = np.zeros((E, 13)); rob[:, 0:2] = [-1.7, -1.7];  # clear of every human: a deep overlap makes the dynamics chaotic
+    rob[:, 3:5] = [0.2, -0.1]; rob[:, 8] = 0.3; rob[:, 9] = 80; rob[:, 10:12] = 5.0
+    S1 = np.concatenate([S, rob[:, None]], 1)
+    if dtype == torch.float32:
+        S1 = S1.astype(np.float32).astype(np.float64); G = G.astype(np.float32).astype(np.float64)
+    walls = scenarios.pack_walls([[[-2.0, -1.0], [-1.2, -1.0], [-1.2, 6.0], [-2.0, 6.0]]])
+    act = np.tile([0.2, -0.1], (E, 1))
+    out = []
+    for mapping in (1, 2):
+        eng = CrowdEngine.from_reference_arrays("hsfm_new_guo", S1, G, walls=walls, consider_robot=True, all_params_equal=True, dtype=dtype)
+        eng.mapping = mapping
+        eng.step(act, 0.0125, n_substeps=10, pre_checks=True, post_checks=True, track_touch=True)
+        out.append((eng.rows(S1), eng.flags.cpu().numpy().copy(), eng.checks.cpu().numpy().copy(), eng.robot.cpu().numpy().copy()))
+    tol = 1e-10 if dtype == torch.float64 else 2e-3
+    assert rel_err(out[0][0][:, :N, :8], out[1][0][:, :N, :8]).max() < tol
+    assert np.array_equal(out[0][1] & 0x7F, out[1][1] & 0x7F) and np.array_equal(out[0][2][:, :2], out[1][2][:, :2])   # pre-step flags / dmin / reward
+    assert np.array_equal(out[0][3], out[1][3])
+    if dtype == torch.float64:
+        cfg = OracleConfig(oracle.type_code("hsfm_new_guo"), True, True, False)
+        params = np.tile(oracle.default_params("hsfm_new_guo"), (E, N, 1))
+        ref, _, _ = oracle.update_humans(cfg, S1, G, walls, params, np.zeros((E, N + 1)), np.zeros((E, N, 2)), 0.0125, 10, robot_vel=act, n_threads=4)
+        assert rel_err(out[1][0][:, :N, :8], ref[:, :N, :8]).max() < 1e-9
+
+
 def test_per_env_walls_and_per_agent_params():
     from social_navigation_pyenvs_b200 import CrowdEngine, scenarios
     E, N = 37, 7
