@@ -21,6 +21,7 @@
  *                                                   social_nav_gym.py:107-118 check_actual_collisions_and_goal
  *   snp_laser / snp_laser_host                    <- src/sensors.py:53-69 LaserSensor.get_laser_measurements
  *                                                   (:24-33 circle, :35-51 segment), src/robot_agent.py:77-82
+ *   respawn option of snp_step                    <- motion_model_manager.py:407-422 (parallel-traffic post_update)
  *   snp_pack_states / snp_unpack_states           <- src/agent.py:256-266 get_safe_state / set_state row layout
  *   snp_large_step                                <- same update for one very large crowd (tiled all-pairs)
  */
@@ -107,6 +108,10 @@ typedef struct snp_step_opts {
     double *time_now;         /* optional [E] global_time; read by the reward, advanced by dt per sub-step */
     int32_t *flags;           /* [E] out, required when any check is on */
     double *checks;           /* [E][4] out: dmin (swept), reward, dmin (actual), unused */
+    double respawn_bounds[2]; /* (traffic_length / 2, traffic_height / 2)  (social_nav_sim.py:360) */
+    int32_t respawn;          /* parallel-traffic respawn after every sub-step (motion_model_manager.py:407-422): humans within 3 m of
+                                 their goal restart at the right end; rewrites goals[0], goal_cnt (N <= 32 only) */
+    int32_t reserved2;
 } snp_step_opts;
 
 typedef struct snp_laser_args {

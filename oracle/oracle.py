@@ -44,7 +44,7 @@ def default_params(title: str) -> np.ndarray:
 
 class _Cfg(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int) for k in ("type", "n", "g", "n_walls", "n_segs", "consider_robot", "symmetric",
-                                             "numba_compat", "walls_per_env")]
+                                             "numba_compat", "walls_per_env", "respawn")] + [("respawn_bounds", ctypes.c_double * 2)]
 
 
 @dataclass
@@ -53,6 +53,7 @@ class OracleConfig:
     consider_robot: bool = False
     symmetric: bool = True
     numba_compat: bool = False
+    respawn_bounds: tuple = None  # (traffic_length/2, traffic_height/2): parallel-traffic respawn after every update (mmm:407-422)
 
 
 _lib = None
@@ -102,7 +103,9 @@ def update_humans(cfg: OracleConfig, states, goals, walls, params, safety, desir
         walls_c = _c(walls)
         per_env = int(walls_c.ndim == 5)
         W, S = walls_c.shape[-4], walls_c.shape[-3]
-    c = _Cfg(cfg.type, n, goals.shape[2], W, S, int(cfg.consider_robot), int(cfg.symmetric), int(cfg.numba_compat), per_env)
+    rb = cfg.respawn_bounds
+    c = _Cfg(cfg.type, n, goals.shape[2], W, S, int(cfg.consider_robot), int(cfg.symmetric), int(cfg.numba_compat), per_env,
+             int(rb is not None), (ctypes.c_double * 2)(*(rb if rb is not None else (0.0, 0.0))))
     forces = np.zeros((E, n, 9)) if want_forces else None
     rv = None if robot_vel is None else _c(robot_vel)
     lib.orc_update_humans(ctypes.byref(c), E, _dp(states), _dp(goals), _dp(walls_c), _dp(params), _dp(safety), _dp(desired),

@@ -42,6 +42,8 @@ typedef struct {
     int symmetric;      /* all_equal_humans -> compute_all_social_forces (mmm:455-457) */
     int numba_compat;   /* 0: serial semantics (the oracle of record); 1: forces_parallel.py semantics */
     int walls_per_env;  /* 0: one wall set shared by all envs; 1: walls[E][W][S][2][2] */
+    int respawn;        /* parallel-traffic respawn after every update (mmm:407-422) */
+    double respawn_bounds[2]; /* (traffic_length / 2, traffic_height / 2)  (sim:360) */
 } orc_cfg;
 
 /* src/utils.py:7-13 (Python float %: result takes the sign of the divisor; here dividend and
@@ -278,6 +280,32 @@ static void update_env(const orc_cfg *c, double *st, double *goals, const double
             double cs = cos(a[2]), sn = sin(a[2]);
             a[3] = np_mv(fm, cs, -sn, a[5], a[6]);
             a[4] = np_mv(fm, sn, cs, a[5], a[6]);
+        }
+    }
+    /* ---- post_update: parallel-traffic respawn (mmm:407-422), sequential in index order: the max runs over the humans as
+     * already moved / respawned so far.  The goal list becomes the single goal (gx, new y) (mmm:418). ---- */
+    if (c->respawn) {
+        for (int i = 0; i < n; ++i) {
+            double *a = st + NS * i;
+            double *gl = goals + (size_t)i * c->g * 2;
+            if (np_norm(1, a[0] - gl[0], a[1] - gl[1]) < 3) {
+                double xmax = -INFINITY, rsmax = -INFINITY;
+                for (int k = 0; k < n; ++k) {
+                    if (st[NS * k] > xmax) xmax = st[NS * k];
+                    if (st[NS * k + 8] + safety[k] > rsmax) rsmax = st[NS * k + 8] + safety[k];
+                }
+                if (c->consider_robot) {
+                    if (st[NS * n] > xmax) xmax = st[NS * n];
+                    if (st[NS * n + 8] + safety[n] > rsmax) rsmax = st[NS * n + 8] + safety[n];
+                }
+                double nx = xmax + rsmax * 2;
+                a[0] = nx > c->respawn_bounds[0] ? nx : c->respawn_bounds[0];
+                if (a[1] >= 0) a[1] = a[1] < c->respawn_bounds[1] ? a[1] : c->respawn_bounds[1];
+                else a[1] = a[1] > -c->respawn_bounds[1] ? a[1] : -c->respawn_bounds[1];
+                gl[1] = a[1];
+                for (int k = 1; k < c->g; ++k) { gl[2 * k] = NAN; gl[2 * k + 1] = NAN; }
+                a[10] = gl[0]; a[11] = gl[1];
+            }
         }
     }
 }

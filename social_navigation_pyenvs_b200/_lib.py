@@ -31,7 +31,8 @@ class SnpStepOpts(ctypes.Structure):
     _fields_ = [("type", c_int32), ("consider_robot", c_int32), ("symmetric", c_int32), ("numba_compat", c_int32),
                 ("n_substeps", c_int32), ("robot_mode", c_int32), ("dt", c_double), ("action", c_void_p),
                 ("pre_checks", c_int32), ("post_checks", c_int32), ("track_touch", c_int32), ("reserved", c_int32),
-                ("consts", c_double * 6), ("time_now", c_void_p), ("flags", c_void_p), ("checks", c_void_p)]
+                ("consts", c_double * 6), ("time_now", c_void_p), ("flags", c_void_p), ("checks", c_void_p),
+                ("respawn_bounds", c_double * 2), ("respawn", c_int32), ("reserved2", c_int32)]
 
 
 class SnpLaserArgs(ctypes.Structure):

@@ -60,6 +60,8 @@ template <typename T> static int build_args(const snp_crowd *c, const snp_step_o
     a.pre_checks = o->pre_checks; a.post_checks = o->post_checks; a.track_touch = o->track_touch;
     for (int k = 0; k < 6; ++k) a.consts[k] = o->consts[k];
     a.time_now = o->time_now; a.flags = o->flags; a.checks = o->checks;
+    a.respawn = o->respawn; a.respawn_bounds[0] = o->respawn_bounds[0]; a.respawn_bounds[1] = o->respawn_bounds[1];
+    if (o->respawn && c->N > 32) { set_error("parallel-traffic respawn is implemented for crowds of at most 32 humans per env"); return SNP_ERR_UNSUPPORTED; }
     a.epw = 1; a.gpb = 1;
     a.mapping = (o->reserved >> 2) & 3;  // bits 2-3 of `reserved`: thread mapping override (tests / tuning)
     a.full_pair_loop = o->reserved & 1;  // bit 0 of `reserved`: SNP_OPT_FULL_PAIR_LOOP

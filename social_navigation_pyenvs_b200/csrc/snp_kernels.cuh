@@ -41,6 +41,8 @@ template <typename T> struct KArgs {
     int *flags;
     double *checks;
     int epw;  // envs per warp (warp-packed kernel)
+    int respawn;              // parallel-traffic respawn after every sub-step (mmm:407-422)
+    double respawn_bounds[2];
     int gpb;  // env groups per block (block-packed kernel)
     int mapping;  // 0 auto, 1 warp-packed, 2 block-packed
     int full_pair_loop;  // 1: always evaluate ordered pairs in j-ascending order (the reference's accumulation order)

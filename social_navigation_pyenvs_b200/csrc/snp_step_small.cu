@@ -96,6 +96,15 @@ __device__ __forceinline__ double seg_min(double v, int i, int n, unsigned mask)
 // needs (N-1)/2 evaluations per lane instead of N-1 (for even N the antipodal pair is evaluated by both ends).  Valid when the
 // law is antisymmetric: uniform parameters, and for Moussaid the reference's symmetric path (lower index is agent 1,
 // forces.py:145-151).  Accumulation order differs from the reference's j-ascending order (rounding-level effect only).
+// Segmented max over the lanes [gbase, gbase + n) of a warp, broadcast to every lane of the group.
+template <typename T> __device__ __forceinline__ T seg_max_bcast(T v, int i, int n, int gbase, unsigned mask) {
+    for (int off = 1; off < n; off <<= 1) {
+        const T o = __shfl_down_sync(mask, v, off);
+        if (i + off < n) v = o > v ? o : v;
+    }
+    return __shfl_sync(mask, v, gbase);
+}
+
 template <typename T, int SOC>
 __device__ __forceinline__ void social_force_halved(const Params<T> &P, const double *tbl, const EntView<T> ents, const T *rs_g, const Agent<T> &me,
                                                     int i, int N, bool with_robot, unsigned wmask, int gbase, T &fsx, T &fsy) {
@@ -416,6 +425,46 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
         if (live) {
             desired_force<T>(P, me, a.numba != 0);
             integrate<T, HEADED>(P, me, fox, foy, fsx, fsy, dt);
+        }
+        if constexpr (!CTA) {
+            // post_update: parallel-traffic respawn (mmm:407-422).  Rare, so the warp first votes; pending humans are then handled
+            // one index at a time per env group (the reference's loop is sequential: the max runs over already respawned humans).
+            if (a.respawn) {
+                const int gbase = lane - i;
+                const unsigned gm = (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) << gbase;
+                unsigned pending = __ballot_sync(wmask, np_norm(me.px - me.gx, me.py - me.gy) < T(3));
+                if (pending) {
+                    T rsmax = seg_max_bcast<T>(me.rs, i, N, gbase, wmask);
+                    if (a.consider_robot) rsmax = rrs > rsmax ? rrs : rsmax;
+                    while (pending) {
+                        const unsigned mine = pending & gm;
+                        const int r = mine ? (__ffs(mine) - 1 - gbase) : -1;  // lowest pending index of my group
+                        T xmax = seg_max_bcast<T>(me.px, i, N, gbase, wmask);
+                        if (a.consider_robot) xmax = rpx > xmax ? rpx : xmax;
+                        if (i == r) {
+                            const T nx = fma_<T>(rsmax, T(2), xmax);
+                            me.px = nx > (T)a.respawn_bounds[0] ? nx : (T)a.respawn_bounds[0];
+                            const T by = (T)a.respawn_bounds[1];
+                            me.py = me.py >= T(0) ? (me.py < by ? me.py : by) : (me.py > -by ? me.py : -by);
+                            me.gy = me.py;  // human.set_goals([[goals[0][0], position[1]]])  (mmm:418)
+                            gidx = 0; gcnt = 1;
+                            const_cast<T *>(a.goals)[(size_t)0 * EN + aidx] = me.gx;
+                            const_cast<T *>(a.goals)[(size_t)1 * EN + aidx] = me.gy;
+                            const_cast<int *>(a.goal_cnt)[aidx] = 1;
+                        }
+                        unsigned clear = 0;  // every group retires its lowest pending index
+                        for (unsigned rest = pending; rest;) {
+                            const int b = __ffs(rest) - 1;
+                            const int gb = b - (b % N);  // groups start at multiples of N within the warp
+                            clear |= 1u << b;
+                            rest &= ~(((N >= 32 ? 0xffffffffu : ((1u << N) - 1u))) << gb);
+                        }
+                        pending &= ~clear;
+                    }
+                }
+            }
+        }
+        if (live) {
             if (a.track_touch && has_robot)
                 touched |= xnorm_np((double)me.px - (double)rpx, (double)me.py - (double)rpy) < __dadd_rn((double)me.r, (double)rr);
         }

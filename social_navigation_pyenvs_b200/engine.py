@@ -68,6 +68,7 @@ class CrowdEngine:
         # False (default): every unordered pair is evaluated once per warp (Newton's third law); True: every ordered pair in
         # j-ascending order, the reference's own accumulation order (forces.py:145-151).  Same result up to rounding.
         self.full_pair_loop = bool(full_pair_loop)
+        self.respawn_bounds = None  # (traffic_length/2, traffic_height/2): parallel-traffic respawn after every update (mmm:407-422)
         self.mapping = 0  # 0 auto, 1 force warp-packed, 2 force block-packed thread mapping (tests / tuning)
         self.params = model_parameters(model) if params is None else np.asarray(params, np.float64).reshape(20)
         kw = dict(dtype=dtype, device=self.device)
@@ -139,7 +140,8 @@ class CrowdEngine:
         c.W, c.S, c.walls_per_env = self.W, self.S, self.walls_per_env
         return c
 
-    def _opts(self, dt, n_substeps, robot_mode=0, pre_checks=False, post_checks=False, track_touch=False, advance_time=False):
+    def _opts(self, dt, n_substeps, robot_mode=0, pre_checks=False, post_checks=False, track_touch=False, advance_time=False,
+              post_update=True):
         o = L.SnpStepOpts()
         o.type, o.consider_robot, o.symmetric, o.numba_compat = self.type, int(self.consider_robot), int(self.symmetric), int(self.numba_compat)
         o.n_substeps, o.robot_mode, o.dt = int(n_substeps), int(robot_mode), float(dt)
@@ -149,6 +151,9 @@ class CrowdEngine:
         o.consts = (ctypes.c_double * 6)(*self.consts)
         o.time_now = self.time_now.data_ptr() if (advance_time or pre_checks) else None
         o.flags, o.checks = self.flags.data_ptr(), self.checks.data_ptr()
+        if self.respawn_bounds is not None and n_substeps > 0 and post_update:
+            o.respawn = 1
+            o.respawn_bounds = (ctypes.c_double * 2)(*self.respawn_bounds)
         return o
 
     # ------------------------------------------------------------------ loading / reading in the reference's layouts
@@ -209,7 +214,7 @@ class CrowdEngine:
     # ------------------------------------------------------------------ the hot path
     def update_humans(self, t=0.0, dt=0.0125, post_update=True, n_substeps=1):
         """MotionModelManager.update_humans (motion_model_manager.py:354) for every env: `n_substeps` Euler updates in one launch."""
-        L.check(self.lib.snp_step(ctypes.byref(self._crowd()), ctypes.byref(self._opts(dt, n_substeps)), _stream()))
+        L.check(self.lib.snp_step(ctypes.byref(self._crowd()), ctypes.byref(self._opts(dt, n_substeps, post_update=post_update)), _stream()))
 
     def step(self, action=None, dt=0.0125, n_substeps=20, pre_checks=True, post_checks=False, track_touch=False):
         """SocialNavGym.step for every env (social_nav_gym.py:227-250): swept collision / goal test and reward on the current

@@ -101,18 +101,22 @@ class MotionModelManager:
             h.linear_velocity, h.body_velocity = out[i, 3:5].copy(), out[i, 5:7].copy()
             h.angular_velocity = float(out[i, 7])
             h.desired_force = df[i].copy()
-            if not np.array_equal(np.array(h.goals[0], np.float64), out[i, 10:12]):  # mmm:364-367
-                goal = h.goals[0]
-                h.goals.remove(goal)
-                h.goals.append(goal)
+            if not np.array_equal(np.array(h.goals[0], np.float64), out[i, 10:12]):
+                if any(np.array_equal(np.array(g, np.float64), out[i, 10:12]) for g in h.goals):  # goal reached: rotate (mmm:364-367)
+                    goal = h.goals[0]
+                    h.goals.remove(goal)
+                    h.goals.append(goal)
+                else:                                                                          # respawn: new single goal (mmm:418)
+                    h.goals = [[float(out[i, 10]), float(out[i, 11])]]
 
     # ------------------------------------------------------------------ the hot path (mmm:354-373)
     def update_humans(self, t, dt, post_update=True):
         eng, rows = self._sync_engine()
-        eng.update_humans(t, dt)
+        # parallel-traffic respawn (mmm:407-422) runs inside the kernel; the caller sets parallel_traffic_humans_respawn and
+        # respawn_bounds exactly like social_nav_sim.py:184-186 does
+        eng.respawn_bounds = tuple(self.respawn_bounds) if (post_update and self.parallel_traffic_humans_respawn) else None
+        eng.update_humans(t, dt, post_update=post_update)
         self._write_back(eng, rows)
-        if post_update and self.parallel_traffic_humans_respawn:
-            raise NotImplementedError("parallel-traffic respawn (mmm:407-422) is listed as NEXT in SURVEY.md 8(f)")
 
     # ------------------------------------------------------------------ state accessors (mmm:285-352)
     def get_human_states(self, include_goal=True, headed=False):

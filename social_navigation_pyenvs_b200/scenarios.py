@@ -152,6 +152,40 @@ def ccso_synthetic(E, N=25, seed0=2000, circle_radius=7.0, robot_radius=0.3, mas
                 robot=robot_rows(E, circle_radius, robot_radius))
 
 
+def _pt_env(e, N, seed0, traffic_length, traffic_height, robot_radius, mass):
+    rs = np.random.RandomState(seed0 + e)
+    st, gl = np.zeros((N, 13)), np.zeros((N, 1, 2))
+    robot_pos = np.array([-(traffic_length / 2) + 1, 0.0])
+    placed = []
+    for i in range(N):
+        while True:
+            a, b = -(traffic_length / 2) + 0.3, traffic_length / 2 - 0.3
+            pos = np.array([(b - a) * rs.random_sample() + a, (rs.random_sample() - 0.5) * traffic_height])
+            if any(np.linalg.norm(pos - o) - 0.3 - 0.3 - 0.1 < 0 for o in placed):
+                continue
+            if np.linalg.norm(pos - robot_pos) - 0.3 - robot_radius - 0.1 < 0:
+                continue
+            break
+        placed.append(pos)
+        goal = [-(traffic_length / 2) - 3, pos[1]]
+        st[i] = _state_row(pos, bound_angle(-math.pi), 0.3, mass, goal, 1.0)
+        gl[i, 0] = goal
+    return st, gl
+
+
+def parallel_traffic(E, N, seed0=2000, traffic_length=14.0, traffic_height=3.0, robot_radius=0.3, mass=75.0):
+    """Parallel-traffic scenario (social_nav_sim.py:301-362, insert_robot=True): humans walk towards x = -L/2 - 3 and are respawned
+    at the right end when they get within 3 m of it (motion_model_manager.py:407-422).  Returns states, goals [E,N,1,2], robot rows
+    and `respawn_bounds` = (L/2, H/2)."""
+    res = _map_envs(_pt_env, E, (N, seed0, traffic_length, traffic_height, robot_radius, mass))
+    robot = np.zeros((E, 13))
+    robot[:, 0] = -(traffic_length / 2) + 1
+    robot[:, 8], robot[:, 9], robot[:, 12] = robot_radius, 80.0, 1.0
+    robot[:, 10] = (traffic_length / 2) - 1
+    return dict(states=np.stack([r[0] for r in res]), goals=np.stack([r[1] for r in res]), robot=robot,
+                respawn_bounds=(traffic_length / 2, traffic_height / 2))
+
+
 def jittered_grid_crowd(n_side, pitch=2.0, jitter=0.5, seed=0, mass=75.0):
     """n_side x n_side jittered grid, every goal mirrored through the crowd centre (G = 2)."""
     rs = np.random.RandomState(seed)

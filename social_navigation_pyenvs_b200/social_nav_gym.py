@@ -29,6 +29,7 @@ class BatchedSocialNavGym:
         self.success_reward, self.collision_penalty, self.discomfort_dist, self.discomfort_penalty_factor = 1.0, -0.25, 0.2, 0.5
         self.human_policy, self.human_num, self.circle_radius, self.robot_radius = "hsfm_farina", 5, 7.0, 0.3
         self.train_val_sim = self.test_sim = "circle_crossing"
+        self.traffic_length, self.traffic_height = 14.0, 3.0
         self.robot_visible = False
         self.walls = None
 
@@ -45,6 +46,7 @@ class BatchedSocialNavGym:
             self.robot_visible = config.getboolean("robot", "visible")
             self.train_val_sim, self.test_sim = config.get("sim", "train_val_sim"), config.get("sim", "test_sim")
             self.circle_radius, self.human_num = config.getfloat("sim", "circle_radius"), config.getint("sim", "human_num")
+            self.traffic_length, self.traffic_height = config.getfloat("sim", "traffic_length"), config.getfloat("sim", "traffic_height")
         else:
             for k, v in config.items():
                 setattr(self, k, v)
@@ -69,8 +71,10 @@ class BatchedSocialNavGym:
             sc = scenarios.circular_crossing(self.E, self.human_num, seed0, self.circle_radius, self.robot_radius)
         elif sim == "circular_crossing_with_static_obstacles":
             sc = scenarios.ccso_synthetic(self.E, self.human_num, seed0, self.circle_radius, self.robot_radius)
+        elif sim == "parallel_traffic":
+            sc = scenarios.parallel_traffic(self.E, self.human_num, seed0, self.traffic_length, self.traffic_height, self.robot_radius)
         else:
-            raise NotImplementedError(f"scenario {sim}: parallel traffic / hybrid are listed as NEXT in SURVEY.md 8(f)")
+            raise NotImplementedError(f"scenario {sim}: the hybrid scenario mixes generators per env (social_nav_gym.py:155-167)")
         self.case_counter[phase] += self.E
         robot = sc["robot"].copy()
         robot[:, 3:5] = 0.0                                                      # robot.set(..., vx=0, vy=0) (social_nav_gym.py:213)
@@ -78,6 +82,7 @@ class BatchedSocialNavGym:
         self.engine = CrowdEngine.from_reference_arrays(self.human_policy, states, sc["goals"], walls=self.walls, consider_robot=self.robot_visible,
                                                         all_params_equal=True, dtype=self.dtype, device=self.device,
                                                         robot=None if self.robot_visible else robot)
+        self.engine.respawn_bounds = sc.get("respawn_bounds")   # parallel traffic: respawn at the right end (mmm:407-422)
         self.engine.consts = [float(self.time_limit), self.collision_penalty, self.success_reward, self.discomfort_dist,
                               self.discomfort_penalty_factor, self.robot_time_step]
         if self.safety_space > 0:

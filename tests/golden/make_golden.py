@@ -220,6 +220,32 @@ def traj_cases():
         run_traj(sim, f"cc25_robot_{model}", 60, 20, robot_vel=(0.0, 1.0), dense_first=5)
 
 
+def pt_sim(model, seed, n, robot_visible):
+    np.random.seed(seed)
+    sim = SocialNavSim({"insert_robot": True, "human_policy": model, "headless": True, "runge_kutta": False, "robot_visible": robot_visible,
+                        "robot_radius": 0.3, "traffic_length": 14, "traffic_height": 3, "n_actors": n, "randomize_human_attributes": False},
+                       scenario="parallel_traffic", parallelize_humans=False)
+    sim.set_time_step(DT)
+    return sim
+
+
+def pt_cases():
+    """Parallel-traffic scenario with the respawn of humans that reach the left end (motion_model_manager.py:407-422,
+    social_nav_sim.py:301-362).  The fixtures carry `respawn` = respawn_bounds; the goal columns change at every respawn."""
+    for model, seed, n, vis in [("hsfm_farina", 2004, 5, True), ("sfm_helbing", 2011, 7, False), ("hsfm_new_guo", 1003, 5, True),
+                                ("sfm_guo", 77, 10, True)]:
+        sim = pt_sim(model, seed, n, vis)
+        assert sim.motion_model_manager.parallel_traffic_humans_respawn
+        name = f"pt{n}_{'robot_' if vis else ''}{model}"
+        run_traj(sim, name, 1600, 50, robot_vel=(0.5, 0.0), dense_first=5)
+        path = os.path.join(HERE, f"traj_{name}.npz")
+        d = dict(np.load(path))
+        d["respawn"] = np.array(sim.motion_model_manager.respawn_bounds, np.float64)
+        np.savez_compressed(path, **d)
+        gy = d["traj"][:, :, 9]
+        print("   respawns seen:", int((np.diff(gy, axis=0) != 0).sum()))
+
+
 def numba_cases():
     """Second witness: the reference's Numba operator update_humans_parallel (forces_parallel.py:184)."""
     out = {}
@@ -434,9 +460,11 @@ def gym_case():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["traj", "numba", "peek", "flags", "laser", "gym"]
+    which = sys.argv[1:] or ["traj", "pt", "numba", "peek", "flags", "laser", "gym"]
     if "traj" in which:
         traj_cases()
+    if "pt" in which:
+        pt_cases()
     if "numba" in which:
         numba_cases()
     if "peek" in which:

@@ -17,6 +17,7 @@ def load_traj(name):
     d["name"] = name
     d["consider_robot"], d["all_equal"] = bool(d["flags"][0]), bool(d["flags"][1])
     d["n"] = d["states0"].shape[0]
+    d["respawn_bounds"] = tuple(float(x) for x in d["respawn"]) if "respawn" in d else None
     return d
 
 
@@ -47,7 +48,11 @@ def inputs_at(d, k):
     S = d["states0"].copy()
     S[:, :8] = row[:, :8]
     S[:, 10:12] = row[:, 8:10]
-    G = rotate_goals_to(d["goals0"], row[:, 8:10])
+    if d.get("respawn_bounds") is not None:  # parallel traffic: a respawn replaces the goal list by the single recorded goal
+        G = np.full_like(d["goals0"], np.nan)
+        G[:, 0] = row[:, 8:10]
+    else:
+        G = rotate_goals_to(d["goals0"], row[:, 8:10])
     if d["consider_robot"]:
         rb = d["robot0"].copy()
         rb[0:2] = d["robot_traj"][k]

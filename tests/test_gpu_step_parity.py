@@ -23,6 +23,7 @@ def _engine(d, S, G, D, dtype, numba=False):
                                             safety=d["safety"][None, : S.shape[0]], consider_robot=d["consider_robot"],
                                             all_params_equal=d["all_equal"], numba_compat=numba, dtype=dtype)
     eng.set_desired_force(D[None])
+    eng.respawn_bounds = d.get("respawn_bounds")
     return eng
 
 
@@ -46,7 +47,7 @@ def test_single_step_vs_reference_golden(name, dtype):
         if dtype == torch.float64:
             ref = d["traj"][k + 1]
         else:  # fp32 inputs were rounded, so the reference value is the oracle on the same rounded inputs
-            cfg = OracleConfig(int(d["type"]), d["consider_robot"], d["all_equal"], False)
+            cfg = OracleConfig(int(d["type"]), d["consider_robot"], d["all_equal"], False, d.get("respawn_bounds"))
             S2, _, D2 = oracle.update_humans(cfg, S[None], G[None], d["walls"], d["params"][None], d["safety"][None, : S.shape[0]],
                                              D[None], float(d["dt"]), 1)
             ref = observed(S2[0], D2[0], n)
@@ -108,6 +109,35 @@ def test_halved_and_full_pair_loops_agree(name):
         out.append(observed(eng.rows(S[None])[0], eng.desired_force()[0], n))
         assert rel_err(out[-1][:, :10], d["traj"][k + 1][:, :10]).max() < 1e-9
     assert rel_err(out[0][:, :10], out[1][:, :10]).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["pt5_robot_hsfm_farina", "pt7_sfm_helbing", "pt5_robot_hsfm_new_guo", "pt10_robot_sfm_guo"])
+def test_parallel_traffic_with_respawn_full_trajectory(name):
+    """1600 fused sub-steps of the parallel-traffic scenario with 5-11 respawns (mmm:407-422) against the recorded reference:
+    positions jump to the right end, the goal list collapses to (gx, new y) -- all inside the kernel."""
+    d = load_traj(name)
+    n = d["n"]
+    S, G, D, rv = inputs_at(d, 0)
+    eng = _engine(d, S, G, D, torch.float64)
+    if eng.robot is not None:
+        eng.action.copy_(torch.as_tensor(rv[:, None]))
+    cur, jumps = 0, 0
+    for k, s_ in enumerate(d["steps"]):
+        if s_ > cur:
+            if d["consider_robot"]:
+                eng.step(None, float(d["dt"]), n_substeps=int(s_ - cur), pre_checks=False)
+            else:
+                eng.update_humans(0.0, float(d["dt"]), n_substeps=int(s_ - cur))
+            cur = s_
+        got = observed(eng.rows(S[None])[0], eng.desired_force()[0], n)
+        ref = d["traj"][k]
+        assert rel_err(got[:, :10], ref[:, :10]).max() < 1e-7, (name, int(s_))
+        # (the respawned goal is (gx, new y): y inherits the 1e-15 rounding history of the GPU trajectory unless it was clamped)
+        if k:
+            jumps += int((ref[:, 0] - d["traj"][k - 1][:, 0] > 5).sum())
+    assert jumps >= 5
+    # a peek (post_update=False) never respawns
+    eng.get_next_human_observable_states(0.25)
 
 
 def test_numba_semantics_operator():

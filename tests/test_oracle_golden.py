@@ -19,7 +19,7 @@ TOL_MOUSSAID_AT_REST = 1e-6
 
 
 def _cfg(d, numba=False):
-    return OracleConfig(int(d["type"]), d["consider_robot"], d["all_equal"], numba)
+    return OracleConfig(int(d["type"]), d["consider_robot"], d["all_equal"], numba, d.get("respawn_bounds"))
 
 
 @pytest.mark.parametrize("name", traj_names())
@@ -85,6 +85,15 @@ def test_goal_rotation_and_stale_desired_force_are_exercised():
     dist = np.linalg.norm(last[:, 8:10] - last[:, 0:2], axis=1)
     inside = dist <= 0.3
     assert inside.any() and np.abs(last[inside, 10:12]).max() > 0           # inside the radius, force not zeroed
+
+
+def test_parallel_traffic_respawn_is_exercised():
+    """The pt* fixtures must contain respawns (goal y and position x jump) so that mmm:407-422 is really pinned."""
+    for name in [n for n in traj_names() if n.startswith("pt")]:
+        d = load_traj(name)
+        assert d["respawn_bounds"] == (7.0, 1.5)
+        jumps = np.diff(d["traj"][:, :, 0], axis=0) > 5.0
+        assert jumps.sum() >= 5, name
 
 
 def test_numba_operator_semantics():

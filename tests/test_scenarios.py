@@ -25,6 +25,15 @@ def test_circular_crossing_replays_the_reference_generator():
     assert np.array_equal(sc["robot"][0, [0, 1, 2, 8, 9, 10, 11, 12]], d["robot0"][[0, 1, 2, 8, 9, 10, 11, 12]])
 
 
+def test_parallel_traffic_replays_the_reference_generator():
+    for name, seed, n in [("pt5_robot_hsfm_farina", 2004, 5), ("pt7_sfm_helbing", 2011, 7), ("pt10_robot_sfm_guo", 77, 10)]:
+        d = load_traj(name)
+        sc = scenarios.parallel_traffic(1, n, seed0=seed)
+        assert np.array_equal(sc["states"][0], d["states0"]) and np.array_equal(sc["goals"][0], d["goals0"]), name
+        assert sc["respawn_bounds"] == d["respawn_bounds"]
+        assert np.array_equal(sc["robot"][0, [0, 1, 2, 8, 9, 10, 11, 12]], d["robot0"][[0, 1, 2, 8, 9, 10, 11, 12]])
+
+
 def test_batches_are_seeded_per_env_and_pool_path_matches_serial_path():
     a = scenarios.circular_crossing(3, 5, seed0=2000)
     b = scenarios.circular_crossing(1, 5, seed0=2002)
