@@ -67,6 +67,9 @@ def _load():
         _lib.orc_update_humans.argtypes = [ctypes.POINTER(_Cfg), ctypes.c_int, dp, dp, dp, dp, dp, dp, ctypes.c_double,
                                            ctypes.c_int, dp, dp, ctypes.c_int]
         _lib.orc_update_humans.restype = None
+        _lib.orc_imitation_steps.argtypes = [ctypes.POINTER(_Cfg), ctypes.c_int, dp, dp, dp, dp, dp, dp, ctypes.c_double, ctypes.c_int, dp, dp,
+                                             ctypes.c_int, dp, dp, ctypes.c_int, dp, ctypes.c_int]
+        _lib.orc_imitation_steps.restype = None
         _lib.orc_checks.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, dp, dp]
         _lib.orc_checks.restype = None
         _lib.orc_laser.argtypes = [ctypes.c_int] * 5 + [dp, dp, dp, ctypes.c_double, ctypes.c_int, ctypes.c_double, dp,
@@ -113,6 +116,34 @@ def update_humans(cfg: OracleConfig, states, goals, walls, params, safety, desir
     if want_forces:
         return states, goals, desired, forces
     return states, goals, desired
+
+
+def imitation_steps(cfg: OracleConfig, states, goals, walls, params, safety, desired, dt, n_steps, robot, robot_goals, robot_desired,
+                    robot_params, robot_type, robot_safety=None, n_threads=1):
+    """n_steps x (update_robot; update_humans) -- the sub-step loop of SocialNavGym.imitation_learning_step (gym:260-265).
+    robot [E,13], robot_goals [E,RG,2], robot_desired [E,2], robot_params [20].  Returns new (states, goals, desired, robot,
+    robot_goals, robot_desired)."""
+    lib = _load()
+    states, goals, desired = _c(states).copy(), _c(goals).copy(), _c(desired).copy()
+    robot, robot_goals, robot_desired = _c(robot).copy(), _c(robot_goals).copy(), _c(robot_desired).copy()
+    params, safety = _c(params), _c(safety)
+    E, rows, _ = states.shape
+    n = goals.shape[1]
+    assert rows == n + int(cfg.consider_robot)
+    if walls is None or np.size(walls) == 0 or walls.shape[-4] == 0:
+        W, S, per_env, walls_c = 0, 1, 0, np.zeros(4)
+    else:
+        walls_c = _c(walls)
+        per_env = int(walls_c.ndim == 5)
+        W, S = walls_c.shape[-4], walls_c.shape[-3]
+    rb = cfg.respawn_bounds
+    c = _Cfg(cfg.type, n, goals.shape[2], W, S, int(cfg.consider_robot), int(cfg.symmetric), int(cfg.numba_compat), per_env,
+             int(rb is not None), (ctypes.c_double * 2)(*(rb if rb is not None else (0.0, 0.0))))
+    rsaf = np.zeros(E) if robot_safety is None else _c(robot_safety)
+    lib.orc_imitation_steps(ctypes.byref(c), E, _dp(states), _dp(goals), _dp(walls_c), _dp(params), _dp(safety), _dp(desired), float(dt),
+                            int(n_steps), _dp(robot), _dp(robot_goals), robot_goals.shape[1], _dp(robot_desired), _dp(_c(robot_params)),
+                            int(robot_type), _dp(rsaf), int(n_threads))
+    return states, goals, desired, robot, robot_goals, robot_desired
 
 
 def checks(states, n_humans, robot, action, time_now, consts):

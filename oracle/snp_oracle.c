@@ -341,6 +341,92 @@ void orc_update_humans(const orc_cfg *c, int E, double *states, double *goals, c
     }
 }
 
+/* One update_robot call (mmm:593-653, Euler, just_velocities=False): the robot moves by its own SFM / HSFM model.
+ * rb: the robot's 13-wide row, rgoals: [rg][2] goal list (rotated in place), rdes: carried desired force [2],
+ * rp: the robot's 20 parameters, rtype: its model (0..8), rs: its safety space.  Humans exert force on it through the
+ * per-agent path compute_social_force_*(index = len(humans), ..., consider_robot = False) (mmm:608, forces.py:153-218). */
+static void update_robot_env(const orc_cfg *c, double *rb, double *rgoals, int rg, double *rdes, const double *rp, int rtype, double rs,
+                             const double *st, const double *safety, const double *walls, double dt, double *scratch) {
+    const int n = c->n, W = c->n_walls, fm = 1;
+    const int soc = rtype % 3, obs = (rtype == 1 || rtype == 4 || rtype == 7) ? 1 : 0, headed = rtype / 3;
+    double *cp = scratch;
+    if (np_norm(fm, rgoals[0] - rb[0], rgoals[1] - rb[1]) < rb[8]) { /* mmm:598 update_goals(robot) */
+        int cnt = 0;
+        while (cnt < rg && !isnan(rgoals[2 * cnt])) ++cnt;
+        double g0 = rgoals[0], g1 = rgoals[1];
+        for (int k = 0; k + 1 < cnt; ++k) { rgoals[2 * k] = rgoals[2 * k + 2]; rgoals[2 * k + 1] = rgoals[2 * k + 3]; }
+        if (cnt > 0) { rgoals[2 * (cnt - 1)] = g0; rgoals[2 * (cnt - 1) + 1] = g1; }
+    }
+    rb[10] = rgoals[0]; rb[11] = rgoals[1];
+    for (int w = 0; w < W; ++w) closest_point(walls + (size_t)w * c->n_segs * 4, c->n_segs, rb[0], rb[1], 0, &cp[2 * w], &cp[2 * w + 1]);
+    double cs = 1.0, sn = 0.0;
+    if (headed) { /* mmm:605 */
+        cs = cos(rb[2]); sn = sin(rb[2]);
+        rb[3] = np_mv(fm, cs, -sn, rb[5], rb[6]);
+        rb[4] = np_mv(fm, sn, cs, rb[5], rb[6]);
+    }
+    double dx = rb[10] - rb[0], dy = rb[11] - rb[1];
+    double dist = np_norm(fm, dx, dy);
+    if (dist > rb[8]) {
+        rdes[0] = rb[9] * ((dx / dist) * rb[12] - rb[3]) / rp[P_RELAX];
+        rdes[1] = rb[9] * ((dy / dist) * rb[12] - rb[4]) / rp[P_RELAX];
+    }
+    double fo[2];
+    obstacle_force(obs, 0, rb, rs, rp, cp, W, fo);
+    double fs0 = 0.0, fs1 = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double f[2];
+        pair_force(soc, fm, rb, rs, st + NS * j, safety[j], rp, f);
+        fs0 += f[0]; fs1 += f[1];
+    }
+    rb[0] += rb[3] * dt; rb[1] += rb[4] * dt;
+    if (!headed) { /* mmm:609,628 */
+        double g0 = rdes[0] + fo[0] + fs0, g1 = rdes[1] + fo[1] + fs1;
+        rb[3] += (g0 / rb[9]) * dt; rb[4] += (g1 / rb[9]) * dt;
+        clip_norm(fm, &rb[3], &rb[4], rb[12]);
+    } else { /* mmm:611-613,629 */
+        double inertia = 0.5 * rb[9] * rb[8] * rb[8];
+        double sx = rdes[0] + fo[0] + fs0, sy = rdes[1] + fo[1] + fs1;
+        double tq = (headed == 1) ? torque_force(fm, rb, inertia, rdes[0], rdes[1], rp) : torque_force(fm, rb, inertia, sx, sy, rp);
+        double g0 = np_dot(fm, sx, sy, cs, sn);
+        double g1 = rp[P_KO] * np_dot(fm, fo[0] + fs0, fo[1] + fs1, -sn, cs) - rp[P_KD] * rb[6];
+        rb[2] = bound_angle(rb[2] + rb[7] * dt);
+        rb[5] += (g0 / rb[9]) * dt; rb[6] += (g1 / rb[9]) * dt;
+        rb[7] += (tq / inertia) * dt;
+        clip_norm(fm, &rb[5], &rb[6], rb[12]);
+        double c2 = cos(rb[2]), s2 = sin(rb[2]);
+        rb[3] = np_mv(fm, c2, -s2, rb[5], rb[6]);
+        rb[4] = np_mv(fm, s2, c2, rb[5], rb[6]);
+    }
+}
+
+/* n_steps x (update_robot; update_humans): the sub-step loop of SocialNavGym.imitation_learning_step (gym:260-265).
+ * robot [E][13] (updated in place; copied into row n of `states` when consider_robot), robot_goals [E][rg][2],
+ * robot_desired [E][2], robot_params [20], robot_safety [E]. */
+void orc_imitation_steps(const orc_cfg *c, int E, double *states, double *goals, const double *walls, const double *params,
+                         const double *safety, double *desired, double dt, int n_steps, double *robot, double *robot_goals, int rg,
+                         double *robot_desired, const double *robot_params, int robot_type, const double *robot_safety, int n_threads) {
+    const int rows = c->n + (c->consider_robot ? 1 : 0);
+    const size_t wstride = c->walls_per_env ? (size_t)c->n_walls * c->n_segs * 4 : 0;
+#pragma omp parallel num_threads(n_threads > 0 ? n_threads : 1)
+    {
+        double *scratch = (double *)malloc(sizeof(double) * scratch_doubles(c));
+#pragma omp for schedule(static)
+        for (int e = 0; e < E; ++e) {
+            double *st = states + (size_t)e * rows * NS;
+            double *rb = robot + (size_t)e * NS;
+            for (int s = 0; s < n_steps; ++s) {
+                update_robot_env(c, rb, robot_goals + (size_t)e * rg * 2, rg, robot_desired + 2 * e, robot_params, robot_type, robot_safety[e],
+                                 st, safety + (size_t)e * rows, walls + e * wstride, dt, scratch);
+                if (c->consider_robot) memcpy(st + NS * c->n, rb, sizeof(double) * NS);
+                update_env(c, st, goals + (size_t)e * c->n * c->g * 2, walls + e * wstride, params + (size_t)e * c->n * NP,
+                           safety + (size_t)e * rows, desired + (size_t)e * c->n * 2, dt, NULL, scratch);
+            }
+        }
+        free(scratch);
+    }
+}
+
 /* utils.py:22-36 */
 static double point_to_segment_dist(double x1, double y1, double x2, double y2, double x3, double y3) {
     double px = x2 - x1, py = y2 - y1;

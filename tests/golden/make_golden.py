@@ -246,6 +246,57 @@ def pt_cases():
         print("   respawns seen:", int((np.diff(gy, axis=0) != 0).sum()))
 
 
+def _near_goal(sim):
+    sim.robot.position = np.array([0.3, 6.0])  # one metre from its goal (0, 7): the robot's goal list rotates within the run
+    return sim
+
+
+def robot_model_cases():
+    """Robot driven by a human motion model, as SocialNavGym.imitation_learning_step does per sub-step (social_nav_gym.py:260-265):
+    update_robot (motion_model_manager.py:593-653) then update_humans.  Fixture il_robot.npz."""
+    out = {}
+    confs = [("cc5_hsfm_farina__hsfm_farina", lambda: cc_sim("hsfm_farina", 1002, 5, True), "hsfm_farina", 600),
+             ("cc5_sfm_helbing__hsfm_new_guo", lambda: cc_sim("sfm_helbing", 2003, 5, True), "hsfm_new_guo", 600),
+             ("cc6_hsfm_new_guo__sfm_guo_invisible", lambda: cc_sim("hsfm_new_guo", 2003, 6, False), "sfm_guo", 400),
+             ("walls7_hsfm_farina__sfm_moussaid", lambda: custom_sim(dense_example_data(), "hsfm_farina", True), "sfm_moussaid", 300),
+             ("cc25_hsfm_farina__hsfm_farina", lambda: cc_sim("hsfm_farina", 2000, 25, True), "hsfm_farina", 100),
+             ("cc5_near_goal_hsfm_guo__hsfm_guo", lambda: _near_goal(cc_sim("hsfm_guo", 31, 5, True)), "hsfm_guo", 400)]
+    for key, mk, robot_model, n_steps in confs:
+        sim = mk()
+        mm = sim.motion_model_manager
+        if len(sim.robot.goals) == 1:
+            sim.robot.goals = [list(sim.robot.goals[0]), [float(sim.robot.position[0]), float(sim.robot.position[1])]]
+        mm.set_robot_motion_model(robot_model, False)
+        humans, robot = sim.humans, sim.robot
+        model = mm.motion_model_title
+        out[key + "_type"] = np.int64(SFMS.index(model))
+        out[key + "_robot_type"] = np.int64(SFMS.index(robot_model))
+        out[key + "_states0"] = np.array([h.get_safe_state() for h in humans])
+        out[key + "_goals0"] = pack_goals(humans)
+        out[key + "_walls"] = pack_walls(mm.walls)
+        out[key + "_params"] = np.array([h.get_parameters(model) for h in humans])
+        out[key + "_robot_params"] = robot.get_parameters(robot_model)
+        out[key + "_robot0"] = robot.get_safe_state()
+        out[key + "_robot_goals"] = np.array(robot.goals, np.float64)
+        out[key + "_flags"] = np.array([int(mm.consider_robot), int(mm.all_equal_humans)], np.int64)
+        steps, traj, rtraj = [0], [np.array([human_row(h) for h in humans])], [human_row(robot)]
+        for s in range(1, n_steps + 1):
+            mm.update_robot(0.0, DT)
+            mm.update_humans(0.0, DT)
+            if s <= 10 or s % 20 == 0:
+                steps.append(s)
+                traj.append(np.array([human_row(h) for h in humans]))
+                rtraj.append(human_row(robot))
+        out[key + "_steps"] = np.array(steps, np.int64)
+        out[key + "_traj"] = np.array(traj)
+        out[key + "_robot_traj"] = np.array(rtraj)
+        rt = np.array(rtraj)
+        print("il", key, "robot goal switches:", int((np.abs(np.diff(rt[:, 8:10], axis=0)).sum(1) > 0).sum()), "final robot pos", rt[-1, :2])
+    path = os.path.join(HERE, "il_robot.npz")
+    np.savez_compressed(path, **out)
+    print("il_robot ->", os.path.getsize(path), "B")
+
+
 def numba_cases():
     """Second witness: the reference's Numba operator update_humans_parallel (forces_parallel.py:184)."""
     out = {}
@@ -460,11 +511,13 @@ def gym_case():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["traj", "pt", "numba", "peek", "flags", "laser", "gym"]
+    which = sys.argv[1:] or ["traj", "pt", "il", "numba", "peek", "flags", "laser", "gym"]
     if "traj" in which:
         traj_cases()
     if "pt" in which:
         pt_cases()
+    if "il" in which:
+        robot_model_cases()
     if "numba" in which:
         numba_cases()
     if "peek" in which:

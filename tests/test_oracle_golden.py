@@ -96,6 +96,39 @@ def test_parallel_traffic_respawn_is_exercised():
         assert jumps.sum() >= 5, name
 
 
+def _il_keys(z):
+    return sorted(k[:-8] for k in z.files if k.endswith("_states0"))
+
+
+def test_robot_driven_by_motion_model():
+    """update_robot + update_humans per sub-step (imitation_learning_step, gym:260-265; mmm:593-653) against 6 recorded runs:
+    robot and human models may differ, robot visible or not, walls, a robot goal switch."""
+    z = np.load(os.path.join(GOLDEN, "il_robot.npz"))
+    keys = _il_keys(z)
+    assert len(keys) == 6
+    for key in keys:
+        vis, equal = (bool(v) for v in z[key + "_flags"])
+        S, G, rb = z[key + "_states0"], z[key + "_goals0"][None], z[key + "_robot0"][None].copy()
+        n = S.shape[0]
+        S = (np.concatenate([S, rb], 0) if vis else S)[None]
+        cfg = OracleConfig(int(z[key + "_type"]), vis, equal, False)
+        D, rD, rG = np.zeros((1, n, 2)), np.zeros((1, 2)), z[key + "_robot_goals"][None].copy()
+        cur = 0
+        moussaid = int(z[key + "_type"]) % 3 == 2 or int(z[key + "_robot_type"]) % 3 == 2
+        for k, s_ in enumerate(z[key + "_steps"]):
+            if s_ > cur:
+                S, G, D, rb, rG, rD = oracle.imitation_steps(cfg, S, G, z[key + "_walls"], z[key + "_params"][None], np.zeros((1, S.shape[1])), D,
+                                                            0.0125, int(s_ - cur), rb, rG, rD, z[key + "_robot_params"], int(z[key + "_robot_type"]))
+                cur = s_
+            got_h = np.concatenate([S[0, :n, :8], S[0, :n, 10:12], D[0]], 1)
+            got_r = np.concatenate([rb[0, :8], rb[0, 10:12], rD[0]])
+            tol = 1e-5 if moussaid else 1e-9
+            assert rel_err(got_h, z[key + "_traj"][k]).max() < tol, (key, int(s_))
+            assert rel_err(got_r, z[key + "_robot_traj"][k]).max() < tol, (key, int(s_))
+    rt = z["cc5_near_goal_hsfm_guo__hsfm_guo_robot_traj"]
+    assert (np.abs(np.diff(rt[:, 8:10], axis=0)).sum(1) > 0).sum() == 1   # the robot's goal list rotated once
+
+
 def test_numba_operator_semantics():
     """Second witness: numba_compat=1 reproduces forces_parallel.update_humans_parallel (fp:184), including the
     Guo wall force divided by the wall count (fp:161) and '<=' goal switching (fp:226)."""
