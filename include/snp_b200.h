@@ -22,6 +22,8 @@
  *   snp_laser / snp_laser_host                    <- src/sensors.py:53-69 LaserSensor.get_laser_measurements
  *                                                   (:24-33 circle, :35-51 segment), src/robot_agent.py:77-82
  *   respawn option of snp_step                    <- motion_model_manager.py:407-422 (parallel-traffic post_update)
+ *   robot_mode 2 of snp_step                      <- motion_model_manager.py:593-653 update_robot / compute_robot_forces,
+ *                                                   social_nav_gym.py:252-274 imitation_learning_step
  *   snp_pack_states / snp_unpack_states           <- src/agent.py:256-266 get_safe_state / set_state row layout
  *   snp_large_step                                <- same update for one very large crowd (tiled all-pairs)
  */
@@ -51,7 +53,12 @@ enum { SNP_DYN_PX = 0, SNP_DYN_PY, SNP_DYN_VX, SNP_DYN_VY, SNP_DYN_TH, SNP_DYN_B
        SNP_DYN_DFX, SNP_DYN_DFY, SNP_DYN_FIELDS };                        /* dfx,dfy: carried desired force (forces.py:12-15) */
 enum { SNP_STAT_R = 0, SNP_STAT_M, SNP_STAT_VD, SNP_STAT_SAFETY, SNP_STAT_FIELDS };
 enum { SNP_ROBOT_PX = 0, SNP_ROBOT_PY, SNP_ROBOT_VX, SNP_ROBOT_VY, SNP_ROBOT_R, SNP_ROBOT_SAFETY, SNP_ROBOT_GX,
-       SNP_ROBOT_GY, SNP_ROBOT_TH, SNP_ROBOT_FIELDS };
+       SNP_ROBOT_GY, SNP_ROBOT_TH,
+       /* only used when the robot is driven by a motion model (robot_mode == 2): */
+       SNP_ROBOT_BVX, SNP_ROBOT_BVY, SNP_ROBOT_OM, SNP_ROBOT_M, SNP_ROBOT_VD, SNP_ROBOT_DFX, SNP_ROBOT_DFY,
+       SNP_ROBOT_GX2, SNP_ROBOT_GY2,   /* the other goal of the robot's (at most two-entry) goal list */
+       SNP_ROBOT_GCNT,                 /* 1 or 2 goals */
+       SNP_ROBOT_SPARE, SNP_ROBOT_FIELDS };
 
 /* Bits of the per-env flags word written by snp_step / snp_checks. */
 enum {
@@ -94,11 +101,14 @@ typedef struct snp_step_opts {
                                  ('<=' goal test, zeroed desired force, Guo wall force / W, first-wins closest segment) */
     int32_t n_substeps;       /* fused update_humans calls per launch (20 in SocialNavGym.step) */
     int32_t robot_mode;       /* 0: robot row fixed during the launch; 1: holonomic action: before every sub-step
-                                 p += a*dt, v = a (robot_agent.py:126-131) */
+                                 p += a*dt, v = a (robot_agent.py:126-131); 2: the robot is moved by its own SFM / HSFM model
+                                 before every human update (motion_model_manager.py:593-653 update_robot, as in
+                                 SocialNavGym.imitation_learning_step, social_nav_gym.py:260-265) */
     double dt;
     const void *action;       /* [2][E] (dtype of the crowd) when robot_mode == 1 or pre_checks */
     int32_t pre_checks;       /* swept collision / goal / reward on the PRE-step state (social_nav_gym.py:232-234) */
-    int32_t post_checks;      /* actual collision / goal on the POST-step state (social_nav_gym.py:269) */
+    int32_t post_checks;      /* 1: actual collision / goal on the POST-step state (social_nav_gym.py:107-118); 2: also reward, terminated,
+                                 truncated and info code from them at the end time (imitation_learning_step, social_nav_gym.py:269-271) */
     int32_t track_touch;      /* OR of the run_k_steps collision test after every sub-step */
     int32_t reserved;         /* bit 0 (SNP_OPT_FULL_PAIR_LOOP): evaluate every ordered pair in j-ascending order (the reference's
                                  accumulation order) instead of each unordered pair once per warp;
@@ -111,7 +121,8 @@ typedef struct snp_step_opts {
     double respawn_bounds[2]; /* (traffic_length / 2, traffic_height / 2)  (social_nav_sim.py:360) */
     int32_t respawn;          /* parallel-traffic respawn after every sub-step (motion_model_manager.py:407-422): humans within 3 m of
                                  their goal restart at the right end; rewrites goals[0], goal_cnt (N <= 32 only) */
-    int32_t reserved2;
+    int32_t robot_type;       /* robot_mode 2: the robot's model, 0..8 (may differ from the humans') */
+    double robot_params[20];  /* robot_mode 2: the robot's parameter row (agent.py:269 for its model) */
 } snp_step_opts;
 
 typedef struct snp_laser_args {

@@ -12,7 +12,8 @@ SNP_F32, SNP_F64 = 0, 1
 # field order of the SoA buffers (include/snp_b200.h)
 DYN_PX, DYN_PY, DYN_VX, DYN_VY, DYN_TH, DYN_BVX, DYN_BVY, DYN_OM, DYN_DFX, DYN_DFY, DYN_FIELDS = range(11)
 STAT_R, STAT_M, STAT_VD, STAT_SAFETY, STAT_FIELDS = range(5)
-ROBOT_PX, ROBOT_PY, ROBOT_VX, ROBOT_VY, ROBOT_R, ROBOT_SAFETY, ROBOT_GX, ROBOT_GY, ROBOT_TH, ROBOT_FIELDS = range(10)
+(ROBOT_PX, ROBOT_PY, ROBOT_VX, ROBOT_VY, ROBOT_R, ROBOT_SAFETY, ROBOT_GX, ROBOT_GY, ROBOT_TH, ROBOT_BVX, ROBOT_BVY, ROBOT_OM, ROBOT_M,
+ ROBOT_VD, ROBOT_DFX, ROBOT_DFY, ROBOT_GX2, ROBOT_GY2, ROBOT_GCNT, ROBOT_SPARE, ROBOT_FIELDS) = range(21)
 FLAG_COLLISION, FLAG_REACHING_GOAL, FLAG_TERMINATED, FLAG_TRUNCATED = 1, 2, 4, 8
 FLAG_INFO_SHIFT = 4
 FLAG_ACTUAL_COLLISION, FLAG_ACTUAL_GOAL, FLAG_TOUCHED = 1 << 7, 1 << 8, 1 << 9
@@ -32,7 +33,7 @@ class SnpStepOpts(ctypes.Structure):
                 ("n_substeps", c_int32), ("robot_mode", c_int32), ("dt", c_double), ("action", c_void_p),
                 ("pre_checks", c_int32), ("post_checks", c_int32), ("track_touch", c_int32), ("reserved", c_int32),
                 ("consts", c_double * 6), ("time_now", c_void_p), ("flags", c_void_p), ("checks", c_void_p),
-                ("respawn_bounds", c_double * 2), ("respawn", c_int32), ("reserved2", c_int32)]
+                ("respawn_bounds", c_double * 2), ("respawn", c_int32), ("robot_type", c_int32), ("robot_params", c_double * 20)]
 
 
 class SnpLaserArgs(ctypes.Structure):

@@ -25,7 +25,7 @@ def _sources():
 
 
 def _deps_mtime():
-    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inl"))]
     files.append(os.path.join(INCLUDE, "snp_b200.h"))
     return max(os.path.getmtime(f) for f in files)
 

@@ -39,6 +39,7 @@ template <typename T> static int build_args(const snp_crowd *c, const snp_step_o
     if (o->n_substeps < 0) { set_error("n_substeps must be >= 0"); return SNP_ERR_INVALID; }
     const bool need_robot = o->consider_robot || o->pre_checks || o->post_checks || o->track_touch || o->robot_mode;
     if (need_robot && !c->robot) { set_error("a robot array is required when consider_robot, robot_mode or any check is on"); return SNP_ERR_INVALID; }
+    if (o->robot_mode < 0 || o->robot_mode > 2) { set_error("robot_mode must be 0, 1 or 2"); return SNP_ERR_INVALID; }
     if ((o->robot_mode == 1 || o->pre_checks) && !o->action) { set_error("an action array is required for robot_mode=1 / pre_checks"); return SNP_ERR_INVALID; }
     if ((o->pre_checks || o->post_checks || o->track_touch) && !o->flags) { set_error("flags output required when checks are on"); return SNP_ERR_INVALID; }
     if (c->W < 0 || c->S < 0 || (c->W > 0 && (!c->walls || c->S == 0))) { set_error("walls: W=%d S=%d but no segment array", c->W, c->S); return SNP_ERR_INVALID; }
@@ -60,6 +61,8 @@ template <typename T> static int build_args(const snp_crowd *c, const snp_step_o
     a.pre_checks = o->pre_checks; a.post_checks = o->post_checks; a.track_touch = o->track_touch;
     for (int k = 0; k < 6; ++k) a.consts[k] = o->consts[k];
     a.time_now = o->time_now; a.flags = o->flags; a.checks = o->checks;
+    a.robot_type = o->robot_type; a.RP = make_params<T>(o->robot_params);
+    if (o->robot_mode == 2 && (o->robot_type < 0 || o->robot_type > 8)) { set_error("Type %d does not exist for this implementation", o->robot_type); return SNP_ERR_INVALID; }
     a.respawn = o->respawn; a.respawn_bounds[0] = o->respawn_bounds[0]; a.respawn_bounds[1] = o->respawn_bounds[1];
     if (o->respawn && c->N > 32) { set_error("parallel-traffic respawn is implemented for crowds of at most 32 humans per env"); return SNP_ERR_UNSUPPORTED; }
     a.epw = 1; a.gpb = 1;

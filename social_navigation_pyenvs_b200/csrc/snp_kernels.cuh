@@ -41,6 +41,8 @@ template <typename T> struct KArgs {
     int *flags;
     double *checks;
     int epw;  // envs per warp (warp-packed kernel)
+    int robot_type;           // robot_mode 2: the robot's model
+    Params<T> RP;             // robot_mode 2: the robot's parameters
     int respawn;              // parallel-traffic respawn after every sub-step (mmm:407-422)
     double respawn_bounds[2];
     int gpb;  // env groups per block (block-packed kernel)

@@ -42,6 +42,9 @@ __global__ void __launch_bounds__(kRowsPerBlock) k_unpack(const double *__restri
         robot[SNP_ROBOT_VX * (long long)E + e] = (T)t[3]; robot[SNP_ROBOT_VY * (long long)E + e] = (T)t[4];
         robot[SNP_ROBOT_R * (long long)E + e] = (T)t[8]; robot[SNP_ROBOT_SAFETY * (long long)E + e] = (T)saf;
         robot[SNP_ROBOT_GX * (long long)E + e] = (T)t[10]; robot[SNP_ROBOT_GY * (long long)E + e] = (T)t[11];
+        robot[SNP_ROBOT_BVX * (long long)E + e] = (T)t[5]; robot[SNP_ROBOT_BVY * (long long)E + e] = (T)t[6];
+        robot[SNP_ROBOT_OM * (long long)E + e] = (T)t[7]; robot[SNP_ROBOT_M * (long long)E + e] = (T)t[9];
+        robot[SNP_ROBOT_VD * (long long)E + e] = (T)t[12];
     }
 }
 

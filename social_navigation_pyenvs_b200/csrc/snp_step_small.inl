@@ -1,4 +1,5 @@
-// snp_step_small.cu -- fused small-crowd step: goal switching, wall closest points, all-pairs social force, desired
+// snp_step_small.inl -- fused small-crowd step (compiled once per arithmetic type by snp_step_small_f32.cu / _f64.cu)
+// fused small-crowd step: goal switching, wall closest points, all-pairs social force, desired
 // force, HSFM torque + body-frame projection, explicit Euler, robot motion and the collision / goal / reward
 // reductions, for `n_substeps` consecutive update_humans calls in ONE launch.  Agent state makes one HBM round trip per
 // launch: it lives in registers across sub-steps and only (x, y, vx, vy) of each entity is republished to shared memory.
@@ -28,13 +29,15 @@ namespace {
 #endif
 
 constexpr int kWarpsPerBlock = 4;
+constexpr int kRobotParamWords = 24;  // Params<T> of the robot staged in shared memory (21 values, padded)
 constexpr int kSlotsPerWarp = 64;  // >= epw * (N + 1) for every N <= 32
 
 // Byte offsets of the dynamic shared-memory regions (same arithmetic on host and device).
 template <typename T> struct SmemLayout {
-    size_t segs, seg_cnt, ents, rs, red, xchg, tflag, total;
+    size_t segs, seg_cnt, ents, rs, red, xchg, tflag, rb, total;
     int slots;
-    __host__ __device__ SmemLayout(int nseg, int seg_groups, int W, int slots_, int red_doubles, int xchg_vec2 = 0, int groups = 0) : slots(slots_) {
+    __host__ __device__ SmemLayout(int nseg, int seg_groups, int W, int slots_, int red_doubles, int xchg_vec2 = 0, int groups = 0,
+                                   int robot_groups = 0) : slots(slots_) {
         size_t off = sizeof(T) == 8 ? 64 * sizeof(double) : 0;  // exp table (fp64 only)
         segs = off; off += sizeof(Seg<T>) * (size_t)nseg * seg_groups;
         off = (off + 15) & ~size_t(15);
@@ -47,6 +50,8 @@ template <typename T> struct SmemLayout {
         off = (off + 15) & ~size_t(15);
         xchg = off; off += sizeof(Vec2<T>) * (size_t)xchg_vec2;   // block-packed halved pair loop: [rounds][lanes] of (fx, fy)
         tflag = off; off += sizeof(int) * (size_t)groups;
+        off = (off + 15) & ~size_t(15);
+        rb = off; off += sizeof(T) * (size_t)(robot_groups ? kRobotParamWords + robot_groups * SNP_ROBOT_FIELDS : 0);  // robot_mode 2
         total = off + 16;
     }
 };
@@ -150,7 +155,65 @@ __device__ __forceinline__ void social_force_halved(const Params<T> &P, const do
     }
 }
 
-template <typename T, int SOC, int OBS, int HEADED, bool CTA, bool PER_AGENT, bool HALF>
+// ---- robot driven by its own SFM / HSFM model (robot_mode 2; motion_model_manager.py:593-653) ----
+// Kept out of line so that the register allocation of the hot human path is untouched; the robot's model is a run-time value
+// (it may differ from the humans').  `rb` is the robot's state in shared memory, indexed by SNP_ROBOT_*.
+
+// Force of human (x2, y2, ...) on the robot: the per-agent path compute_social_force_*(index = len(humans)) (mmm:608).
+template <typename T>
+__device__ __noinline__ void robot_pair(int soc, const Params<T> *RP, const double *tbl, unsigned mask, const T *rb, T x2, T y2, T vx2, T vy2,
+                                        T rs2, T *fx, T *fy) {
+    const T rx = rb[SNP_ROBOT_PX], ry = rb[SNP_ROBOT_PY], rvx = rb[SNP_ROBOT_VX], rvy = rb[SNP_ROBOT_VY];
+    const T rrs = rb[SNP_ROBOT_R] + rb[SNP_ROBOT_SAFETY];
+    if (soc == 0) pair_force<T, 0>(*RP, tbl, mask, rx, ry, rvx, rvy, rrs, x2, y2, vx2, vy2, rs2, *fx, *fy);
+    else if (soc == 1) pair_force<T, 1>(*RP, tbl, mask, rx, ry, rvx, rvy, rrs, x2, y2, vx2, vy2, rs2, *fx, *fy);
+    else pair_force<T, 2>(*RP, tbl, mask, rx, ry, rvx, rvy, rrs, x2, y2, vx2, vy2, rs2, *fx, *fy);
+}
+
+// compute_robot_forces + Euler (mmm:593-629) by ONE lane, given the summed force of the humans (fsx, fsy).
+template <typename T>
+__device__ __noinline__ void robot_update(int rtype, const Params<T> *RPp, const double *tbl, const Seg<T> *segs, const int *seg_cnt, int W, int S,
+                                          T *rb, T fsx, T fsy, T dt) {
+    using R = Real<T>;
+    const Params<T> &RP = *RPp;
+    const int obs = (rtype == 1 || rtype == 4 || rtype == 7) ? 1 : 0, headed = rtype / 3;
+    const unsigned self = 1u << (threadIdx.x & 31);
+    Agent<T> m;
+    m.px = rb[SNP_ROBOT_PX]; m.py = rb[SNP_ROBOT_PY]; m.vx = rb[SNP_ROBOT_VX]; m.vy = rb[SNP_ROBOT_VY]; m.th = rb[SNP_ROBOT_TH];
+    m.bvx = rb[SNP_ROBOT_BVX]; m.bvy = rb[SNP_ROBOT_BVY]; m.om = rb[SNP_ROBOT_OM]; m.dfx = rb[SNP_ROBOT_DFX]; m.dfy = rb[SNP_ROBOT_DFY];
+    m.r = rb[SNP_ROBOT_R]; m.m = rb[SNP_ROBOT_M]; m.vd = rb[SNP_ROBOT_VD]; m.rs = m.r + rb[SNP_ROBOT_SAFETY];
+    m.gx = rb[SNP_ROBOT_GX]; m.gy = rb[SNP_ROBOT_GY];
+    agent_static<T>(RP, m);
+    if (np_norm(m.gx - m.px, m.gy - m.py) < m.r && rb[SNP_ROBOT_GCNT] > T(1.5)) {  // update_goals(robot) (mmm:598): rotate the 2-goal list
+        const T ox = m.gx, oy = m.gy;
+        m.gx = rb[SNP_ROBOT_GX2]; m.gy = rb[SNP_ROBOT_GY2];
+        rb[SNP_ROBOT_GX2] = ox; rb[SNP_ROBOT_GY2] = oy;
+    }
+    m.cs = T(1); m.sn = T(0);
+    if (headed) R::sincos_(m.th, &m.sn, &m.cs);  // v = R(yaw) bv was refreshed when the state was published (mmm:605)
+    T fox = T(0), foy = T(0);
+    if (W > 0) {
+        if (obs == 0) obstacle_force<T, 0>(RP, tbl, self, segs, seg_cnt, W, S, false, m.px, m.py, m.vx, m.vy, m.rs, fox, foy);
+        else obstacle_force<T, 1>(RP, tbl, self, segs, seg_cnt, W, S, false, m.px, m.py, m.vx, m.vy, m.rs, fox, foy);
+    }
+    desired_force<T>(RP, m, false);
+    if (headed == 0) integrate<T, 0>(RP, m, fox, foy, fsx, fsy, dt);
+    else if (headed == 1) integrate<T, 1>(RP, m, fox, foy, fsx, fsy, dt);
+    else integrate<T, 2>(RP, m, fox, foy, fsx, fsy, dt);
+    rb[SNP_ROBOT_PX] = m.px; rb[SNP_ROBOT_PY] = m.py; rb[SNP_ROBOT_VX] = m.vx; rb[SNP_ROBOT_VY] = m.vy; rb[SNP_ROBOT_TH] = m.th;
+    rb[SNP_ROBOT_BVX] = m.bvx; rb[SNP_ROBOT_BVY] = m.bvy; rb[SNP_ROBOT_OM] = m.om; rb[SNP_ROBOT_DFX] = m.dfx; rb[SNP_ROBOT_DFY] = m.dfy;
+    rb[SNP_ROBOT_GX] = m.gx; rb[SNP_ROBOT_GY] = m.gy;
+}
+
+template <typename T> __device__ __forceinline__ T seg_sum(T v, int i, int n, unsigned mask) {  // valid in the group's lane 0
+    for (int off = 1; off < n; off <<= 1) {
+        const T o = __shfl_down_sync(mask, v, off);
+        if (i + off < n) v += o;
+    }
+    return v;
+}
+
+template <typename T, int SOC, int OBS, int HEADED, bool CTA, bool PER_AGENT, bool HALF, bool ROBOT2>
 __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (sizeof(T) == 4 ? SNP_MINB_F32 : SNP_MINB_F64)) k_step(const KArgs<T> a) {
     // CTA == true is the block-packed mapping (a.gpb env groups per CTA), CTA == false the warp-packed one (a.epw per warp).
     using R = Real<T>;
@@ -186,7 +249,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
     const int nseg = a.W * a.S;
     const int seg_groups = a.walls_per_env ? groups : 1;
     const SmemLayout<T> lay(nseg, seg_groups, a.W, CTA ? a.gpb * (N + 1) : kWarpsPerBlock * kSlotsPerWarp, CTA ? a.gpb * N : 0,
-                            (CTA && HALF) ? rounds * a.gpb * N : 0, CTA ? a.gpb : 0);
+                            (CTA && HALF) ? rounds * a.gpb * N : 0, CTA ? a.gpb : 0, ROBOT2 ? groups : 0);
     double *exp_tbl_s = reinterpret_cast<double *>(smem_raw);
     Seg<T> *segs_all = reinterpret_cast<Seg<T> *>(smem_raw + lay.segs);
     int *seg_cnt_all = reinterpret_cast<int *>(smem_raw + lay.seg_cnt);
@@ -196,8 +259,11 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
     double *red = reinterpret_cast<double *>(smem_raw + lay.red) + (CTA ? g * N : 0);  // block-packed only: this group's [N] doubles
     Vec2<T> *xchg = reinterpret_cast<Vec2<T> *>(smem_raw + lay.xchg) + (CTA ? g * N : 0);
     int *tflag = reinterpret_cast<int *>(smem_raw + lay.tflag);
+    Params<T> *RPs = reinterpret_cast<Params<T> *>(smem_raw + lay.rb);  // robot_mode 2 only
+    T *rb = reinterpret_cast<T *>(smem_raw + lay.rb) + kRobotParamWords + (size_t)g * SNP_ROBOT_FIELDS;
 
     if (sizeof(T) == 8) exp_table_init(exp_tbl_s);
+    if constexpr (ROBOT2) { if (threadIdx.x == 0) *RPs = a.RP; }
     // walls -> shared memory (whole block cooperates, before anyone leaves)
     if (nseg > 0) {
         const int total = nseg * seg_groups;
@@ -271,6 +337,16 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
         rgx = a.robot[SNP_ROBOT_GX * E + env]; rgy = a.robot[SNP_ROBOT_GY * E + env];
         if (a.action) { ax = a.action[env]; ay = a.action[E + env]; }
         if (leader) rs_g[N] = rrs;
+        if constexpr (ROBOT2) if (leader) {  // the robot's full state lives in shared memory (one lane updates it)
+#pragma unroll
+            for (int f = 0; f < SNP_ROBOT_FIELDS; ++f) rb[f] = a.robot[(size_t)f * E + env];
+            if (a.robot_type >= 3) {  // headed robot: linear velocity = R(yaw) bv (mmm:605)
+                T sn, cs;
+                R::sincos_(rb[SNP_ROBOT_TH], &sn, &cs);
+                rb[SNP_ROBOT_VX] = np_mv(cs, -sn, rb[SNP_ROBOT_BVX], rb[SNP_ROBOT_BVY]);
+                rb[SNP_ROBOT_VY] = np_mv(sn, cs, rb[SNP_ROBOT_BVX], rb[SNP_ROBOT_BVY]);
+            }
+        }
     }
     double tnow = (a.time_now && live) ? a.time_now[env] : 0.0;
 
@@ -327,8 +403,37 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             rvx = ax; rvy = ay;
         }
         if (live) ents.put(i, me.px, me.py, me.vx, me.vy);
-        if (leader && a.consider_robot) ents.put(N, rpx, rpy, rvx, rvy);
+        if (!ROBOT2 && leader && a.consider_robot) ents.put(N, rpx, rpy, rvx, rvy);
         if constexpr (CTA) __syncthreads(); else __syncwarp(wmask);
+
+        if constexpr (ROBOT2) {
+            // update_robot first (gym:262): every human lane evaluates its force on the robot with the ROBOT's model and
+            // parameters, the group sums them, the leader integrates the robot and republishes it; the humans then see the
+            // moved robot (gym:264).
+            T rfx = T(0), rfy = T(0);
+            if (live) robot_pair<T>(a.robot_type % 3, RPs, exp_tbl_s, wmask, rb, me.px, me.py, me.vx, me.vy, me.rs, &rfx, &rfy);
+            if constexpr (CTA) {
+                if (live) { red[i] = (double)rfx; }
+                __syncthreads();
+                double sx = 0.0;
+                if (leader) for (int k = 0; k < N; ++k) sx += red[k];
+                __syncthreads();
+                if (live) { red[i] = (double)rfy; }
+                __syncthreads();
+                double sy = 0.0;
+                if (leader) for (int k = 0; k < N; ++k) sy += red[k];
+                rfx = (T)sx; rfy = (T)sy;
+            } else {
+                rfx = seg_sum<T>(rfx, i, N, wmask); rfy = seg_sum<T>(rfy, i, N, wmask);
+            }
+            if (leader) {
+                robot_update<T>(a.robot_type, RPs, exp_tbl_s, segs, seg_cnt, a.W, a.S, rb, rfx, rfy, dt);
+                if (a.consider_robot) ents.put(N, rb[SNP_ROBOT_PX], rb[SNP_ROBOT_PY], rb[SNP_ROBOT_VX], rb[SNP_ROBOT_VY]);
+            }
+            if constexpr (CTA) __syncthreads(); else __syncwarp(wmask);
+            rpx = rb[SNP_ROBOT_PX]; rpy = rb[SNP_ROBOT_PY]; rvx = rb[SNP_ROBOT_VX]; rvy = rb[SNP_ROBOT_VY];
+            rgx = rb[SNP_ROBOT_GX]; rgy = rb[SNP_ROBOT_GY];
+        }
 
         T fox = T(0), foy = T(0), fsx = T(0), fsy = T(0);
         if (live) {
@@ -499,6 +604,11 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
                 const bool agoal = xnorm_np(__dsub_rn((double)rpx, (double)rgx), __dsub_rn((double)rpy, (double)rgy)) < (double)rr;
                 out_admin = admin;
                 flags |= (admin <= 0.0 ? SNP_FLAG_ACTUAL_COLLISION : 0) | (agoal ? SNP_FLAG_ACTUAL_GOAL : 0);
+                if (a.post_checks == 2) {  // imitation_learning_step: reward / info from the ACTUAL end state and end time (gym:269-271)
+                    bool term, trunc;
+                    const int code = reward_and_info(admin <= 0.0, admin, agoal, tnow, a.consts, out_reward, term, trunc);
+                    flags |= (term ? SNP_FLAG_TERMINATED : 0) | (trunc ? SNP_FLAG_TRUNCATED : 0) | (code << SNP_FLAG_INFO_SHIFT);
+                }
             }
             if (any_touch) flags |= SNP_FLAG_TOUCHED;
         }
@@ -521,6 +631,13 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             const long long E = a.E;
             a.robot[SNP_ROBOT_PX * E + env] = rpx; a.robot[SNP_ROBOT_PY * E + env] = rpy;
             a.robot[SNP_ROBOT_VX * E + env] = rvx; a.robot[SNP_ROBOT_VY * E + env] = rvy;
+        }
+        if (ROBOT2 && has_robot && a.n_substeps > 0) {
+            const long long E = a.E;
+#pragma unroll
+            for (int f = 0; f < SNP_ROBOT_FIELDS; ++f)
+                if (f != SNP_ROBOT_R && f != SNP_ROBOT_SAFETY && f != SNP_ROBOT_M && f != SNP_ROBOT_VD && f != SNP_ROBOT_GCNT && f != SNP_ROBOT_SPARE)
+                    a.robot[(size_t)f * E + env] = rb[f];
         }
         if (a.time_now) a.time_now[env] = tnow;
         if (a.flags) a.flags[env] = flags;
@@ -555,7 +672,7 @@ int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
         const int epb = a.epw * kWarpsPerBlock;
         grid = dim3((unsigned)((a.E + epb - 1) / epb));
         block = dim3(kWarpsPerBlock * 32);
-        smem = SmemLayout<T>(nseg, a.walls_per_env ? epb : 1, a.W, kWarpsPerBlock * kSlotsPerWarp, 0).total;
+        smem = SmemLayout<T>(nseg, a.walls_per_env ? epb : 1, a.W, kWarpsPerBlock * kSlotsPerWarp, 0, 0, 0, a.robot_mode == 2 ? epb : 0).total;
     } else {
         a.epw = 1;
         a.gpb = gpb;
@@ -563,22 +680,30 @@ int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
         block = dim3((unsigned)block_threads);
         const int rounds = (a.N - 1) >> 1;
         if (half && sizeof(Vec2<T>) * (size_t)rounds * gpb * a.N > 64 * 1024) half = false;  // exchange planes would not fit: ordered loop
-        smem = SmemLayout<T>(nseg, a.walls_per_env ? gpb : 1, a.W, gpb * (a.N + 1), gpb * a.N, half ? rounds * gpb * a.N : 0, gpb).total;
+        smem = SmemLayout<T>(nseg, a.walls_per_env ? gpb : 1, a.W, gpb * (a.N + 1), gpb * a.N, half ? rounds * gpb * a.N : 0, gpb,
+                             a.robot_mode == 2 ? gpb : 0).total;
     }
     if (smem > 200 * 1024) { set_error("wall/segment tables need %zu bytes of shared memory (limit 200 KiB)", smem); return SNP_ERR_UNSUPPORTED; }
-#define SNP_LAUNCH(CTA_, PA_, HALF_)                                                                                   \
+#define SNP_LAUNCH2(CTA_, PA_, HALF_, R2_)                                                                             \
     do {                                                                                                               \
-        auto kern = k_step<T, SOC, OBS, HEADED, CTA_, PA_, HALF_>;                                                     \
+        auto kern = k_step<T, SOC, OBS, HEADED, CTA_, PA_, HALF_, R2_>;                                                \
         if (smem > 48 * 1024) SNP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, block, smem, st>>>(a);                                                                            \
     } while (0)
-    if (cta) {
+#define SNP_LAUNCH(CTA_, PA_, HALF_) SNP_LAUNCH2(CTA_, PA_, HALF_, false)
+    if (a.robot_mode == 2) {  // robot driven by its own model: separate instantiations so the common path keeps its registers
+        if (per_agent) { set_error("robot_mode 2 with per-agent parameter rows is not supported"); return SNP_ERR_UNSUPPORTED; }
+        if (!a.robot) { set_error("robot_mode 2 needs a robot array"); return SNP_ERR_INVALID; }
+        if (cta) { if (half) SNP_LAUNCH2(true, false, true, true); else SNP_LAUNCH2(true, false, false, true); }
+        else { if (half) SNP_LAUNCH2(false, false, true, true); else SNP_LAUNCH2(false, false, false, true); }
+    } else if (cta) {
         if (per_agent) SNP_LAUNCH(true, true, false);
         else if (half) SNP_LAUNCH(true, false, true);
         else SNP_LAUNCH(true, false, false);
     } else if (per_agent) SNP_LAUNCH(false, true, false);
     else if (half) SNP_LAUNCH(false, false, true);
     else SNP_LAUNCH(false, false, false);
+#undef SNP_LAUNCH2
 #undef SNP_LAUNCH
     count_launch();
     SNP_CUDA_OK(cudaGetLastError());
@@ -603,7 +728,6 @@ template <typename T> int launch_step_small(const KArgs<T> &a, int type, cudaStr
     return SNP_ERR_INVALID;
 }
 
-template int launch_step_small<float>(const KArgs<float> &, int, cudaStream_t);
-template int launch_step_small<double>(const KArgs<double> &, int, cudaStream_t);
+template int launch_step_small<SNP_STEP_DTYPE>(const KArgs<SNP_STEP_DTYPE> &, int, cudaStream_t);
 
 }  // namespace snp

@@ -68,6 +68,7 @@ class CrowdEngine:
         # False (default): every unordered pair is evaluated once per warp (Newton's third law); True: every ordered pair in
         # j-ascending order, the reference's own accumulation order (forces.py:145-151).  Same result up to rounding.
         self.full_pair_loop = bool(full_pair_loop)
+        self.robot_type, self.robot_params = None, None  # set_robot_motion_model
         self.respawn_bounds = None  # (traffic_length/2, traffic_height/2): parallel-traffic respawn after every update (mmm:407-422)
         self.mapping = 0  # 0 auto, 1 force warp-packed, 2 force block-packed thread mapping (tests / tuning)
         self.params = model_parameters(model) if params is None else np.asarray(params, np.float64).reshape(20)
@@ -142,6 +143,7 @@ class CrowdEngine:
 
     def _opts(self, dt, n_substeps, robot_mode=0, pre_checks=False, post_checks=False, track_touch=False, advance_time=False,
               post_update=True):
+        # post_checks: False/True/2 (2 = imitation-learning reward from the actual end state)
         o = L.SnpStepOpts()
         o.type, o.consider_robot, o.symmetric, o.numba_compat = self.type, int(self.consider_robot), int(self.symmetric), int(self.numba_compat)
         o.n_substeps, o.robot_mode, o.dt = int(n_substeps), int(robot_mode), float(dt)
@@ -149,8 +151,11 @@ class CrowdEngine:
         o.pre_checks, o.post_checks, o.track_touch = int(pre_checks), int(post_checks), int(track_touch)
         o.reserved = (1 if self.full_pair_loop else 0) | (self.mapping << 2)
         o.consts = (ctypes.c_double * 6)(*self.consts)
-        o.time_now = self.time_now.data_ptr() if (advance_time or pre_checks) else None
+        o.time_now = self.time_now.data_ptr() if (advance_time or pre_checks or int(post_checks) == 2) else None
         o.flags, o.checks = self.flags.data_ptr(), self.checks.data_ptr()
+        if robot_mode == 2:
+            o.robot_type = int(self.robot_type)
+            o.robot_params = (ctypes.c_double * 20)(*self.robot_params.tolist())
         if self.respawn_bounds is not None and n_substeps > 0 and post_update:
             o.respawn = 1
             o.respawn_bounds = (ctypes.c_double * 2)(*self.respawn_bounds)
@@ -187,11 +192,53 @@ class CrowdEngine:
         out[L.ROBOT_PX], out[L.ROBOT_PY], out[L.ROBOT_TH] = r[:, 0], r[:, 1], r[:, 2]
         out[L.ROBOT_VX], out[L.ROBOT_VY] = r[:, 3], r[:, 4]
         out[L.ROBOT_R], out[L.ROBOT_GX], out[L.ROBOT_GY] = r[:, 8], r[:, 10], r[:, 11]
+        out[L.ROBOT_BVX], out[L.ROBOT_BVY], out[L.ROBOT_OM], out[L.ROBOT_M], out[L.ROBOT_VD] = r[:, 5], r[:, 6], r[:, 7], r[:, 9], r[:, 12]
+        out[L.ROBOT_GCNT] = 1.0
         if safety is not None:
             out[L.ROBOT_SAFETY] = np.asarray(safety, np.float64).reshape(self.E)
         else:
             out[L.ROBOT_SAFETY] = self.robot[L.ROBOT_SAFETY].double().cpu().numpy()
         self.robot.copy_(torch.as_tensor(out, dtype=self.dtype))
+
+    def set_robot_motion_model(self, title, goals=None):
+        """MotionModelManager.set_robot_motion_model (mmm:552-591, Euler only): the robot will be moved by the SFM / HSFM model
+        `title` (parameters of agent.py:79-243) in `imitation_learning_step`.  goals: optional [E,1..2,2] robot goal list."""
+        if title not in SFMS:
+            raise Exception(f"The robot motion model '{title}' does not exist")
+        self.robot_motion_model_title = title
+        self.robot_type, self.robot_params = SFMS.index(title), model_parameters(title)
+        if goals is not None:
+            self.set_robot_goals(goals)
+
+    def set_robot_goals(self, goals):
+        g = np.asarray(goals, np.float64).reshape(self.E, -1, 2)
+        if g.shape[1] > 2:
+            raise NotImplementedError("the robot's goal list holds at most two goals (every reference scenario: goal and start)")
+        t = lambda a: torch.as_tensor(a, dtype=self.dtype, device=self.device)
+        self.robot[L.ROBOT_GX].copy_(t(g[:, 0, 0])); self.robot[L.ROBOT_GY].copy_(t(g[:, 0, 1]))
+        if g.shape[1] == 2 and not np.isnan(g[:, 1]).any():
+            self.robot[L.ROBOT_GX2].copy_(t(g[:, 1, 0])); self.robot[L.ROBOT_GY2].copy_(t(g[:, 1, 1]))
+            self.robot[L.ROBOT_GCNT].fill_(2.0)
+        else:
+            self.robot[L.ROBOT_GCNT].fill_(1.0)
+
+    def imitation_learning_step(self, dt=0.0125, n_substeps=20):
+        """SocialNavGym.imitation_learning_step (social_nav_gym.py:252-274): `n_substeps` x (update_robot; update_humans) with
+        the robot moved by its own motion model, then the ACTUAL collision / goal checks and the reward at the end time --
+        one launch.  Results in self.flags / self.checks (decode_flags) and self.robot."""
+        if self.robot_type is None:
+            raise ValueError("set_robot_motion_model(title) first")
+        o = self._opts(dt, n_substeps, robot_mode=2, post_checks=2, advance_time=True)
+        L.check(self.lib.snp_step(ctypes.byref(self._crowd()), ctypes.byref(o), _stream()))
+
+    def robot_rows(self):
+        """Robot state as reference rows [E,13] + carried desired force [E,2]."""
+        r = self.robot.double().cpu().numpy()
+        rows = np.zeros((self.E, 13))
+        rows[:, 0], rows[:, 1], rows[:, 2] = r[L.ROBOT_PX], r[L.ROBOT_PY], r[L.ROBOT_TH]
+        rows[:, 3], rows[:, 4], rows[:, 5], rows[:, 6], rows[:, 7] = r[L.ROBOT_VX], r[L.ROBOT_VY], r[L.ROBOT_BVX], r[L.ROBOT_BVY], r[L.ROBOT_OM]
+        rows[:, 8], rows[:, 9], rows[:, 10], rows[:, 11], rows[:, 12] = r[L.ROBOT_R], r[L.ROBOT_M], r[L.ROBOT_GX], r[L.ROBOT_GY], r[L.ROBOT_VD]
+        return rows, np.stack([r[L.ROBOT_DFX], r[L.ROBOT_DFY]], 1)
 
     def rows(self, template):
         """Download the state in reference row form: `template` [E,rows,13] provides the static columns and the robot row

@@ -31,6 +31,8 @@ class BatchedSocialNavGym:
         self.train_val_sim = self.test_sim = "circle_crossing"
         self.traffic_length, self.traffic_height = 14.0, 3.0
         self.robot_visible = False
+        self.robot_motion_model_title = None
+        self._robot_goals = None
         self.walls = None
 
     def configure(self, config):
@@ -77,6 +79,8 @@ class BatchedSocialNavGym:
             raise NotImplementedError(f"scenario {sim}: the hybrid scenario mixes generators per env (social_nav_gym.py:155-167)")
         self.case_counter[phase] += self.E
         robot = sc["robot"].copy()
+        # robot goal list of the reference scenarios: [goal, start] (social_nav_sim.py:237,309)
+        self._robot_goals = np.stack([robot[:, 10:12], robot[:, 0:2]], 1)
         robot[:, 3:5] = 0.0                                                      # robot.set(..., vx=0, vy=0) (social_nav_gym.py:213)
         states = np.concatenate([sc["states"], robot[:, None]], 1) if self.robot_visible else sc["states"]
         self.engine = CrowdEngine.from_reference_arrays(self.human_policy, states, sc["goals"], walls=self.walls, consider_robot=self.robot_visible,
@@ -98,6 +102,21 @@ class BatchedSocialNavGym:
 
     def step(self, action):
         self.engine.step(action, self.time_step, n_substeps=self.time_step_factor, pre_checks=True)
+        r = self.engine.decode_flags()
+        return self.observation(), r["reward"], r["terminated"], r["truncated"], r["info"]
+
+    def set_robot_motion_model(self, title):
+        """The robot will be moved by the SFM / HSFM model `title` in imitation_learning_step (mmm:552-591, Euler)."""
+        self.robot_motion_model_title = title
+        if self.engine is not None:
+            self.engine.set_robot_motion_model(title, goals=self._robot_goals)
+
+    def imitation_learning_step(self):
+        """social_nav_gym.py:252-274 for every env: time_step_factor x (update_robot; update_humans), then the ACTUAL collision /
+        goal checks and the reward at the end time -- one launch."""
+        if self.engine.robot_type is None:
+            self.engine.set_robot_motion_model(self.robot_motion_model_title, goals=self._robot_goals)
+        self.engine.imitation_learning_step(self.time_step, n_substeps=self.time_step_factor)
         r = self.engine.decode_flags()
         return self.observation(), r["reward"], r["terminated"], r["truncated"], r["info"]
 

@@ -77,3 +77,39 @@ def test_batched_gym_env0_equals_recorded_reference_episode():
         assert abs(env.global_time[0] - 15.0) < 1e-9
         col, dmin, goal = env.check_actual_collisions_and_goal()
         assert col.shape == (3,) and dmin.shape == (3,)
+
+
+def test_robot_driven_by_motion_model_vs_reference_golden():
+    """imitation-learning sub-step loop (update_robot then update_humans, gym:260-265; mmm:593-653) inside ONE launch per block of
+    sub-steps, against 6 runs recorded from the live reference: robot and human models may differ, the robot may be invisible to
+    the humans, walls, and one run where the robot's goal list rotates."""
+    from social_navigation_pyenvs_b200 import CrowdEngine, SFMS
+    z = np.load(os.path.join(GOLDEN, "il_robot.npz"))
+    keys = sorted(k[:-8] for k in z.files if k.endswith("_states0"))
+    assert len(keys) == 6
+    for key in keys:
+        vis, equal = (bool(v) for v in z[key + "_flags"])
+        S, G, rb = z[key + "_states0"], z[key + "_goals0"][None], z[key + "_robot0"][None]
+        n = S.shape[0]
+        S1 = (np.concatenate([S, rb], 0) if vis else S)[None]
+        eng = CrowdEngine.from_reference_arrays(SFMS[int(z[key + "_type"])], S1, G, walls=z[key + "_walls"], consider_robot=vis,
+                                                all_params_equal=equal, robot=None if vis else rb)
+        eng.set_robot_motion_model(SFMS[int(z[key + "_robot_type"])], goals=z[key + "_robot_goals"][None])
+        assert np.array_equal(eng.robot_params, z[key + "_robot_params"])
+        moussaid = int(z[key + "_type"]) % 3 == 2 or int(z[key + "_robot_type"]) % 3 == 2
+        cur = 0
+        for k, s_ in enumerate(z[key + "_steps"]):
+            if s_ > cur:
+                eng.imitation_learning_step(0.0125, n_substeps=int(s_ - cur))
+                cur = s_
+            got_h = eng.rows(S1)[0]
+            rr, rdf = eng.robot_rows()
+            ref_h, ref_r = z[key + "_traj"][k], z[key + "_robot_traj"][k]
+            tol = 1e-5 if moussaid else 1e-8
+            assert rel_err(np.concatenate([got_h[:n, :8], got_h[:n, 10:12]], 1), ref_h[:, :10]).max() < tol, (key, int(s_))
+            got_r = np.concatenate([rr[0, :8], rr[0, 10:12]])
+            got_r[2] = ref_r[2] + (got_r[2] - ref_r[2] + np.pi) % (2 * np.pi) - np.pi
+            assert rel_err(got_r, ref_r[:10]).max() < tol, (key, int(s_))
+            assert rel_err(rdf[0], ref_r[10:12], scale=100.0).max() < tol
+        f = eng.decode_flags()
+        assert f["info"][0] in (0, 2, 3, 4)

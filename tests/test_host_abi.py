@@ -38,7 +38,7 @@ def test_ctypes_struct_layouts_match_the_header():
     assert ctypes.sizeof(L.SnpCrowd) == 4 * 4 + 6 * 8 + 20 * 8 + 2 * 8 + 3 * 4 + 4  # ints, ptrs, params, ptrs, ints, tail padding
     assert L.SnpCrowd.params.offset == 64 and L.SnpCrowd.robot.offset == 224 and L.SnpCrowd.W.offset == 240
     assert L.SnpStepOpts.dt.offset == 24 and L.SnpStepOpts.action.offset == 32 and L.SnpStepOpts.consts.offset == 56
-    assert L.SnpStepOpts.time_now.offset == 104 and L.SnpStepOpts.respawn_bounds.offset == 128 and ctypes.sizeof(L.SnpStepOpts) == 152
+    assert L.SnpStepOpts.time_now.offset == 104 and L.SnpStepOpts.respawn_bounds.offset == 128 and L.SnpStepOpts.robot_params.offset == 152 and ctypes.sizeof(L.SnpStepOpts) == 312
     assert L.SnpLaserArgs.pose.offset == 64 and L.SnpLaserArgs.ranges.offset == 96 and ctypes.sizeof(L.SnpLaserArgs) == 112
 
 
