@@ -185,7 +185,8 @@ def run_large_crowd(args, rank, world, local_rank):
     tdtype = torch.float64 if args.dtype == "f64" else torch.float32
     sc = scenarios.jittered_grid_crowd(256, pitch=2.0, jitter=0.5, seed=0)
     n = sc["states"].shape[1]
-    crowd = LargeCrowd("hsfm_farina", sc["states"][0], sc["goals"][0], dtype=tdtype, rank=rank, world=world)
+    crowd = LargeCrowd("hsfm_farina", sc["states"][0], sc["goals"][0], dtype=tdtype, rank=rank, world=world,
+                       exchange=os.environ.get("SNP_EXCHANGE", "auto"))
     steps = min(args.steps, 50)
     for _ in range(args.warmup):
         crowd.step(DT, 1)
@@ -239,7 +240,8 @@ def run_large_crowd(args, rank, world, local_rank):
                 "warmup": args.warmup, "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": args.workload, "humans": n, "model": "hsfm_farina", "substeps_per_step": 1, "dt": DT,
-                           "sharding": f"by agent over {world} GPU(s), all-gather of the [5,N] entity view per sub-step",
+                           "sharding": f"by agent over {world} GPU(s); entity view [5,N] exchanged per sub-step via " +
+                                       ("peer (NVLink) stores fused into the producer kernel + barrier" if crowd.exchange == "p2p" else "NCCL all-gather"),
                            "culling": "exact far-tile culling on for `value` (tiles beyond the exp-underflow distance contribute exactly 0); "
                                       "roofline measured with culling off (every ordered pair evaluated)",
                            "ms_per_step_all_pairs": allpairs_ms,

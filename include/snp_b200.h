@@ -167,6 +167,12 @@ int snp_rotate_goal_rows(const snp_crowd *crowd, double *goal_rows_dev, void *cu
 int64_t snp_large_scratch_bytes(int64_t n_local, int64_t M, int32_t dtype);
 int snp_large_step(const snp_crowd *crowd, const snp_step_opts *opts, const void *others, int64_t M, int64_t self_offset,
                    void *next_view, void *scratch, int64_t scratch_bytes, void *cuda_stream);
+/* Same sub-step with the all-gather FUSED into the producer kernel: `peer_next_views` is a host array of `n_peers` device
+ * pointers -- the NEXT-view buffer of every rank of the node (this rank's own included), peer-mapped over NVLink (e.g. torch
+ * symmetric memory) -- and the finish kernel stores each agent's new entry straight into all of them.  The caller only needs a
+ * cross-rank barrier between sub-steps; no collective moves data. */
+int snp_large_step_p2p(const snp_crowd *crowd, const snp_step_opts *opts, const void *others, int64_t M, int64_t self_offset,
+                       const void *const *peer_next_views, int32_t n_peers, void *scratch, int64_t scratch_bytes, void *cuda_stream);
 /* Writes this crowd's [5][.] entity view (x,y,vx,vy,r+safety; v = R(yaw) bv for headed models) into `view` (field stride
  * `stride` elements, starting at element `offset`). */
 int snp_large_publish(const snp_crowd *crowd, int32_t type, void *view, int64_t stride, int64_t offset, void *cuda_stream);

@@ -59,6 +59,8 @@ _SIGNATURES = {
     "snp_large_scratch_bytes": (c_int64, [c_int64, c_int64, c_int32]),
     "snp_large_step": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpStepOpts), c_void_p, c_int64, c_int64, c_void_p, c_void_p,
                                       c_int64, c_void_p]),
+    "snp_large_step_p2p": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpStepOpts), c_void_p, c_int64, c_int64,
+                                          ctypes.POINTER(c_void_p), c_int32, c_void_p, c_int64, c_void_p]),
     "snp_large_publish": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), c_int32, c_void_p, c_int64, c_int64, c_void_p]),
     "snp_update_humans_parallel_host": (ctypes.c_int, [c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                                        c_void_p, c_double, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,

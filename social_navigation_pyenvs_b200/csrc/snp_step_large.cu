@@ -27,6 +27,8 @@ template <typename T> struct LargeArgs {
     const T *others;
     long long M, self_offset;
     T *next_view;
+    T *peers[8];  // next-view buffers of every rank (peer-mapped device pointers); the finish kernel stores into all of them
+    int n_peers;
     T *partial;   // [J][2][N_local]
     T *boxes;     // [n_tiles][5] xmin, xmax, ymin, ymax, max(r+s)
     int J, n_tiles;
@@ -206,7 +208,15 @@ __global__ void __launch_bounds__(kTile) k_large_finish(const LargeArgs<T> la) {
         a.dyn[SNP_DYN_OM * N + i] = m.om;
     }
     a.goal_idx[i] = gidx;
-    if (la.next_view) {
+    if (la.n_peers > 0) {
+        // the all-gather of the entity view fused into the producer: every rank's copy of the NEXT view receives this agent's
+        // entry through peer (NVLink) stores, so no separate collective runs between sub-steps -- only a barrier
+        const long long o = la.self_offset + i;
+        for (int p = 0; p < la.n_peers; ++p) {
+            T *v = la.peers[p];
+            v[o] = m.px; v[M + o] = m.py; v[2 * M + o] = m.vx; v[3 * M + o] = m.vy; v[4 * M + o] = m.rs;
+        }
+    } else if (la.next_view) {
         const long long o = la.self_offset + i;
         la.next_view[o] = m.px; la.next_view[M + o] = m.py; la.next_view[2 * M + o] = m.vx; la.next_view[3 * M + o] = m.vy;
         la.next_view[4 * M + o] = m.rs;
@@ -250,8 +260,11 @@ inline long long large_J(long long M) { return (M + kChunk - 1) / kChunk; }
 inline long long large_tiles(long long M) { return (M + kTile - 1) / kTile; }
 
 template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, const void *others, long long M, long long self_offset,
-                                    void *next_view, void *scratch, long long scratch_bytes, cudaStream_t st) {
+                                    void *next_view, const void *const *peer_views, int n_peers, void *scratch, long long scratch_bytes,
+                                    cudaStream_t st) {
     LargeArgs<T> la;
+    la.n_peers = n_peers;
+    for (int p = 0; p < 8; ++p) la.peers[p] = (p < n_peers) ? (T *)peer_views[p] : nullptr;
     KArgs<T> &a = la.k;
     a.E = 1; a.N = 0; a.G = c->G; a.EN = (long long)c->E * c->N;
     a.dyn = (T *)c->dyn; a.stat = (const T *)c->stat; a.goals = (const T *)c->goals; a.goal_idx = c->goal_idx; a.goal_cnt = c->goal_cnt;
@@ -310,8 +323,22 @@ int snp_large_step(const snp_crowd *c, const snp_step_opts *o, const void *other
     if (c->walls_per_env) { set_error("snp_large_step: one wall set per crowd"); return SNP_ERR_INVALID; }
     const long long N = (long long)c->E * c->N;
     if (M < N || self_offset < 0 || self_offset + N > M + 1) { set_error("snp_large_step: M=%lld offset=%lld N=%lld", (long long)M, (long long)self_offset, N); return SNP_ERR_INVALID; }
-    if (c->dtype == SNP_F64) return run_large<double>(c, o, others, M, self_offset, next_view, scratch, scratch_bytes, (cudaStream_t)stream);
-    if (c->dtype == SNP_F32) return run_large<float>(c, o, others, M, self_offset, next_view, scratch, scratch_bytes, (cudaStream_t)stream);
+    if (c->dtype == SNP_F64) return run_large<double>(c, o, others, M, self_offset, next_view, nullptr, 0, scratch, scratch_bytes, (cudaStream_t)stream);
+    if (c->dtype == SNP_F32) return run_large<float>(c, o, others, M, self_offset, next_view, nullptr, 0, scratch, scratch_bytes, (cudaStream_t)stream);
+    set_error("bad dtype %d", c->dtype);
+    return SNP_ERR_INVALID;
+}
+
+int snp_large_step_p2p(const snp_crowd *c, const snp_step_opts *o, const void *others, int64_t M, int64_t self_offset,
+                       const void *const *peer_next_views, int32_t n_peers, void *scratch, int64_t scratch_bytes, void *stream) {
+    if (!c || !o || !others || !peer_next_views) { set_error("snp_large_step_p2p: null argument"); return SNP_ERR_INVALID; }
+    if (n_peers < 1 || n_peers > 8) { set_error("snp_large_step_p2p: 1..8 peers (got %d)", n_peers); return SNP_ERR_INVALID; }
+    if (!c->dyn || !c->stat || !c->goals || !c->goal_idx || !c->goal_cnt) { set_error("snp_large_step_p2p: crowd arrays missing"); return SNP_ERR_INVALID; }
+    if (c->agent_params || c->walls_per_env) { set_error("snp_large_step_p2p: uniform parameters and one wall set only"); return SNP_ERR_UNSUPPORTED; }
+    const long long N = (long long)c->E * c->N;
+    if (M < N || self_offset < 0 || self_offset + N > M + 1) { set_error("snp_large_step_p2p: M=%lld offset=%lld N=%lld", (long long)M, (long long)self_offset, N); return SNP_ERR_INVALID; }
+    if (c->dtype == SNP_F64) return run_large<double>(c, o, others, M, self_offset, nullptr, peer_next_views, n_peers, scratch, scratch_bytes, (cudaStream_t)stream);
+    if (c->dtype == SNP_F32) return run_large<float>(c, o, others, M, self_offset, nullptr, peer_next_views, n_peers, scratch, scratch_bytes, (cudaStream_t)stream);
     set_error("bad dtype %d", c->dtype);
     return SNP_ERR_INVALID;
 }

@@ -17,7 +17,7 @@ from .parallel import all_gather_columns, agent_shard
 
 class LargeCrowd:
     def __init__(self, model, states, goals, walls=None, dtype=torch.float64, device="cuda", symmetric=True, numba_compat=False,
-                 rank=0, world=1, group=None, safety=None):
+                 rank=0, world=1, group=None, safety=None, exchange="auto"):
         """states [N_total,13], goals [N_total,G,2] (the WHOLE crowd on every rank; each rank keeps its slice)."""
         states = np.asarray(states, np.float64)
         goals = np.asarray(goals, np.float64)
@@ -29,7 +29,27 @@ class LargeCrowd:
         self.eng = CrowdEngine.from_reference_arrays(model, states[None, sl], goals[None, sl], walls=walls, safety=saf, consider_robot=False,
                                                      all_params_equal=symmetric, numba_compat=numba_compat, dtype=dtype, device=device)
         self.type = SFMS.index(model)
-        self.view = [torch.zeros((5, self.n_total), dtype=dtype, device=self.eng.device) for _ in range(2)]
+        # exchange of the entity view between ranks: "p2p" = the producer kernel stores into every rank's next view through
+        # peer-mapped (torch symmetric memory, NVLink) pointers and only a barrier separates sub-steps; "nccl" = all-gather
+        # after every sub-step.  "auto" tries p2p on multi-GPU runs and falls back to nccl.
+        self.exchange, self._symm = "nccl", None
+        if world > 1 and exchange in ("auto", "p2p"):
+            try:
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = group if group is not None else dist.group.WORLD
+                self.view = [symm_mem.empty((5, self.n_total), dtype=dtype, device=self.eng.device) for _ in range(2)]
+                for v in self.view:
+                    v.zero_()
+                self._symm = [symm_mem.rendezvous(v, grp) for v in self.view]
+                self._peer_ptrs = [(ctypes.c_void_p * world)(*[int(p) for p in h.buffer_ptrs]) for h in self._symm]
+                self.exchange = "p2p"
+            except Exception as exc:  # no peer access / symmetric memory unavailable
+                if exchange == "p2p":
+                    raise
+                self._p2p_error = repr(exc)
+        if self.exchange == "nccl":
+            self.view = [torch.zeros((5, self.n_total), dtype=dtype, device=self.eng.device) for _ in range(2)]
         nbytes = int(self.eng.lib.snp_large_scratch_bytes(self.n_local, self.n_total, L.SNP_F64 if dtype == torch.float64 else L.SNP_F32))
         self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.eng.device)
         self.culling = True
@@ -41,6 +61,8 @@ class LargeCrowd:
 
     def _gather(self, buf):
         all_gather_columns(buf, self.offset, self.n_local, self.world, self.group)
+        if self.exchange == "p2p":
+            self._symm[0].barrier()
 
     def _publish(self):
         v = self.view[self.cur]
@@ -54,10 +76,16 @@ class LargeCrowd:
         o.reserved = 0 if self.culling else 2  # SNP_OPT_NO_CULLING
         for _ in range(n_substeps):
             cur, nxt = self.view[self.cur], self.view[self.cur ^ 1]
-            L.check(self.eng.lib.snp_large_step(ctypes.byref(c), ctypes.byref(o), ctypes.c_void_p(cur.data_ptr()), self.n_total, self.offset,
-                                                ctypes.c_void_p(nxt.data_ptr()), ctypes.c_void_p(self.scratch.data_ptr()), self.scratch.numel(),
-                                                self._stream()))
-            self._gather(nxt)
+            if self.exchange == "p2p":
+                L.check(self.eng.lib.snp_large_step_p2p(ctypes.byref(c), ctypes.byref(o), ctypes.c_void_p(cur.data_ptr()), self.n_total, self.offset,
+                                                        self._peer_ptrs[self.cur ^ 1], self.world, ctypes.c_void_p(self.scratch.data_ptr()),
+                                                        self.scratch.numel(), self._stream()))
+                self._symm[self.cur ^ 1].barrier()  # every rank's stores into everybody's next view have landed
+            else:
+                L.check(self.eng.lib.snp_large_step(ctypes.byref(c), ctypes.byref(o), ctypes.c_void_p(cur.data_ptr()), self.n_total, self.offset,
+                                                    ctypes.c_void_p(nxt.data_ptr()), ctypes.c_void_p(self.scratch.data_ptr()), self.scratch.numel(),
+                                                    self._stream()))
+                self._gather(nxt)
             self.cur ^= 1
 
     def local_rows(self, template):

@@ -22,14 +22,15 @@ sc = scenarios.jittered_grid_crowd(32, pitch=1.0, jitter=0.3, seed=1)
 S, G = sc["states"][0], sc["goals"][0]
 rng = np.random.RandomState(0)
 S[:, 5:7] = rng.uniform(-0.5, 0.5, (S.shape[0], 2))
-for dtype in (torch.float64, torch.float32):
-    sharded = LargeCrowd("hsfm_new_guo", S, G, dtype=dtype, rank=rank, world=world)
+for dtype, exchange in ((torch.float64, "nccl"), (torch.float32, "nccl"), (torch.float64, "p2p"), (torch.float32, "p2p")):
+    sharded = LargeCrowd("hsfm_new_guo", S, G, dtype=dtype, rank=rank, world=world, exchange=exchange)
+    assert sharded.exchange == exchange
     sharded.step(0.0125, n_substeps=4)
     mine = sharded.local_rows(S[sharded.offset:sharded.offset + sharded.n_local])
     single = LargeCrowd("hsfm_new_guo", S, G, dtype=dtype, rank=0, world=1)
     single.step(0.0125, n_substeps=4)
     ref = single.local_rows(S)[sharded.offset:sharded.offset + sharded.n_local]
-    assert np.array_equal(mine, ref), f"rank {rank}: sharded crowd differs from single-GPU crowd ({dtype})"
+    assert np.array_equal(mine, ref), f"rank {rank}: sharded crowd differs from single-GPU crowd ({dtype}, {exchange})"
 
 # ---- independent envs sharded by env: no collective on the data path ----
 states = np.concatenate([sc_env["states"], sc_env["robot"][:, None]], 1)
