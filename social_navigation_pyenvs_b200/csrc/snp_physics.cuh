@@ -86,13 +86,16 @@ __device__ __forceinline__ void pair_force(const Params<T> &P, const double *tbl
 }
 
 // One wall-segment slot staged in shared memory: a, e = b - a, 1/|e|^2.  ax is NaN for padding slots.
-template <typename T> struct Seg { T ax, ay, ex, ey, inv_len2; };
+// Padded to six words and 16-byte aligned so that a segment is fetched with three LDS.128 (fp64) / LDS.64 + LDS.128 (fp32)
+// instead of five scalar loads.
+template <typename T> struct alignas(16) Seg { T ax, ay, ex, ey, inv_len2, pad; };
 
 template <typename T> __device__ __forceinline__ Seg<T> make_seg(T ax, T ay, T bx, T by) {
     Seg<T> s;
     s.ax = ax; s.ay = ay; s.ex = bx - ax; s.ey = by - ay;
     const T len = np_norm(s.ex, s.ey);
     s.inv_len2 = Real<T>::rcp_(len * len);
+    s.pad = T(0);
     return s;
 }
 
@@ -100,9 +103,9 @@ template <typename T> __device__ __forceinline__ Seg<T> make_seg(T ax, T ay, T b
 // Numba keeps the first (np.argmin, fp:252).  Distances are compared squared (sqrt is monotone; one sqrt per polygon is
 // then taken by the caller instead of one per segment).  Padding slots (ax = NaN) sit at the end of each polygon's slots
 // (motion_model_manager.py:270-275) and `cnt` excludes them.
-template <typename T>
-__device__ __forceinline__ void closest_point(const Seg<T> *segs, int cnt, T px, T py, bool first_wins, T &dxb, T &dyb, T &best) {
-    best = first_wins ? Real<T>::inf() : T(1.0e8);
+template <typename T, bool FIRST_WINS>
+__device__ __forceinline__ void closest_point_impl(const Seg<T> *segs, int cnt, T px, T py, T &dxb, T &dyb, T &best) {
+    best = FIRST_WINS ? Real<T>::inf() : T(1.0e8);
     dxb = px; dyb = py;  // closest point (0,0) when no segment qualifies (obstacle.py:55)
     for (int s = 0; s < cnt; ++s) {
         const Seg<T> g = segs[s];
@@ -112,9 +115,15 @@ __device__ __forceinline__ void closest_point(const Seg<T> *segs, int cnt, T px,
         t = t < T(1) ? t : T(1);
         const T ux = fma_<T>(-t, g.ex, qx), uy = fma_<T>(-t, g.ey, qy);  // p - h,  h = a + t e
         const T d = np_sq(ux, uy);
-        const bool take = first_wins ? (d < best) : (d <= best);
+        const bool take = FIRST_WINS ? (d < best) : (d <= best);
         best = take ? d : best; dxb = take ? ux : dxb; dyb = take ? uy : dyb;
     }
+}
+
+template <typename T>
+__device__ __forceinline__ void closest_point(const Seg<T> *segs, int cnt, T px, T py, bool first_wins, T &dxb, T &dyb, T &best) {
+    if (first_wins) closest_point_impl<T, true>(segs, cnt, px, py, dxb, dyb, best);   // Numba: np.argmin (fp:252)
+    else closest_point_impl<T, false>(segs, cnt, px, py, dxb, dyb, best);             // serial: '<=' keeps the last (obstacle.py:63)
 }
 
 // Wall force of all W polygons on one agent (forces.py:27-53).  OBS: 0 Helbing (mean over walls), 1 Guo (sum; mean in Numba).
