@@ -70,6 +70,8 @@ def _load():
         _lib.orc_imitation_steps.argtypes = [ctypes.POINTER(_Cfg), ctypes.c_int, dp, dp, dp, dp, dp, dp, ctypes.c_double, ctypes.c_int, dp, dp,
                                              ctypes.c_int, dp, dp, ctypes.c_int, dp, ctypes.c_int]
         _lib.orc_imitation_steps.restype = None
+        _lib.orc_lookahead.argtypes = [ctypes.c_int] * 4 + [dp, dp, dp, dp, ctypes.c_double, dp, dp, ctypes.c_int]
+        _lib.orc_lookahead.restype = None
         _lib.orc_checks.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, dp, dp]
         _lib.orc_checks.restype = None
         _lib.orc_laser.argtypes = [ctypes.c_int] * 5 + [dp, dp, dp, ctypes.c_double, ctypes.c_int, ctypes.c_double, dp,
@@ -144,6 +146,19 @@ def imitation_steps(cfg: OracleConfig, states, goals, walls, params, safety, des
                             int(n_steps), _dp(robot), _dp(robot_goals), robot_goals.shape[1], _dp(robot_desired), _dp(_c(robot_params)),
                             int(robot_type), _dp(rsaf), int(n_threads))
     return states, goals, desired, robot, robot_goals, robot_desired
+
+
+def lookahead(cur, nxt, robot, actions, dt, visible=False, n_threads=1):
+    """compute_rotated_states_and_reward (crowd_nav/policy/cadrl.py:42-83) for E envs: cur [E,N,5|7], nxt [E,N,4|6], robot [E,9],
+    actions [A,2].  Returns (rotated [E,A,N,13|15], rewards [E,A])."""
+    lib = _load()
+    cur, nxt, robot, actions = _c(cur), _c(nxt), _c(robot), _c(actions)
+    E, N, _ = cur.shape
+    A = actions.shape[0]
+    rotated = np.zeros((E, A, N, 15 if visible else 13))
+    rewards = np.zeros((E, A))
+    lib.orc_lookahead(E, N, A, int(visible), _dp(cur), _dp(nxt), _dp(robot), _dp(actions), float(dt), _dp(rotated), _dp(rewards), int(n_threads))
+    return rotated, rewards
 
 
 def checks(states, n_humans, robot, action, time_now, consts):

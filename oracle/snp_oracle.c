@@ -538,4 +538,46 @@ void orc_laser(int E, int n, int W, int S, int walls_per_env, const double *huma
     }
 }
 
+/* crowd_nav/policy/cadrl.py:42-83 compute_rotated_states_and_reward with :13-40 transform_state_to_agent_centric (Numba: plain
+ * arithmetic).  cur [E][N][5|7] = px,py,vx,vy,r(,theta,omega); next [E][N][4|6] = x,y,vx,vy | x,y,yaw,vx,vy,omega;
+ * robot [E][9] = px,py,vx,vy,r,gx,gy,vd,theta; actions [A][2]; rotated [E][A][N][13|15]; rewards [E][A]. */
+void orc_lookahead(int E, int N, int A, int visible, const double *cur, const double *next, const double *robot, const double *actions,
+                   double dt, double *rotated, double *rewards, int n_threads) {
+    const int cw = visible ? 7 : 5, nw = visible ? 6 : 4, ow = visible ? 15 : 13;
+#pragma omp parallel for schedule(static) num_threads(n_threads > 0 ? n_threads : 1)
+    for (int e = 0; e < E; ++e) {
+        const double *rb = robot + 9 * (size_t)e;
+        for (int a = 0; a < A; ++a) {
+            const double ax = actions[2 * a], ay = actions[2 * a + 1];
+            const double npx = rb[0] + ax * dt, npy = rb[1] + ay * dt;
+            double dmin = (double)INT64_MAX; int collision = 0;
+            for (int j = 0; j < N; ++j) {
+                const double *h = cur + ((size_t)e * N + j) * cw;
+                const double dx = h[0] - rb[0], dy = h[1] - rb[1];
+                const double ex = dx + (h[2] - ax) * dt, ey = dy + (h[3] - ay) * dt;
+                const double dist = point_to_segment_dist(dx, dy, ex, ey, 0, 0) - h[4] - rb[4];
+                if (dist < 0) { collision = 1; break; }
+                else if (dist >= 0 && dist < dmin) dmin = dist;
+            }
+            const int reached = norm2(npx - rb[5], npy - rb[6]) < rb[4];
+            double rew;
+            if (collision) rew = -0.25; else if (reached) rew = 1; else if (dmin < 0.2) rew = (dmin - 0.2) * 0.5 * dt; else rew = 0;
+            rewards[(size_t)e * A + a] = rew;
+            const double rot = atan2(rb[6] - npy, rb[5] - npx), c = cos(rot), s = sin(rot);
+            for (int j = 0; j < N; ++j) {
+                const double *h = cur + ((size_t)e * N + j) * cw;
+                const double *nx = next + ((size_t)e * N + j) * nw;
+                const double hx = nx[0], hy = nx[1], hvx = visible ? nx[3] : nx[2], hvy = visible ? nx[4] : nx[3];
+                double *o = rotated + (((size_t)e * A + a) * N + j) * ow;
+                o[0] = norm2(rb[5] - npx, rb[6] - npy); o[1] = rb[7]; o[2] = 0.0; o[3] = rb[4];
+                o[4] = ax * c + ay * s; o[5] = ay * c - ax * s;
+                o[6] = (hx - npx) * c + (hy - npy) * s; o[7] = (hy - npy) * c - (hx - npx) * s;
+                o[8] = hvx * c + hvy * s; o[9] = hvy * c - hvx * s;
+                o[10] = h[4]; o[11] = norm2(hx - npx, hy - npy); o[12] = rb[4] + h[4];
+                if (visible) { o[13] = nx[2] - o[2]; o[14] = nx[5]; }
+            }
+        }
+    }
+}
+
 int orc_abi_version(void) { return 1; }

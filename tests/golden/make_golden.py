@@ -297,6 +297,51 @@ def robot_model_cases():
     print("il_robot ->", os.path.getsize(path), "B")
 
 
+def lookahead_case():
+    """The policy-side operator the CrowdNav value-network policies call once per decision (crowd_nav/policy/cadrl.py:42-83
+    compute_rotated_states_and_reward, used by CADRL.predict :235-276): peek of the humans at dt = 0.25
+    (get_next_human_observable_states), then rewards and agent-centric rotated states for all 81 actions."""
+    from crowd_nav.policy.cadrl import compute_rotated_states_and_reward
+    speeds = [(np.exp((i + 1) / 5) - 1) / (np.e - 1) * 1.0 for i in range(5)]            # cadrl.py build_action_space (holonomic)
+    rotations = np.linspace(0, 2 * np.pi, 16, endpoint=False)
+    actions = np.array([[0.0, 0.0]] + [[sp * np.cos(r), sp * np.sin(r)] for r in rotations for sp in speeds])
+    out = {"actions": actions}
+    for model, seed, n, steps in [("hsfm_farina", 1002, 5, 330), ("sfm_helbing", 2003, 6, 200), ("hsfm_new_guo", 2000, 25, 120)]:
+        sim = cc_sim(model, seed, n, robot_visible=False)
+        mm = sim.motion_model_manager
+        for k in range(steps):
+            sim.robot.position = sim.robot.position + np.array([0.0, 1.0]) * DT
+            mm.update_humans(0.0, DT)
+        rng = np.random.RandomState(seed)
+        for rep in range(3):
+            h0 = sim.humans[rng.randint(n)]
+            sim.robot.position = h0.position + rng.uniform(-1.2, 1.2, 2) if rep < 2 else np.array(sim.robot.goals[0], float) - [0.1, 0.2]
+            sim.robot.linear_velocity = rng.uniform(-1, 1, 2)
+            r = sim.robot
+            robot_state = np.array([r.position[0], r.position[1], r.linear_velocity[0], r.linear_velocity[1], r.radius, r.goals[0][0], r.goals[0][1],
+                                    r.desired_speed, r.yaw])
+            for vis in (False, True):
+                if vis:
+                    cur = np.array([[h.position[0], h.position[1], h.linear_velocity[0], h.linear_velocity[1], h.radius, h.yaw, h.angular_velocity]
+                                    for h in sim.humans])
+                    nxt = mm.get_next_human_observable_states(0.25, theta_and_omega_visible=True)[:, :6]
+                else:
+                    cur = np.array([[h.position[0], h.position[1], h.linear_velocity[0], h.linear_velocity[1], h.radius] for h in sim.humans])
+                    nxt = mm.get_next_human_observable_states(0.25)
+                rot, rew = compute_rotated_states_and_reward(actions, nxt, cur, robot_state, 0.25, theta_and_omega_visible=vis)
+                key = f"{model}_{rep}_{int(vis)}"
+                out[key + "_cur"], out[key + "_next"], out[key + "_robot"] = cur, nxt, robot_state
+                out[key + "_rotated"], out[key + "_rewards"] = rot, rew
+            out[f"{model}_{rep}_states"] = np.array([h.get_safe_state() for h in sim.humans])
+            out[f"{model}_{rep}_desired"] = np.array([h.desired_force for h in sim.humans])
+            out[f"{model}_{rep}_goals"] = pack_goals(sim.humans)
+            rw = out[f"{model}_{rep}_0_rewards"]
+            print("lookahead", model, rep, "collisions", int((rw == -0.25).sum()), "goal", int((rw == 1).sum()), "discomfort", int(((rw < 0) & (rw > -0.25)).sum()))
+    path = os.path.join(HERE, "lookahead.npz")
+    np.savez_compressed(path, **out)
+    print("lookahead ->", os.path.getsize(path), "B")
+
+
 def numba_cases():
     """Second witness: the reference's Numba operator update_humans_parallel (forces_parallel.py:184)."""
     out = {}
@@ -511,13 +556,15 @@ def gym_case():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["traj", "pt", "il", "numba", "peek", "flags", "laser", "gym"]
+    which = sys.argv[1:] or ["traj", "pt", "il", "lookahead", "numba", "peek", "flags", "laser", "gym"]
     if "traj" in which:
         traj_cases()
     if "pt" in which:
         pt_cases()
     if "il" in which:
         robot_model_cases()
+    if "lookahead" in which:
+        lookahead_case()
     if "numba" in which:
         numba_cases()
     if "peek" in which:

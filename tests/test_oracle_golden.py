@@ -129,6 +129,21 @@ def test_robot_driven_by_motion_model():
     assert (np.abs(np.diff(rt[:, 8:10], axis=0)).sum(1) > 0).sum() == 1   # the robot's goal list rotated once
 
 
+def test_lookahead_rewards_and_rotated_states():
+    """compute_rotated_states_and_reward (cadrl.py:42-83) for 81 actions: rewards bit-exact, rotated states to 1e-13."""
+    z = np.load(os.path.join(GOLDEN, "lookahead.npz"))
+    keys = sorted(k[:-4] for k in z.files if k.endswith("_cur"))
+    assert len(keys) == 18
+    seen = set()
+    for key in keys:
+        vis = key.endswith("_1")
+        rot, rew = oracle.lookahead(z[key + "_cur"][None], z[key + "_next"][None], z[key + "_robot"][None], z["actions"], 0.25, visible=vis)
+        assert np.array_equal(rew[0], z[key + "_rewards"]), key
+        assert np.abs(rot[0] - z[key + "_rotated"]).max() < 1e-13, key
+        seen |= set(np.unique(np.sign(rew)))
+    assert seen == {-1.0, 0.0, 1.0}
+
+
 def test_numba_operator_semantics():
     """Second witness: numba_compat=1 reproduces forces_parallel.update_humans_parallel (fp:184), including the
     Guo wall force divided by the wall count (fp:161) and '<=' goal switching (fp:226)."""
