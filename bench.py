@@ -36,6 +36,8 @@ WORKLOADS = {
     "65536_hsfm_single_crowd": ("hsfm_farina", 1, 65536, False, False),
     # BASELINE configs[3]: 4096 envs x 360-ray laser over 25 humans + 14 wall segments (metric: rays/s)
     "laser_4096x360": ("hsfm_farina", 4096, 25, True, True),
+    # the value-network policies' one-step lookahead for 4096 envs x 81 actions x 25 humans (metric: rotated rows/s)
+    "lookahead_4096x81x25": ("hsfm_farina", 4096, 25, True, False),
 }
 
 
@@ -331,6 +333,97 @@ def run_laser(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_lookahead(args, rank, world, local_rank):
+    """what CADRL.predict computes per decision (crowd_nav/policy/cadrl.py:235-262) for every env at once: peek of the
+    humans at dt = 0.25 (1 launch of k_step into a side buffer) + rewards and agent-centric states of the 81 actions (1 launch of
+    k_lookahead, 862 MB of output in fp64 -> HBM-write bound).  A step = both launches.  Env-sharded (weak scaling)."""
+    inp = build_inputs("4096x25_hsfm_ccso_walls_robot", 2000 + rank * 4096)
+    import torch
+    import torch.distributed as dist
+    from social_navigation_pyenvs_b200 import CrowdEngine, _lib
+    from social_navigation_pyenvs_b200.parallel import max_over_ranks
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.lib()
+    tdtype = torch.float64 if args.dtype == "f64" else torch.float32
+    E, N = inp["E"], inp["N"]
+    robot = inp["robot"].copy()
+    robot[:, 12] = 1.0
+    eng = CrowdEngine.from_reference_arrays(inp["model"], inp["states"][:, :N], inp["goals"], walls=inp["walls"], safety=inp["safety"][:, :N],
+                                            consider_robot=False, all_params_equal=True, dtype=tdtype, robot=robot)
+    speeds = [(np.exp((i + 1) / 5) - 1) / (np.e - 1) for i in range(5)]  # cadrl.py build_action_space, holonomic, v_pref = 1
+    rots = np.linspace(0, 2 * np.pi, 16, endpoint=False)
+    actions = np.array([[0.0, 0.0]] + [[sp * np.cos(r), sp * np.sin(r)] for r in rots for sp in speeds])
+    eng.set_action_space(actions)
+    A, OW = actions.shape[0], 13
+    bulk = os.environ.get("SNP_LOOKAHEAD_STORE", "bulk") == "bulk"
+    for _ in range(args.warmup):
+        eng.lookahead(0.25, bulk_store=bulk)
+    torch.cuda.synchronize()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    lib.snp_launch_count(1)
+    with ClockSampler(local_rank) as clocks:
+        for s in range(args.steps):
+            flush.fill_(s & 0xFF)
+            ev[s][0].record(stream)
+            nxt = eng.peek(0.25)
+            ev[s][1].record(stream)
+            eng.lookahead_from(nxt, 0.25, bulk_store=bulk)
+            ev[s][2].record(stream)
+        torch.cuda.synchronize()
+    launches = int(lib.snp_launch_count(0))
+    total_ms = max_over_ranks(sum(e[0].elapsed_time(e[2]) for e in ev), "cuda", world)
+    look_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    peek_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    # end to end: the robot's state changes every decision (H2D from pinned memory), the rewards come back (D2H); the rotated
+    # states stay on the device, where the value network that consumes them runs (cadrl.py:255-259)
+    robot_host = eng.robot.cpu().pin_memory()
+    rew_host = torch.empty((E, A), dtype=torch.float64).pin_memory()
+    reps = max(10, args.steps // 2)
+    for it in range(3 + reps):
+        if it == 3:
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        eng.robot.copy_(robot_host, non_blocking=True)
+        _, rew = eng.lookahead(0.25, bulk_store=bulk)
+        rew_host.copy_(rew, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, "cuda", world)
+    if rank == 0:
+        w = 8 if args.dtype == "f64" else 4
+        rows = E * A * N
+        out_bytes = rows * OW * w + E * A * 8
+        in_bytes = E * N * 11 * w + E * 6 * w + A * 16
+        hbm_peak, hbm_src = 6650.0, "fallback"
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            hbm_peak, hbm_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy read+write)"
+        ach = (out_bytes + in_bytes) / (look_ms * 1e-3) / 1e9
+        line = {"metric": "lookahead rows/sec (envs x actions x humans)", "value": world * rows * args.steps / (total_ms * 1e-3), "unit": "rows/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": args.workload, "envs_per_gpu": E, "actions": A, "humans": N, "values_per_row": OW, "time_step": 0.25,
+                           "store": "cp.async.bulk shared->global" if bulk else "per-thread 16-byte stores",
+                           "ms_peek": peek_ms, "ms_lookahead": look_ms, "l2": "256 MiB flush write between timed steps; output (862 MB fp64) exceeds L2"},
+                "clocks": clocks.summary(), "gpu_launches": launches,
+                "e2e": {"value": world * rows * reps / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(robot_host.numel() * robot_host.element_size()),
+                        "d2h_bytes_per_step": int(rew_host.numel() * 8), "api": "CrowdEngine.lookahead: pinned H2D robot state, peek + lookahead, D2H rewards "
+                        "(rotated states stay on the device for the value network)", "steps": reps},
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                             "kernel": "snp::k_lookahead", "bytes_per_row": (out_bytes + in_bytes) / rows, "peak_source": hbm_src}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -355,6 +448,9 @@ def main():
         return
     if args.workload == "laser_4096x360":
         run_laser(args, rank, world, local_rank)
+        return
+    if args.workload == "lookahead_4096x81x25":
+        run_lookahead(args, rank, world, local_rank)
         return
     # host-side scenario generation forks worker processes: do it before CUDA is initialised in this process
     inp = build_inputs(args.workload, 2000 + rank * 4096)  # every rank owns different envs

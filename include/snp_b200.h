@@ -24,6 +24,8 @@
  *   respawn option of snp_step                    <- motion_model_manager.py:407-422 (parallel-traffic post_update)
  *   robot_mode 2 of snp_step                      <- motion_model_manager.py:593-653 update_robot / compute_robot_forces,
  *                                                   social_nav_gym.py:252-274 imitation_learning_step
+ *   snp_lookahead (+ dyn_out peek of snp_step)    <- crowd_nav/policy/cadrl.py:42-83 compute_rotated_states_and_reward, :13-40;
+ *                                                   motion_model_manager.py:691-709 get_next_human_observable_states
  *   snp_pack_states / snp_unpack_states           <- src/agent.py:256-266 get_safe_state / set_state row layout
  *   snp_large_step                                <- same update for one very large crowd (tiled all-pairs)
  */
@@ -123,6 +125,10 @@ typedef struct snp_step_opts {
                                  their goal restart at the right end; rewrites goals[0], goal_cnt (N <= 32 only) */
     int32_t robot_type;       /* robot_mode 2: the robot's model, 0..8 (may differ from the humans') */
     double robot_params[20];  /* robot_mode 2: the robot's parameter row (agent.py:269 for its model) */
+    void *dyn_out;            /* optional [SNP_DYN_FIELDS][E*N]: PEEK (motion_model_manager.py:691-709 get_next_human_observable_states):
+                                 the updated px..omega fields are written here instead of in place and the goal index is not
+                                 advanced; the carried desired force is still updated in place (the reference does not restore it) */
+    int32_t *goal_idx_out;    /* optional [E*N], with dyn_out: the goal index the update arrived at (the peek reports the goal after it) */
 } snp_step_opts;
 
 typedef struct snp_laser_args {
@@ -139,6 +145,21 @@ typedef struct snp_laser_args {
     int32_t *hits;            /* [E][samples] out (optional): human index, N + segment ordinal, or -1 */
 } snp_laser_args;
 
+/* One-step lookahead of the value-network policies (crowd_nav/policy/cadrl.py:42-83 compute_rotated_states_and_reward,
+ * called from CADRL.predict :235-262) for every env of a crowd and every action of the action space. */
+typedef struct snp_lookahead_args {
+    int32_t type;             /* the humans' model 0..8 (headed models take yaw / omega from `next`, the others from the crowd) */
+    int32_t A;                /* number of actions */
+    int32_t theta_and_omega_visible; /* 0: 13 values per (action, human); 1: 15 (cadrl.py:14-21) */
+    int32_t reserved;         /* bit 0: write the rows with per-thread vector stores instead of bulk asynchronous copies (A/B measurement) */
+    const void *next;         /* [SNP_DYN_FIELDS][E*N] the humans one policy time step ahead: output of the peek (snp_step with dyn_out) */
+    const double *actions;    /* [A][2] holonomic velocities (vx, vy), shared by all envs (cadrl.py build_action_space) */
+    double dt;                /* the policy's time step (0.25) */
+    void *rotated;            /* out [E][A][N][13|15] in the crowd's dtype: dg, v_pref, theta, radius, vx, vy, px1, py1, vx1, vy1, radius1, da,
+                                 radius_sum (, theta1, omega1) */
+    double *rewards;          /* out [E][A]: -0.25 collision, 1 goal, (dmin - 0.2) * 0.5 * dt discomfort, 0 (cadrl.py:68-72), bit-exact */
+} snp_lookahead_args;
+
 int snp_abi_version(void);
 const char *snp_last_error(void);
 /* Device properties the host side sizes grids with: sm_count, cc_major, cc_minor, l2_bytes. */
@@ -148,6 +169,8 @@ int snp_device_info(int32_t *out4);
 int snp_step(const snp_crowd *crowd, const snp_step_opts *opts, void *cuda_stream);
 int snp_checks(const snp_crowd *crowd, const snp_step_opts *opts, void *cuda_stream);
 int snp_laser(const snp_laser_args *args, void *cuda_stream);
+/* Uses crowd->dyn (current px,py,vx,vy,theta,omega), crowd->stat (radius) and crowd->robot (px,py,r,gx,gy,vd). */
+int snp_lookahead(const snp_crowd *crowd, const snp_lookahead_args *args, void *cuda_stream);
 /* AoS <-> SoA: rows are the reference's 13-wide float64 state rows [E][rows][13] with the robot (if any) as row N. */
 int snp_unpack_states(const snp_crowd *crowd, const double *rows_dev, int32_t rows_per_env, const double *safety_dev,
                       void *cuda_stream);

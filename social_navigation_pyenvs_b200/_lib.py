@@ -33,7 +33,8 @@ class SnpStepOpts(ctypes.Structure):
                 ("n_substeps", c_int32), ("robot_mode", c_int32), ("dt", c_double), ("action", c_void_p),
                 ("pre_checks", c_int32), ("post_checks", c_int32), ("track_touch", c_int32), ("reserved", c_int32),
                 ("consts", c_double * 6), ("time_now", c_void_p), ("flags", c_void_p), ("checks", c_void_p),
-                ("respawn_bounds", c_double * 2), ("respawn", c_int32), ("robot_type", c_int32), ("robot_params", c_double * 20)]
+                ("respawn_bounds", c_double * 2), ("respawn", c_int32), ("robot_type", c_int32), ("robot_params", c_double * 20),
+                ("dyn_out", c_void_p), ("goal_idx_out", c_void_p)]
 
 
 class SnpLaserArgs(ctypes.Structure):
@@ -44,6 +45,11 @@ class SnpLaserArgs(ctypes.Structure):
                 ("ranges", c_void_p), ("hits", c_void_p)]
 
 
+class SnpLookaheadArgs(ctypes.Structure):
+    _fields_ = [("type", c_int32), ("A", c_int32), ("theta_and_omega_visible", c_int32), ("reserved", c_int32),
+                ("next", c_void_p), ("actions", c_void_p), ("dt", c_double), ("rotated", c_void_p), ("rewards", c_void_p)]
+
+
 # every symbol include/snp_b200.h declares, with its ctypes signature
 _SIGNATURES = {
     "snp_abi_version": (ctypes.c_int, []),
@@ -52,6 +58,7 @@ _SIGNATURES = {
     "snp_step": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpStepOpts), c_void_p]),
     "snp_checks": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpStepOpts), c_void_p]),
     "snp_laser": (ctypes.c_int, [ctypes.POINTER(SnpLaserArgs), c_void_p]),
+    "snp_lookahead": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpLookaheadArgs), c_void_p]),
     "snp_unpack_states": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), c_void_p, c_int32, c_void_p, c_void_p]),
     "snp_pack_states": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), c_void_p, c_int32, c_void_p]),
     "snp_unpack_goals": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), c_void_p, c_void_p, c_void_p]),

@@ -58,25 +58,6 @@ template <typename T> struct SmemLayout {
 
 // ---- checks (double arithmetic, formula-exact; see snp_math.cuh) ----
 
-// utils.py:22-36 point_to_segment_dist(x1, y1, x2, y2, 0, 0) with (x1,y1) = d, (x2,y2) = e.
-__device__ __forceinline__ double origin_to_segment(double x1, double y1, double x2, double y2) {
-    const double px = __dsub_rn(x2, x1), py = __dsub_rn(y2, y1);
-    if (px == 0.0 && py == 0.0) return xnorm_plain(-x1, -y1);
-    double u = __ddiv_rn(__dadd_rn(__dmul_rn(-x1, px), __dmul_rn(-y1, py)), __dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
-    if (u > 1.0) u = 1.0; else if (u < 0.0) u = 0.0;
-    const double x = __dadd_rn(x1, __dmul_rn(u, px)), y = __dadd_rn(y1, __dmul_rn(u, py));
-    return xnorm_plain(x, y);
-}
-
-// social_nav_sim.py:962-976: closest boundary distance between human and robot over one robot step of length T.
-__device__ __forceinline__ double swept_distance(double hx, double hy, double hvx, double hvy, double hr, double rx, double ry,
-                                                 double rr, double ax, double ay, double T) {
-    const double dx = __dsub_rn(hx, rx), dy = __dsub_rn(hy, ry);
-    const double vx = __dsub_rn(hvx, ax), vy = __dsub_rn(hvy, ay);
-    const double ex = __dadd_rn(dx, __dmul_rn(vx, T)), ey = __dadd_rn(dy, __dmul_rn(vy, T));
-    return __dsub_rn(__dsub_rn(origin_to_segment(dx, dy, ex, ey), hr), rr);
-}
-
 // social_nav_sim.py:986-1029.  Returns info code, writes reward / terminated / truncated.
 __device__ __forceinline__ int reward_and_info(bool collision, double dmin, bool goal, double t, const double *c, double &reward,
                                                bool &terminated, bool &truncated) {
@@ -616,15 +597,19 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
 
     // ---- store ----
     if (live && a.n_substeps > 0) {
-        a.dyn[SNP_DYN_PX * EN + aidx] = me.px; a.dyn[SNP_DYN_PY * EN + aidx] = me.py;
-        a.dyn[SNP_DYN_VX * EN + aidx] = me.vx; a.dyn[SNP_DYN_VY * EN + aidx] = me.vy;
+        // peek (get_next_human_observable_states, mmm:691-709): pose and velocities go to a side buffer and the goal index is
+        // left alone; the carried desired force is still updated in place -- the reference does not restore it either
+        T *out = a.dyn_out ? a.dyn_out : a.dyn;
+        out[SNP_DYN_PX * EN + aidx] = me.px; out[SNP_DYN_PY * EN + aidx] = me.py;
+        out[SNP_DYN_VX * EN + aidx] = me.vx; out[SNP_DYN_VY * EN + aidx] = me.vy;
         a.dyn[SNP_DYN_DFX * EN + aidx] = me.dfx; a.dyn[SNP_DYN_DFY * EN + aidx] = me.dfy;
         if (HEADED) {
-            a.dyn[SNP_DYN_TH * EN + aidx] = me.th;
-            a.dyn[SNP_DYN_BVX * EN + aidx] = me.bvx; a.dyn[SNP_DYN_BVY * EN + aidx] = me.bvy;
-            a.dyn[SNP_DYN_OM * EN + aidx] = me.om;
+            out[SNP_DYN_TH * EN + aidx] = me.th;
+            out[SNP_DYN_BVX * EN + aidx] = me.bvx; out[SNP_DYN_BVY * EN + aidx] = me.bvy;
+            out[SNP_DYN_OM * EN + aidx] = me.om;
         }
-        a.goal_idx[aidx] = gidx;
+        if (!a.dyn_out) a.goal_idx[aidx] = gidx;
+        else if (a.goal_idx_out) a.goal_idx_out[aidx] = gidx;
     }
     if (leader) {
         if (has_robot && a.robot_mode == 1) {

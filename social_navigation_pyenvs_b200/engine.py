@@ -87,6 +87,7 @@ class CrowdEngine:
         # reward constants of crowd_nav/configs/env.config: time_limit, collision_penalty, success_reward,
         # discomfort_dist, discomfort_penalty_factor, robot_time_step
         self.consts = [50.0, -0.25, 1.0, 0.2, 0.5, 0.25]
+        self._peek_buf, self._peek_idx, self.action_space, self._rotated, self._rewards = None, None, None, None, None
         self.walls, self.W, self.S, self.walls_per_env = None, 0, 0, 0
         if walls is not None:
             self.set_walls(walls)
@@ -254,8 +255,8 @@ class CrowdEngine:
         df = torch.as_tensor(np.asarray(df, np.float64), dtype=self.dtype, device=self.device)
         self.dyn[L.DYN_DFX].copy_(df[..., 0]); self.dyn[L.DYN_DFY].copy_(df[..., 1])
 
-    def current_goals(self):
-        idx = self.goal_idx.long()[None, None]  # [1,1,E,N]
+    def current_goals(self, goal_idx=None):
+        idx = (self.goal_idx if goal_idx is None else goal_idx).long()[None, None]  # [1,1,E,N]
         return torch.gather(self.goals, 0, idx.expand(1, 2, self.E, self.N))[0].permute(1, 2, 0)  # [E,N,2]
 
     # ------------------------------------------------------------------ the hot path
@@ -334,14 +335,58 @@ class CrowdEngine:
             self.goals[0, 0, e, n] = s[e, n, 6].to(self.dtype); self.goals[0, 1, e, n] = s[e, n, 7].to(self.dtype)
             self.goal_cnt[e, n] = 1
 
+    def peek(self, dt):
+        """One update of length dt into a side buffer (snp_step with dyn_out): returns the [DYN_FIELDS,E,N] device tensor of the
+        humans one step ahead; pose, velocities and goal index of the crowd are untouched.  As in the reference
+        (motion_model_manager.py:691-709) the carried desired force IS updated.  No clone / restore traffic."""
+        if self._peek_buf is None:
+            self._peek_buf, self._peek_idx = torch.empty_like(self.dyn), torch.empty_like(self.goal_idx)
+        o = self._opts(dt, 1, post_update=False)
+        o.dyn_out, o.goal_idx_out = self._peek_buf.data_ptr(), self._peek_idx.data_ptr()
+        L.check(self.lib.snp_step(ctypes.byref(self._crowd()), ctypes.byref(o), _stream()))
+        return self._peek_buf
+
     def get_next_human_observable_states(self, dt, theta_and_omega_visible=False):
-        """motion_model_manager.py:691-709: peek one update of length dt and restore pose, velocity and goal.  As in the
-        reference, the carried desired force is NOT restored."""
-        keep_dyn, keep_idx = self.dyn[:L.DYN_DFX].clone(), self.goal_idx.clone()
-        self.update_humans(0.0, dt, post_update=False)
-        out = self.get_human_states(include_goal=True, headed=False) if theta_and_omega_visible else self.get_human_states(False, False)
-        self.dyn[:L.DYN_DFX].copy_(keep_dyn); self.goal_idx.copy_(keep_idx)
-        return out
+        """motion_model_manager.py:691-709: the humans' observable states one update of length dt ahead, [E,N,4] = x,y,Vx,Vy or
+        [E,N,8] = x,y,yaw,Vx,Vy,Omega,Gx,Gy (:288,:307).  As in the reference, the carried desired force is NOT restored."""
+        nx = self.peek(dt)
+        if not theta_and_omega_visible:
+            return torch.stack([nx[L.DYN_PX], nx[L.DYN_PY], nx[L.DYN_VX], nx[L.DYN_VY]], -1).double().cpu().numpy()
+        ho = nx if self.headed else self.dyn  # non-headed models do not integrate yaw / omega
+        g = self.current_goals(self._peek_idx)  # read before the restore (mmm:705-707): the goal the peeked update arrived at
+        return torch.stack([nx[L.DYN_PX], nx[L.DYN_PY], ho[L.DYN_TH], nx[L.DYN_VX], nx[L.DYN_VY], ho[L.DYN_OM], g[..., 0], g[..., 1]],
+                           -1).double().cpu().numpy()
+
+    # ------------------------------------------------------------------ policy-side lookahead (SURVEY 8f-3)
+    def set_action_space(self, actions):
+        """actions [A,2] holonomic velocities shared by all envs (crowd_nav/policy/cadrl.py build_action_space)."""
+        self.action_space = torch.as_tensor(np.ascontiguousarray(actions, np.float64), device=self.device).reshape(-1, 2).contiguous()
+        self._rotated = self._rewards = None
+
+    def lookahead(self, time_step=0.25, theta_and_omega_visible=False, query_env=True, bulk_store=True):
+        """What CADRL.predict computes before evaluating its value network (crowd_nav/policy/cadrl.py:235-262), for every env:
+        peek the humans `time_step` ahead (query_env; else the constant-velocity model :85-105 is NOT offered -- pass your own
+        `next` through lookahead_from), then compute_rotated_states_and_reward (:42-83) for the whole action space.
+        Returns device tensors (rotated [E,A,N,13|15] in the engine's dtype, rewards [E,A] float64); two launches."""
+        if not query_env:
+            raise NotImplementedError("query_env=False (constant-velocity propagation) is not part of the engine")
+        return self.lookahead_from(self.peek(time_step), time_step, theta_and_omega_visible, bulk_store)
+
+    def lookahead_from(self, nxt, time_step=0.25, theta_and_omega_visible=False, bulk_store=True):
+        if getattr(self, "action_space", None) is None:
+            raise ValueError("set_action_space(actions) first")
+        if self.robot is None:
+            raise ValueError("the lookahead needs the robot's state")
+        A, ow = self.action_space.shape[0], 15 if theta_and_omega_visible else 13
+        if self._rotated is None or self._rotated.shape[-1] != ow:
+            self._rotated = torch.empty((self.E, A, self.N, ow), dtype=self.dtype, device=self.device)
+            self._rewards = torch.empty((self.E, A), dtype=torch.float64, device=self.device)
+        g = L.SnpLookaheadArgs()
+        g.type, g.A, g.theta_and_omega_visible, g.reserved = self.type, A, int(theta_and_omega_visible), 0 if bulk_store else 1
+        g.next, g.actions, g.dt = nxt.data_ptr(), self.action_space.data_ptr(), float(time_step)
+        g.rotated, g.rewards = self._rotated.data_ptr(), self._rewards.data_ptr()
+        L.check(self.lib.snp_lookahead(ctypes.byref(self._crowd()), ctypes.byref(g), _stream()))
+        return self._rotated, self._rewards
 
     def set_safety_space(self, safety_space):
         """motion_model_manager.py:147-164: humans (and a visible robot) get 0.01 + safety_space."""

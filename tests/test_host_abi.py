@@ -32,14 +32,26 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert lib.snp_abi_version() == 1
 
 
-def test_ctypes_struct_layouts_match_the_header():
-    """Field order / sizes of the ctypes mirrors (a drift here would silently corrupt every call)."""
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """Field offsets / sizes of the ctypes mirrors against the header itself, as gcc lays it out (a drift here would silently
+    corrupt every call)."""
+    import subprocess
     from social_navigation_pyenvs_b200 import _lib as L
-    assert ctypes.sizeof(L.SnpCrowd) == 4 * 4 + 6 * 8 + 20 * 8 + 2 * 8 + 3 * 4 + 4  # ints, ptrs, params, ptrs, ints, tail padding
-    assert L.SnpCrowd.params.offset == 64 and L.SnpCrowd.robot.offset == 224 and L.SnpCrowd.W.offset == 240
-    assert L.SnpStepOpts.dt.offset == 24 and L.SnpStepOpts.action.offset == 32 and L.SnpStepOpts.consts.offset == 56
-    assert L.SnpStepOpts.time_now.offset == 104 and L.SnpStepOpts.respawn_bounds.offset == 128 and L.SnpStepOpts.robot_params.offset == 152 and ctypes.sizeof(L.SnpStepOpts) == 312
-    assert L.SnpLaserArgs.pose.offset == 64 and L.SnpLaserArgs.ranges.offset == 96 and ctypes.sizeof(L.SnpLaserArgs) == 112
+    structs = {"snp_crowd": L.SnpCrowd, "snp_step_opts": L.SnpStepOpts, "snp_laser_args": L.SnpLaserArgs, "snp_lookahead_args": L.SnpLookaheadArgs}
+    lines = []
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for f, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "snp_b200.h"\nint main(void) {\n' + "\n".join(lines) + "\nreturn 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for f, _ in cls._fields_:
+            assert int(out[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
