@@ -20,42 +20,51 @@ namespace {
 constexpr int kLookThreads = 256;
 
 struct LookArgs {
-    int E, N, A, visible, headed, chunk;  // chunk = actions per CTA
+    int E, N, A, visible, headed;
+    int chunk;   // actions per tile (one bulk copy)
+    int aper;    // actions per CTA (a CTA walks its range tile by tile)
     long long EN;
     const void *dyn, *stat, *next, *robot;
     const double *actions;
     double dt;
     void *rotated;
     double *rewards;
-    int bulk;  // 1: tile leaves through cp.async.bulk; 0: cooperative vector stores (fallback for comparison)
+    int bulk;  // 1: tiles leave through cp.async.bulk; 0: cooperative vector stores (A/B comparison)
 };
 
-template <typename T> struct PerAction { T npx, npy, c, s, dg, ax, ay; };
+// Per-action quantities shared by the humans of an env: next robot position, (cos, sin) of the rotation, distance to goal.
+template <typename T> struct PerAction { double axd, ayd; T npx, npy, c, s, dg, ax, ay, pad; };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <typename T> struct LookSmem {
+    size_t pa, dist, tile, tile_stride, total;
+    __host__ __device__ LookSmem(int N, int OW, int chunk, int aper) {
+        size_t off = (sizeof(T) * 11 * (size_t)N + 15) & ~size_t(15);
+        pa = off; off = (off + sizeof(PerAction<T>) * (size_t)aper + 15) & ~size_t(15);
+        dist = off; off = (off + 2 * sizeof(double) * (size_t)chunk * N + 15) & ~size_t(15);
+        tile = off;
+        tile_stride = ((size_t)chunk * N * OW * sizeof(T) + 16 + 15) & ~size_t(15);  // + 16: room for the alignment offset
+        total = off + 2 * tile_stride;
+    }
+};
 
 template <typename T>
 __global__ void __launch_bounds__(kLookThreads) k_lookahead(const LookArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.N, OW = a.visible ? 15 : 13;
     const int e = blockIdx.y;
-    const int a0 = blockIdx.x * a.chunk;
-    const int na = min(a.chunk, a.A - a0);
+    const int abeg = blockIdx.x * a.aper;
+    const int acnt = min(a.aper, a.A - abeg);
     const T *dyn = (const T *)a.dyn, *stat = (const T *)a.stat, *nxt = (const T *)a.next, *robot = (const T *)a.robot;
     const long long EN = a.EN, base = (long long)e * N;
 
-    // shared memory: [cur: px py vx vy r | N each][next: x y vx vy th om | N each][per-action][dist: chunk x N doubles][tile]
+    // shared memory: [cur: px py vx vy r | N each][next: x y vx vy th om | N each][per-action][dist x2][tile x2]
+    const LookSmem<T> lay(N, OW, a.chunk, a.aper);
     T *cur = reinterpret_cast<T *>(smem_raw);
     T *nx = cur + 5 * N;
-    size_t off = (sizeof(T) * 11 * (size_t)N + 15) & ~size_t(15);
-    PerAction<T> *pa = reinterpret_cast<PerAction<T> *>(smem_raw + off);
-    off = (off + sizeof(PerAction<T>) * a.chunk + 15) & ~size_t(15);
-    double *dist = reinterpret_cast<double *>(smem_raw + off);
-    off = (off + sizeof(double) * (size_t)a.chunk * N + 15) & ~size_t(15);
-    const size_t row_words = (size_t)N * OW;
-    T *gdst = (T *)a.rotated + ((size_t)e * a.A + a0) * row_words;
-    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(gdst) & 15);
-    T *tile = reinterpret_cast<T *>(smem_raw + off + mis);
+    PerAction<T> *pa = reinterpret_cast<PerAction<T> *>(smem_raw + lay.pa);
+    double *dist_all = reinterpret_cast<double *>(smem_raw + lay.dist);
 
     // ---- stage the env's humans (coalesced SoA loads) and the robot ----
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
@@ -71,25 +80,25 @@ __global__ void __launch_bounds__(kLookThreads) k_lookahead(const LookArgs a) {
     const long long E = a.E;
     const T rpx = robot[SNP_ROBOT_PX * E + e], rpy = robot[SNP_ROBOT_PY * E + e], rr = robot[SNP_ROBOT_R * E + e];
     const T rgx = robot[SNP_ROBOT_GX * E + e], rgy = robot[SNP_ROBOT_GY * E + e], rvd = robot[SNP_ROBOT_VD * E + e];
-    const T dtT = (T)a.dt;
-    // ---- per action: next robot position, rotation (cadrl.py:22,54), distance to goal ----
-    if ((int)threadIdx.x < na) {
-        const int k = threadIdx.x;
-        const double axd = a.actions[2 * (a0 + k)], ayd = a.actions[2 * (a0 + k) + 1];
+    // ---- per action, once per CTA: next robot position (cadrl.py:54), rotation (:22), distance to goal ----
+    // (cos rot, sin rot) with rot = atan2(gy, gx) is the unit vector towards the goal: g / |g| (and (1, 0) for g = 0, atan2(0,0) = 0)
+    // -- one division instead of an atan2 + sincos chain; agrees with the reference's libm round trip to ~1e-16.
+    for (int k = threadIdx.x; k < acnt; k += blockDim.x) {
         PerAction<T> p;
-        p.ax = (T)axd; p.ay = (T)ayd;
-        if (sizeof(T) == 8) {  // no contraction: next_robot_position = p + a * dt (cadrl.py:54)
-            p.npx = (T)__dadd_rn((double)rpx, __dmul_rn(axd, a.dt)); p.npy = (T)__dadd_rn((double)rpy, __dmul_rn(ayd, a.dt));
+        p.axd = a.actions[2 * (abeg + k)]; p.ayd = a.actions[2 * (abeg + k) + 1];
+        p.ax = (T)p.axd; p.ay = (T)p.ayd; p.pad = T(0);
+        if (sizeof(T) == 8) {  // no contraction: p + a * dt
+            p.npx = (T)__dadd_rn((double)rpx, __dmul_rn(p.axd, a.dt)); p.npy = (T)__dadd_rn((double)rpy, __dmul_rn(p.ayd, a.dt));
             const double gx = __dsub_rn((double)rgx, (double)p.npx), gy = __dsub_rn((double)rgy, (double)p.npy);
-            p.dg = (T)xnorm_plain(gx, gy);
-            double sn, cs;
-            sincos(atan2(gy, gx), &sn, &cs);
-            p.c = (T)cs; p.s = (T)sn;
+            const double dg = xnorm_plain(gx, gy);
+            p.dg = (T)dg;
+            const double inv = dg > 0.0 ? 1.0 / dg : 0.0;
+            p.c = (T)(dg > 0.0 ? gx * inv : 1.0); p.s = (T)(gy * inv);
         } else {
+            const T dtT = (T)a.dt;
             p.npx = rpx + p.ax * dtT; p.npy = rpy + p.ay * dtT;
             const T gx = rgx - p.npx, gy = rgy - p.npy;
             p.dg = Real<T>::sqrt_exact(gx * gx + gy * gy);
-            // unit vector towards the goal = (cos rot, sin rot) without the atan2 / sincos round trip (fp32 tolerance 1e-4)
             const T inv = p.dg > T(0) ? T(1) / p.dg : T(0);
             p.c = p.dg > T(0) ? gx * inv : T(1); p.s = gy * inv;
         }
@@ -97,99 +106,122 @@ __global__ void __launch_bounds__(kLookThreads) k_lookahead(const LookArgs a) {
     }
     __syncthreads();
 
-    // ---- a thread per (action, human): swept distance for the reward, rotated row into the tile ----
-    const int pairs = na * N;
-    for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
-        const int k = p / N, j = p - k * N;
-        const PerAction<T> q = pa[k];
-        const T hx = cur[j], hy = cur[N + j], hvx = cur[2 * N + j], hvy = cur[3 * N + j], hr = cur[4 * N + j];
-        dist[p] = swept_distance((double)hx, (double)hy, (double)hvx, (double)hvy, (double)hr, (double)rpx, (double)rpy, (double)rr,
-                                 a.actions[2 * (a0 + k)], a.actions[2 * (a0 + k) + 1], a.dt);
-        const T nxx = nx[j], nxy = nx[N + j], nvx = nx[2 * N + j], nvy = nx[3 * N + j];
-        const T ddx = nxx - q.npx, ddy = nxy - q.npy;
-        T *o = tile + (size_t)p * OW;
-        o[0] = q.dg; o[1] = rvd; o[2] = T(0); o[3] = rr;
-        o[4] = q.ax * q.c + q.ay * q.s; o[5] = q.ay * q.c - q.ax * q.s;
-        o[6] = ddx * q.c + ddy * q.s; o[7] = ddy * q.c - ddx * q.s;
-        o[8] = nvx * q.c + nvy * q.s; o[9] = nvy * q.c - nvx * q.s;
-        o[10] = hr;
-        o[11] = sizeof(T) == 8 ? (T)xnorm_plain((double)ddx, (double)ddy) : Real<T>::sqrt_exact(ddx * ddx + ddy * ddy);
-        o[12] = rr + hr;
-        if (a.visible) { o[13] = nx[4 * N + j] - T(0); o[14] = nx[5 * N + j]; }
-    }
-    if (a.bulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy tile writes -> visible to the bulk copy
-    __syncthreads();
+    const size_t row_words = (size_t)N * OW;
+    const int nchunks = (acnt + a.chunk - 1) / a.chunk;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int c = 0; c < nchunks; ++c) {
+        const int k0 = c * a.chunk;                    // first action of the tile, relative to abeg
+        const int na = min(a.chunk, acnt - k0);
+        const int pairs = na * N;
+        T *gdst = (T *)a.rotated + ((size_t)e * a.A + abeg + k0) * row_words;
+        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(gdst) & 15);
+        // the tile sits in shared memory at the same offset modulo 16 as its destination: both sides of the copy 16-byte aligned
+        T *tile = reinterpret_cast<T *>(smem_raw + lay.tile + (size_t)(c & 1) * lay.tile_stride + mis);
+        double *dist = dist_all + (size_t)(c & 1) * a.chunk * N;
 
-    // ---- tile -> global ----
-    const size_t total = (size_t)pairs * OW * sizeof(T);
-    const size_t head = ((16 - mis) & 15) < total ? ((16 - mis) & 15) : total;
-    const size_t body = (total - head) & ~size_t(15);
-    const size_t tail = total - head - body;
-    unsigned char *g8 = reinterpret_cast<unsigned char *>(gdst);
-    const unsigned char *s8 = reinterpret_cast<const unsigned char *>(tile);
-    if (a.bulk) {
-        if (threadIdx.x == 0 && body) {
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g8 + head), "r"(smem_u32(s8 + head)), "r"((unsigned)body)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // ---- a thread per (action, human): swept distance for the reward, rotated row into the tile ----
+        for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
+            const int k = p / N, j = p - k * N;
+            const PerAction<T> q = pa[k0 + k];
+            const T hx = cur[j], hy = cur[N + j], hvx = cur[2 * N + j], hvy = cur[3 * N + j], hr = cur[4 * N + j];
+            dist[p] = swept_distance((double)hx, (double)hy, (double)hvx, (double)hvy, (double)hr, (double)rpx, (double)rpy, (double)rr,
+                                     q.axd, q.ayd, a.dt);
+            const T nxx = nx[j], nxy = nx[N + j], nvx = nx[2 * N + j], nvy = nx[3 * N + j];
+            const T ddx = nxx - q.npx, ddy = nxy - q.npy;
+            T *o = tile + (size_t)p * OW;
+            o[0] = q.dg; o[1] = rvd; o[2] = T(0); o[3] = rr;
+            o[4] = q.ax * q.c + q.ay * q.s; o[5] = q.ay * q.c - q.ax * q.s;
+            o[6] = ddx * q.c + ddy * q.s; o[7] = ddy * q.c - ddx * q.s;
+            o[8] = nvx * q.c + nvy * q.s; o[9] = nvy * q.c - nvx * q.s;
+            o[10] = hr;
+            o[11] = sizeof(T) == 8 ? (T)xnorm_plain((double)ddx, (double)ddy) : Real<T>::sqrt_exact(ddx * ddx + ddy * ddy);
+            o[12] = rr + hr;
+            if (a.visible) { o[13] = nx[4 * N + j] - T(0); o[14] = nx[5 * N + j]; }
         }
-        // head and tail (< 16 bytes each) in words of T
-        const int hw = (int)(head / sizeof(T)), tw = (int)(tail / sizeof(T));
-        if ((int)threadIdx.x >= 32 && (int)threadIdx.x < 32 + hw) gdst[threadIdx.x - 32] = tile[threadIdx.x - 32];
-        if ((int)threadIdx.x >= 64 && (int)threadIdx.x < 64 + tw) {
-            const size_t w = (head + body) / sizeof(T) + (threadIdx.x - 64);
-            gdst[w] = tile[w];
+        const size_t total = (size_t)pairs * OW * sizeof(T);
+        const size_t head = ((16 - mis) & 15) < total ? ((16 - mis) & 15) : total;
+        const size_t body = (total - head) & ~size_t(15);
+        const size_t tail = total - head - body;
+        unsigned char *g8 = reinterpret_cast<unsigned char *>(gdst);
+        const unsigned char *s8 = reinterpret_cast<const unsigned char *>(tile);
+        if (a.bulk) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy tile writes -> visible to the bulk copy
+            // the copy of tile c-1 (other buffer) has had this whole compute phase to drain; the buffer is rewritten in iteration c+1
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-    } else {
-        const int hw = (int)(head / sizeof(T));
-        if ((int)threadIdx.x < hw) gdst[threadIdx.x] = tile[threadIdx.x];
-        const uint4 *sv = reinterpret_cast<const uint4 *>(s8 + head);
-        uint4 *gv = reinterpret_cast<uint4 *>(g8 + head);
-        for (size_t v = threadIdx.x; v < body / 16; v += blockDim.x) gv[v] = sv[v];
-        const int tw = (int)(tail / sizeof(T));
-        if ((int)threadIdx.x < tw) { const size_t w = (head + body) / sizeof(T) + threadIdx.x; gdst[w] = tile[w]; }
-    }
+        __syncthreads();
 
-    // ---- rewards (cadrl.py:56-72): collision = some human's swept distance < 0; dmin over the others ----
-    if ((int)threadIdx.x < na) {
-        const int k = threadIdx.x;
-        bool collision = false;
-        double dmin = 9223372036854775807.0;  // np.iinfo(np.int64).max
-        for (int j = 0; j < N; ++j) {
-            const double d = dist[k * N + j];
-            if (d < 0) { collision = true; break; }
-            else if (d >= 0 && d < dmin) dmin = d;
+        // ---- tile -> global ----
+        if (a.bulk) {
+            if (threadIdx.x == 0 && body) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g8 + head), "r"(smem_u32(s8 + head)), "r"((unsigned)body)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            // head and tail (< 16 bytes each) in words of T
+            const int hw = (int)(head / sizeof(T)), tw = (int)(tail / sizeof(T));
+            if ((int)threadIdx.x >= 32 && (int)threadIdx.x < 32 + hw) gdst[threadIdx.x - 32] = tile[threadIdx.x - 32];
+            if ((int)threadIdx.x >= 64 && (int)threadIdx.x < 64 + tw) {
+                const size_t w = (head + body) / sizeof(T) + (threadIdx.x - 64);
+                gdst[w] = tile[w];
+            }
+        } else {
+            const int hw = (int)(head / sizeof(T));
+            if ((int)threadIdx.x < hw) gdst[threadIdx.x] = tile[threadIdx.x];
+            const uint4 *sv = reinterpret_cast<const uint4 *>(s8 + head);
+            uint4 *gv = reinterpret_cast<uint4 *>(g8 + head);
+            for (size_t v = threadIdx.x; v < body / 16; v += blockDim.x) gv[v] = sv[v];
+            const int tw = (int)(tail / sizeof(T));
+            if ((int)threadIdx.x < tw) { const size_t w = (head + body) / sizeof(T) + threadIdx.x; gdst[w] = tile[w]; }
+            __syncthreads();  // single-phase fallback: the tile is reused two iterations later, the dist buffer too
         }
-        const double axd = a.actions[2 * (a0 + k)], ayd = a.actions[2 * (a0 + k) + 1];
-        const double npx = __dadd_rn((double)rpx, __dmul_rn(axd, a.dt)), npy = __dadd_rn((double)rpy, __dmul_rn(ayd, a.dt));
-        const bool reached = xnorm_plain(__dsub_rn(npx, (double)rgx), __dsub_rn(npy, (double)rgy)) < (double)rr;
-        double rew;
-        if (collision) rew = -0.25;
-        else if (reached) rew = 1.0;
-        else if (dmin < 0.2) rew = __dmul_rn(__dmul_rn(__dsub_rn(dmin, 0.2), 0.5), a.dt);
-        else rew = 0.0;
-        a.rewards[(size_t)e * a.A + a0 + k] = rew;
+
+        // ---- rewards of this tile (cadrl.py:56-72) by the lanes of one warp (a different one per tile); `break` in the reference
+        //      only cuts the loop short: collision = some swept distance < 0, else dmin = the smallest one ----
+        if (warp == c % nwarps) {
+            for (int k = lane; k < na; k += 32) {
+                bool collision = false;
+                double dmin = 9223372036854775807.0;  // np.iinfo(np.int64).max
+#pragma unroll 5
+                for (int j = 0; j < N; ++j) {
+                    const double d = dist[k * N + j];
+                    collision |= d < 0;
+                    dmin = (d >= 0 && d < dmin) ? d : dmin;
+                }
+                const PerAction<T> q = pa[k0 + k];
+                const double npx = __dadd_rn((double)rpx, __dmul_rn(q.axd, a.dt)), npy = __dadd_rn((double)rpy, __dmul_rn(q.ayd, a.dt));
+                const bool reached = xnorm_plain(__dsub_rn(npx, (double)rgx), __dsub_rn(npy, (double)rgy)) < (double)rr;
+                double rew;
+                if (collision) rew = -0.25;
+                else if (reached) rew = 1.0;
+                else if (dmin < 0.2) rew = __dmul_rn(__dmul_rn(__dsub_rn(dmin, 0.2), 0.5), a.dt);
+                else rew = 0.0;
+                a.rewards[(size_t)e * a.A + abeg + k0 + k] = rew;
+            }
+        }
     }
-    if (a.bulk && threadIdx.x == 0 && body) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // tile must outlive the copy's reads
+    if (a.bulk && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // tiles must outlive the copies' reads
 }
 
 template <typename T> int launch_lookahead(LookArgs a, cudaStream_t st) {
     const int N = a.N, OW = a.visible ? 15 : 13;
-    // actions per CTA: as many (action, human) pairs as threads, balanced over the chunks; capped by the shared-memory tile
+    // actions per tile: as many (action, human) pairs as threads, balanced over the tiles of a CTA; capped by shared memory
     int per = kLookThreads / N;
     if (per < 1) per = 1;
     const size_t row = (size_t)N * OW * sizeof(T);
-    while (per > 1 && per * row > 96 * 1024) --per;
-    const int chunks = (a.A + per - 1) / per;
-    a.chunk = (a.A + chunks - 1) / chunks;
-    size_t smem = (sizeof(T) * 11 * (size_t)N + 15) & ~size_t(15);
-    smem = (smem + sizeof(PerAction<T>) * a.chunk + 15) & ~size_t(15);
-    smem = (smem + sizeof(double) * (size_t)a.chunk * N + 15) & ~size_t(15);
-    smem += 16 + a.chunk * row + 16;
-    if (smem > 200 * 1024) { set_error("snp_lookahead: %d humans x %d values do not fit a shared-memory tile", N, OW); return SNP_ERR_UNSUPPORTED; }
+    while (per > 1 && 2 * per * row > 64 * 1024) --per;
+    // actions per CTA: whole envs when there are enough of them to fill the machine several times over, else split the action range
+    const int sms = device_sm_count();
+    int splits = 1;
+    while (splits < a.A && (long long)a.E * splits < 8LL * 3 * sms) ++splits;
+    a.aper = (a.A + splits - 1) / splits;
+    const int tiles = (a.aper + per - 1) / per;
+    a.chunk = (a.aper + tiles - 1) / tiles;
+    const LookSmem<T> lay(N, OW, a.chunk, a.aper);
+    if (lay.total > 200 * 1024) { set_error("snp_lookahead: %d humans x %d values do not fit a shared-memory tile", N, OW); return SNP_ERR_UNSUPPORTED; }
     auto kern = k_lookahead<T>;
-    if (smem > 48 * 1024) SNP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3((unsigned)((a.A + a.chunk - 1) / a.chunk), (unsigned)a.E), kLookThreads, smem, st>>>(a);
+    if (lay.total > 48 * 1024) SNP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total));
+    kern<<<dim3((unsigned)((a.A + a.aper - 1) / a.aper), (unsigned)a.E), kLookThreads, lay.total, st>>>(a);
     count_launch();
     SNP_CUDA_OK(cudaGetLastError());
     return SNP_OK;
@@ -210,7 +242,7 @@ extern "C" int snp_lookahead(const snp_crowd *c, const snp_lookahead_args *g, vo
     }
     if (g->type < 0 || g->type > 8) { set_error("Type %d does not exist for this implementation", g->type); return SNP_ERR_INVALID; }
     LookArgs a;
-    a.E = c->E; a.N = c->N; a.A = g->A; a.visible = g->theta_and_omega_visible ? 1 : 0; a.headed = g->type >= 3; a.chunk = 1;
+    a.E = c->E; a.N = c->N; a.A = g->A; a.visible = g->theta_and_omega_visible ? 1 : 0; a.headed = g->type >= 3; a.chunk = 1; a.aper = g->A;
     a.EN = (long long)c->E * c->N;
     a.dyn = c->dyn; a.stat = c->stat; a.next = g->next; a.robot = c->robot;
     a.actions = g->actions; a.dt = g->dt; a.rotated = g->rotated; a.rewards = g->rewards;

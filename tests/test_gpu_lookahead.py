@@ -64,10 +64,23 @@ def _actions():
     return np.array([[0.0, 0.0]] + [[s * np.cos(r), s * np.sin(r)] for r in rot for s in speeds])
 
 
+def _oracle_inputs(eng, nxt, vis, sel=slice(None)):
+    """The engine's own device state in the array forms compute_rotated_states_and_reward takes (cadrl.py:43-49)."""
+    from social_navigation_pyenvs_b200 import _lib as L
+    d, st, rb = eng.dyn.double().cpu().numpy()[:, sel], eng.stat.double().cpu().numpy()[:, sel], eng.robot.double().cpu().numpy()[:, sel]
+    nx = nxt.double().cpu().numpy()[:, sel]
+    ho = nx if eng.headed else d
+    cur = np.stack([d[L.DYN_PX], d[L.DYN_PY], d[L.DYN_VX], d[L.DYN_VY], st[L.STAT_R]] + ([d[L.DYN_TH], d[L.DYN_OM]] if vis else []), -1)
+    nxo = np.stack([nx[L.DYN_PX], nx[L.DYN_PY]] + ([ho[L.DYN_TH]] if vis else []) + [nx[L.DYN_VX], nx[L.DYN_VY]] + ([ho[L.DYN_OM]] if vis else []), -1)
+    rob = np.stack([rb[L.ROBOT_PX], rb[L.ROBOT_PY], rb[L.ROBOT_VX], rb[L.ROBOT_VY], rb[L.ROBOT_R], rb[L.ROBOT_GX], rb[L.ROBOT_GY],
+                    rb[L.ROBOT_VD], rb[L.ROBOT_TH]], -1)
+    return cur, nxo, rob
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-4)])
 @pytest.mark.parametrize("n", [5, 25, 40])
 def test_lookahead_vs_oracle_batch(dtype, tol, n):
-    from social_navigation_pyenvs_b200 import CrowdEngine, _lib as L
+    from social_navigation_pyenvs_b200 import CrowdEngine
     E = 96 if n <= 25 else 24  # the rejection sampler of the scenario generator is slow for dense crowds
     sc, S, R = _batch(E, n, 4000 + n)
     acts = _actions()
@@ -76,13 +89,7 @@ def test_lookahead_vs_oracle_batch(dtype, tol, n):
         eng.set_action_space(acts)
         nxt = eng.peek(0.25)
         rot, rew = eng.lookahead_from(nxt, 0.25, theta_and_omega_visible=vis)
-        d, st, rb = eng.dyn.double().cpu().numpy(), eng.stat.double().cpu().numpy(), eng.robot.double().cpu().numpy()
-        nx = nxt.double().cpu().numpy()
-        ho = nx if eng.headed else d
-        cur = np.stack([d[L.DYN_PX], d[L.DYN_PY], d[L.DYN_VX], d[L.DYN_VY], st[L.STAT_R]] + ([d[L.DYN_TH], d[L.DYN_OM]] if vis else []), -1)
-        nxo = np.stack([nx[L.DYN_PX], nx[L.DYN_PY]] + ([ho[L.DYN_TH]] if vis else []) + [nx[L.DYN_VX], nx[L.DYN_VY]] + ([ho[L.DYN_OM]] if vis else []), -1)
-        rob = np.stack([rb[L.ROBOT_PX], rb[L.ROBOT_PY], rb[L.ROBOT_VX], rb[L.ROBOT_VY], rb[L.ROBOT_R], rb[L.ROBOT_GX], rb[L.ROBOT_GY],
-                        rb[L.ROBOT_VD], rb[L.ROBOT_TH]], -1)
+        cur, nxo, rob = _oracle_inputs(eng, nxt, vis)
         rot_ref, rew_ref = oracle.lookahead(cur, nxo, rob, acts, 0.25, visible=vis)
         assert np.array_equal(rew.cpu().numpy(), rew_ref), (model, vis)   # flags-like output: bit-exact (double from the engine's state)
         assert rel_err(rot.double().cpu().numpy(), rot_ref).max() < tol, (model, vis)
@@ -118,3 +125,12 @@ def test_lookahead_full_size_properties(dtype):
     assert ((speed - acts.norm(dim=1)[None, :, None]).abs() <= tol * 2).all()
     ok = (rew == -0.25) | (rew == 1.0) | (rew == 0.0) | ((rew < 0) & (rew >= -0.2 * 0.5 * 0.25))
     assert ok.all() and (rew == -0.25).any() and (rew == 1.0).any()
+    # at this size one CTA walks the whole action space of an env tile by tile (double-buffered bulk copies): oracle on a sample of envs
+    sel = np.r_[0:48, 2000:2016, E - 48:E]
+    cur, nxo, rob = _oracle_inputs(eng, eng._peek_buf, False, sel)
+    rot_ref, rew_ref = oracle.lookahead(cur, nxo, rob, _actions(), 0.25)
+    assert np.array_equal(rew[sel].cpu().numpy(), rew_ref)
+    assert rel_err(rot[sel].double().cpu().numpy(), rot_ref).max() < (1e-9 if dtype == torch.float64 else 1e-4)
+    rot2 = rot.clone()
+    rot3, _ = eng.lookahead(0.25, bulk_store=False)
+    assert torch.equal(rot2, rot3)
