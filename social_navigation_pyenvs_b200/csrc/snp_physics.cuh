@@ -29,13 +29,14 @@ template <typename T> __host__ __device__ inline Params<T> make_params(const dou
 
 // Force exerted on agent 1 by agent 2 (forces.py:63-128).  rs = radius + safety_space.
 // SOC: 0 Helbing, 1 Guo, 2 Moussaid.
-// `vote_mask`: lanes of the warp executing this call together.  The body-compression and sliding-friction terms
-// (k1 max(0,rd), k2 max(0,rd) dv) are identically zero unless the two bodies overlap, which is rare; the warp votes and skips
-// them (and the relative-velocity projection they need) when no lane has a contact.  The result is bit-identical to the
-// always-evaluated form (the skipped terms are exact zeros added to / multiplied into the rest).
-template <typename T, int SOC>
-__device__ __forceinline__ void pair_force(const Params<T> &P, const double *tbl, unsigned vote_mask, T x1, T y1, T vx1, T vy1, T rs1, T x2,
-                                           T y2, T vx2, T vy2, T rs2, T &fx, T &fy) {
+// The body-compression and sliding-friction terms (k1 max(0,rd), k2 max(0,rd) dv) are identically zero unless the two bodies
+// overlap, which is rare.  pair_eval<CONTACT = false> leaves them (and the relative-velocity projection they need) out and is
+// completely branch-free, so several independent evaluations interleave in the pipes; it returns rd = r_ij - d_ij, and callers
+// re-evaluate with CONTACT = true only when some lane of the warp has rd > 0.  For a lane without contact both forms give the
+// same bits (the extra terms are exact zeros added to / multiplied into the rest).
+template <typename T, int SOC, bool CONTACT>
+__device__ __forceinline__ T pair_eval(const Params<T> &P, const double *tbl, T x1, T y1, T vx1, T vy1, T rs1, T x2, T y2, T vx2, T vy2, T rs2,
+                                       T &fx, T &fy) {
     using R = Real<T>;
     const T dx = x1 - x2, dy = y1 - y2;
     const T d2 = fma_<T>(dy, dy, fma_<T>(dx, dx, tiny_<T>()));  // self pair: n = (0,0) -> zero force, no branch (see tiny_)
@@ -43,18 +44,17 @@ __device__ __forceinline__ void pair_force(const Params<T> &P, const double *tbl
     const T dist = d2 * inv;
     const T nx = dx * inv, ny = dy * inv;
     const T rd = (rs1 + rs2) - dist;
-    const bool contact = __any_sync(vote_mask, rd > T(0));
     if (SOC < 2) {
         T cn = P.Ai * R::exp_(rd * P.inv_Bi, tbl);
         T ct = T(0);
-        if (contact) {
+        if (CONTACT) {
             const T prd = max0(rd);
             const T dv = np_dot(vx2 - vx1, vy2 - vy1, -ny, nx);  // t = (-ny, nx); dv = (v2 - v1) . t
             cn = fma_<T>(P.k1, prd, cn);
             ct = P.k2 * prd * dv;
         }
         if (SOC == 1) ct = fma_<T>(P.Ci, R::exp_(rd * P.inv_Di, tbl), ct);
-        if (SOC == 1 || contact) {
+        if (SOC == 1 || CONTACT) {
             fx = fma_<T>(cn, nx, ct * -ny);
             fy = fma_<T>(cn, ny, ct * nx);
         } else {
@@ -74,7 +74,7 @@ __device__ __forceinline__ void pair_force(const Params<T> &P, const double *tbl
         const T a = P.ns1 * F * theta, b = P.ns * F * theta;
         const T ea = R::exp_(-(a * a), tbl), eb = k * R::exp_(-(b * b), tbl);
         T ci = e0 * ea, ch = e0 * eb;  // coefficients of i_ij and h_ij = (-iy, ix)
-        if (contact) {
+        if (CONTACT) {
             const T prd = max0(rd);
             const T dvh = np_dot(vx2 - vx1, vy2 - vy1, -iy, ix);
             ci = fma_<T>(P.k1, prd, ci);
@@ -83,6 +83,15 @@ __device__ __forceinline__ void pair_force(const Params<T> &P, const double *tbl
         fx = -fma_<T>(ci, ix, ch * -iy);
         fy = -fma_<T>(ci, iy, ch * ix);
     }
+    return rd;
+}
+
+// `vote_mask`: lanes of the warp executing this call together.
+template <typename T, int SOC>
+__device__ __forceinline__ void pair_force(const Params<T> &P, const double *tbl, unsigned vote_mask, T x1, T y1, T vx1, T vy1, T rs1, T x2,
+                                           T y2, T vx2, T vy2, T rs2, T &fx, T &fy) {
+    const T rd = pair_eval<T, SOC, false>(P, tbl, x1, y1, vx1, vy1, rs1, x2, y2, vx2, vy2, rs2, fx, fy);
+    if (__any_sync(vote_mask, rd > T(0))) pair_eval<T, SOC, true>(P, tbl, x1, y1, vx1, vy1, rs1, x2, y2, vx2, vy2, rs2, fx, fy);
 }
 
 // One wall-segment slot staged in shared memory: a, e = b - a, 1/|e|^2.  ax is NaN for padding slots.

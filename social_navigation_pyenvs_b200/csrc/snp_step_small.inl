@@ -28,6 +28,12 @@ namespace {
 #define SNP_MINB_F64 4
 #endif
 
+// Pair evaluations of the halved loop issued together (independent, branch-free dependency chains per warp; see halved_rounds).
+#ifndef SNP_PAIR_UNROLL
+#define SNP_PAIR_UNROLL 2
+#endif
+
+constexpr int kPairUnroll = SNP_PAIR_UNROLL;
 constexpr int kWarpsPerBlock = 4;
 constexpr int kRobotParamWords = 24;  // Params<T> of the robot staged in shared memory (21 values, padded)
 constexpr int kSlotsPerWarp = 64;  // >= epw * (N + 1) for every N <= 32
@@ -91,49 +97,80 @@ template <typename T> __device__ __forceinline__ T seg_max_bcast(T v, int i, int
     return __shfl_sync(mask, v, gbase);
 }
 
+// One evaluation of the halved loop: lane i against partner p; for Moussaid the lower index is agent 1 (forces.py:145-151).
+template <typename T, int SOC, bool CONTACT>
+__device__ __forceinline__ T halved_eval(const Params<T> &P, const double *tbl, const Agent<T> &me, const Ent<T> &o, T rsj, bool sw, T &fx, T &fy) {
+    if (SOC == 2) {
+        const T rd = pair_eval<T, SOC, CONTACT>(P, tbl, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
+                                                sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
+        fx = sw ? -fx : fx; fy = sw ? -fy : fy;
+        return rd;
+    }
+    return pair_eval<T, SOC, CONTACT>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+}
+
+// U rounds of the halved loop starting after partner index p / source lane q: the U evaluations are independent and branch-free,
+// so their dependency chains interleave; ONE vote covers the rare contact re-evaluation of all of them.
+template <typename T, int SOC, int U>
+__device__ __forceinline__ void halved_rounds(const Params<T> &P, const double *tbl, const EntView<T> &ents, const T *rs_g, const Agent<T> &me,
+                                              int i, int N, unsigned wmask, int gbase, int &p, int &q, T &fsx, T &fsy) {
+    Ent<T> o[U];
+    T rsj[U], fx[U], fy[U];
+    int src[U];
+    bool sw[U];
+    bool contact = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        p = (p + 1 == N) ? 0 : p + 1;  // partner (i + k) mod N
+        q = (q == 0) ? N - 1 : q - 1;  // the lane whose partner in this round is me: (i - k) mod N
+        o[u] = ents.get(p);
+        rsj[u] = rs_g[p];
+        src[u] = gbase + q;
+        sw[u] = p < i;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) contact |= halved_eval<T, SOC, false>(P, tbl, me, o[u], rsj[u], sw[u], fx[u], fy[u]) > T(0);
+    if (__any_sync(wmask, contact)) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) halved_eval<T, SOC, true>(P, tbl, me, o[u], rsj[u], sw[u], fx[u], fy[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const T rx = __shfl_sync(wmask, fx[u], src[u]), ry = __shfl_sync(wmask, fy[u], src[u]);
+        fsx += fx[u] - rx; fsy += fy[u] - ry;
+    }
+}
+
 template <typename T, int SOC>
 __device__ __forceinline__ void social_force_halved(const Params<T> &P, const double *tbl, const EntView<T> ents, const T *rs_g, const Agent<T> &me,
                                                     int i, int N, bool with_robot, unsigned wmask, int gbase, T &fsx, T &fsy) {
     int p = i, q = i;
     const int rounds = (N - 1) >> 1;
-    for (int k = 1; k <= rounds; ++k) {
-        p = (p + 1 == N) ? 0 : p + 1;  // partner (i + k) mod N
-        q = (q == 0) ? N - 1 : q - 1;  // the lane whose partner in this round is me: (i - k) mod N
-        const Ent<T> o = ents.get(p);
-        const T rsj = rs_g[p];
-        T fx, fy;
-        if (SOC == 2) {
-            const bool sw = p < i;  // the lower index is agent 1
-            pair_force<T, SOC>(P, tbl, wmask, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
-                               sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
-            fx = sw ? -fx : fx; fy = sw ? -fy : fy;
-        } else {
-            pair_force<T, SOC>(P, tbl, wmask, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
-        }
-        const T rx = __shfl_sync(wmask, fx, gbase + q), ry = __shfl_sync(wmask, fy, gbase + q);
-        fsx += fx - rx; fsy += fy - ry;
-    }
-    if (!(N & 1)) {  // antipodal pair: both ends evaluate it
+    int k = 0;
+    for (; k + kPairUnroll <= rounds; k += kPairUnroll) halved_rounds<T, SOC, kPairUnroll>(P, tbl, ents, rs_g, me, i, N, wmask, gbase, p, q, fsx, fsy);
+    for (; k < rounds; ++k) halved_rounds<T, SOC, 1>(P, tbl, ents, rs_g, me, i, N, wmask, gbase, p, q, fsx, fsy);
+    // tail: the antipodal pair of an even crowd (both ends evaluate it) and the robot, which exerts force but feels none
+    // (forces.py:146,151) -- independent evaluations again, one vote
+    const bool anti = !(N & 1);
+    T fax = T(0), fay = T(0), frx = T(0), fry = T(0);
+    Ent<T> oa{}, orb{};
+    T rsa = T(0), rsr = T(0);
+    bool sw = false, contact = false;
+    if (anti) {
         p = (p + 1 == N) ? 0 : p + 1;
-        const Ent<T> o = ents.get(p);
-        const T rsj = rs_g[p];
-        T fx, fy;
-        if (SOC == 2) {
-            const bool sw = p < i;
-            pair_force<T, SOC>(P, tbl, wmask, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
-                               sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
-            fx = sw ? -fx : fx; fy = sw ? -fy : fy;
-        } else {
-            pair_force<T, SOC>(P, tbl, wmask, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
-        }
-        fsx += fx; fsy += fy;
+        oa = ents.get(p); rsa = rs_g[p]; sw = p < i;
+        contact |= halved_eval<T, SOC, false>(P, tbl, me, oa, rsa, sw, fax, fay) > T(0);
     }
-    if (with_robot) {  // the robot exerts force but feels none (forces.py:146,151)
-        const Ent<T> o = ents.get(N);
-        T fx, fy;
-        pair_force<T, SOC>(P, tbl, wmask, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rs_g[N], fx, fy);
-        fsx += fx; fsy += fy;
+    if (with_robot) {
+        orb = ents.get(N); rsr = rs_g[N];
+        contact |= pair_eval<T, SOC, false>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, orb.x, orb.y, orb.vx, orb.vy, rsr, frx, fry) > T(0);
     }
+    if (__any_sync(wmask, contact)) {
+        if (anti) halved_eval<T, SOC, true>(P, tbl, me, oa, rsa, sw, fax, fay);
+        if (with_robot) pair_eval<T, SOC, true>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, orb.x, orb.y, orb.vx, orb.vy, rsr, frx, fry);
+    }
+    fsx += fax; fsy += fay;
+    fsx += frx; fsy += fry;
 }
 
 // ---- robot driven by its own SFM / HSFM model (robot_mode 2; motion_model_manager.py:593-653) ----
