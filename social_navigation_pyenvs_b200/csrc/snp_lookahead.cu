@@ -50,7 +50,7 @@ template <typename T> struct LookSmem {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(kLookThreads) k_lookahead(const LookArgs a) {
+__global__ void __launch_bounds__(kLookThreads, sizeof(T) == 4 ? 4 : 1) k_lookahead(const LookArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.N, OW = a.visible ? 15 : 13;
     const int e = blockIdx.y;
@@ -109,6 +109,38 @@ __global__ void __launch_bounds__(kLookThreads) k_lookahead(const LookArgs a) {
     const size_t row_words = (size_t)N * OW;
     const int nchunks = (acnt + a.chunk - 1) / a.chunk;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // A thread keeps the same (action slot k, human j) in every tile (a tile holds at most blockDim pairs unless N > blockDim):
+    // the human's state and everything of the swept test that does not depend on the action stay in registers across tiles.
+    const int k_own = threadIdx.x / N, j_own = threadIdx.x - k_own * N;
+    const bool own = k_own < a.chunk;
+    struct Human { T hr, nxx, nxy, nvx, nvy, th, om; double dx, dy, hvx, hvy, rsum; };
+    auto load_human = [&](int j) {
+        Human h;
+        h.hr = cur[4 * N + j];
+        h.nxx = nx[j]; h.nxy = nx[N + j]; h.nvx = nx[2 * N + j]; h.nvy = nx[3 * N + j]; h.th = nx[4 * N + j]; h.om = nx[5 * N + j];
+        h.dx = __dsub_rn((double)cur[j], (double)rpx); h.dy = __dsub_rn((double)cur[N + j], (double)rpy);  // sim:962 difference
+        h.hvx = (double)cur[2 * N + j]; h.hvy = (double)cur[3 * N + j];
+        h.rsum = (double)h.hr;
+        return h;
+    };
+    // one (action, human) pair: swept distance (social_nav_sim.py:962-976 via utils.py:22-36, formula-exact) and the rotated row
+    auto do_pair = [&](const Human &h, const PerAction<T> &q, double *dist_out, T *o) {
+        const double vx = __dsub_rn(h.hvx, q.axd), vy = __dsub_rn(h.hvy, q.ayd);
+        const double ex = __dadd_rn(h.dx, __dmul_rn(vx, a.dt)), ey = __dadd_rn(h.dy, __dmul_rn(vy, a.dt));
+        *dist_out = __dsub_rn(__dsub_rn(origin_to_segment(h.dx, h.dy, ex, ey), h.rsum), (double)rr);
+        const T ddx = h.nxx - q.npx, ddy = h.nxy - q.npy;
+        o[0] = q.dg; o[1] = rvd; o[2] = T(0); o[3] = rr;
+        o[4] = q.ax * q.c + q.ay * q.s; o[5] = q.ay * q.c - q.ax * q.s;
+        o[6] = ddx * q.c + ddy * q.s; o[7] = ddy * q.c - ddx * q.s;
+        o[8] = h.nvx * q.c + h.nvy * q.s; o[9] = h.nvy * q.c - h.nvx * q.s;
+        o[10] = h.hr;
+        o[11] = Real<T>::sqrt_(ddx * ddx + ddy * ddy);  // < 1.5 ulp (snp_math.cuh); the rotated states carry the 1e-9 / 1e-4 tolerance
+        o[12] = rr + h.hr;
+        if (a.visible) { o[13] = h.th - T(0); o[14] = h.om; }
+    };
+    Human mine{};
+    if (own) mine = load_human(j_own);
+
     for (int c = 0; c < nchunks; ++c) {
         const int k0 = c * a.chunk;                    // first action of the tile, relative to abeg
         const int na = min(a.chunk, acnt - k0);
@@ -119,24 +151,11 @@ __global__ void __launch_bounds__(kLookThreads) k_lookahead(const LookArgs a) {
         T *tile = reinterpret_cast<T *>(smem_raw + lay.tile + (size_t)(c & 1) * lay.tile_stride + mis);
         double *dist = dist_all + (size_t)(c & 1) * a.chunk * N;
 
-        // ---- a thread per (action, human): swept distance for the reward, rotated row into the tile ----
-        for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
+        // ---- a thread per (action, human) ----
+        if (own && k_own < na) do_pair(mine, pa[k0 + k_own], dist + threadIdx.x, tile + (size_t)threadIdx.x * OW);
+        for (int p = threadIdx.x + blockDim.x; p < pairs; p += blockDim.x) {  // only when a tile holds more pairs than threads
             const int k = p / N, j = p - k * N;
-            const PerAction<T> q = pa[k0 + k];
-            const T hx = cur[j], hy = cur[N + j], hvx = cur[2 * N + j], hvy = cur[3 * N + j], hr = cur[4 * N + j];
-            dist[p] = swept_distance((double)hx, (double)hy, (double)hvx, (double)hvy, (double)hr, (double)rpx, (double)rpy, (double)rr,
-                                     q.axd, q.ayd, a.dt);
-            const T nxx = nx[j], nxy = nx[N + j], nvx = nx[2 * N + j], nvy = nx[3 * N + j];
-            const T ddx = nxx - q.npx, ddy = nxy - q.npy;
-            T *o = tile + (size_t)p * OW;
-            o[0] = q.dg; o[1] = rvd; o[2] = T(0); o[3] = rr;
-            o[4] = q.ax * q.c + q.ay * q.s; o[5] = q.ay * q.c - q.ax * q.s;
-            o[6] = ddx * q.c + ddy * q.s; o[7] = ddy * q.c - ddx * q.s;
-            o[8] = nvx * q.c + nvy * q.s; o[9] = nvy * q.c - nvx * q.s;
-            o[10] = hr;
-            o[11] = sizeof(T) == 8 ? (T)xnorm_plain((double)ddx, (double)ddy) : Real<T>::sqrt_exact(ddx * ddx + ddy * ddy);
-            o[12] = rr + hr;
-            if (a.visible) { o[13] = nx[4 * N + j] - T(0); o[14] = nx[5 * N + j]; }
+            do_pair(load_human(j), pa[k0 + k], dist + p, tile + (size_t)p * OW);
         }
         const size_t total = (size_t)pairs * OW * sizeof(T);
         const size_t head = ((16 - mis) & 15) < total ? ((16 - mis) & 15) : total;

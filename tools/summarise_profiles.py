@@ -19,6 +19,10 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 
 
 def ncu_csv(rep, page, extra=()):
+    """Page of a capture: the CSV tools/profile_round.sh exported on the GPU box, else read from the .ncu-rep here."""
+    exported = rep[:-8] + (".raw.csv" if page == "raw" else ".source.csv")
+    if os.path.exists(exported):
+        return list(csv.reader(open(exported)))
     return list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", page, "--csv", *extra], capture_output=True, text=True).stdout.splitlines()))
 
 
@@ -39,7 +43,8 @@ def launches():
 
 
 def metrics():
-    reps = [f for f in sorted(os.listdir(SRC)) if f.startswith(R + "_k_") and f.endswith(".ncu-rep")]
+    reps = sorted({f[:-8] + ".ncu-rep" for f in os.listdir(SRC) if f.startswith(R + "_k_") and f.endswith(".raw.csv")} |
+                  {f for f in os.listdir(SRC) if f.startswith(R + "_k_") and f.endswith(".ncu-rep")})
     cols, names = [], []
     for f in reps:
         rows = ncu_csv(os.path.join(SRC, f), "raw")
