@@ -50,7 +50,7 @@ template <typename T> struct LookSmem {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(kLookThreads, sizeof(T) == 4 ? 4 : 1) k_lookahead(const LookArgs a) {
+__global__ void __launch_bounds__(kLookThreads, sizeof(T) == 4 ? 4 : 3) k_lookahead(const LookArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.N, OW = a.visible ? 15 : 13;
     const int e = blockIdx.y;
