@@ -26,6 +26,7 @@
  *                                                   social_nav_gym.py:252-274 imitation_learning_step
  *   snp_lookahead (+ dyn_out peek of snp_step)    <- crowd_nav/policy/cadrl.py:42-83 compute_rotated_states_and_reward, :13-40;
  *                                                   motion_model_manager.py:691-709 get_next_human_observable_states
+ *   snp_reset                                     <- social_nav_gym.py:120-225 reset, social_nav_sim.py:200-431 scenario generators
  *   snp_pack_states / snp_unpack_states           <- src/agent.py:256-266 get_safe_state / set_state row layout
  *   snp_large_step                                <- same update for one very large crowd (tiled all-pairs)
  */
@@ -128,6 +129,8 @@ typedef struct snp_step_opts {
     void *dyn_out;            /* optional [SNP_DYN_FIELDS][E*N]: PEEK (motion_model_manager.py:691-709 get_next_human_observable_states):
                                  the updated px..omega fields are written here instead of in place and the goal index is not
                                  advanced; the carried desired force is still updated in place (the reference does not restore it) */
+    const int32_t *respawn_envs; /* optional [E], with respawn: only envs with a non-zero entry respawn (hybrid scenario: the parallel-traffic
+                                 envs of a mixed batch; snp_reset's scenario_out works as is) */
     int32_t *goal_idx_out;    /* optional [E*N], with dyn_out: the goal index the update arrived at (the peek reports the goal after it) */
 } snp_step_opts;
 
@@ -160,6 +163,29 @@ typedef struct snp_lookahead_args {
     double *rewards;          /* out [E][A]: -0.25 collision, 1 goal, (dmin - 0.2) * 0.5 * dt discomfort, 0 (cadrl.py:68-72), bit-exact */
 } snp_lookahead_args;
 
+/* SocialNavGym.reset for every (selected) environment of a crowd, on the device (social_gym/social_nav_gym.py:120-225): env e replays
+ * the reference's scenario generator (social_gym/social_nav_sim.py:200-299 circular crossing, :301-362 parallel traffic, :364-431
+ * circular crossing with static obstacles; insert_robot = True, randomize_human_positions = True) on NumPy's own MT19937 stream seeded
+ * with seeds[e] (the gym seeds np.random with offset[phase] + case, social_nav_gym.py:135-137): same draws, same accept / reject
+ * decisions, positions equal up to the last ulp of cos / sin. */
+enum { SNP_RESET_CIRCULAR_CROSSING = 0, SNP_RESET_PARALLEL_TRAFFIC = 1, SNP_RESET_CCSO = 2,
+       SNP_RESET_CCSO_SYNTHETIC = 3, /* 3 static humans + the circular-crossing sampler: the 25-human crowd of SURVEY.md 8(d) config 3 */
+       SNP_RESET_HYBRID = 4          /* np.random.choice between the first two, then re-seed (social_nav_gym.py:155-157) */ };
+typedef struct snp_reset_args {
+    int32_t scenario;
+    int32_t randomize_attributes; /* desired speed ~ U(0.5,1.5), radius ~ U(0.3,0.5) per human, drawn first (social_nav_sim.py:217-220) */
+    const uint32_t *seeds;        /* optional [E] device: np.random.seed argument of each env; NULL -> seed0 + env index */
+    uint32_t seed0;
+    uint32_t reserved;
+    const uint8_t *mask;          /* optional [E] device: only envs with a non-zero entry are reset (restart of finished episodes) */
+    double circle_radius, robot_radius, traffic_length, traffic_height;
+    double human_mass, robot_mass, robot_desired_speed; /* 75 (social_nav_sim.py:141), 80 (robot_agent.py:16), 1 */
+    double *time_now;             /* optional [E]: set to 0 (social_nav_gym.py:129) */
+    int32_t *flags;               /* optional [E]: cleared */
+    int32_t *scenario_out;        /* optional [E]: the scenario generated (the hybrid scenario's coin) */
+    int32_t *draws_out;           /* optional [E]: number of uniforms the generator consumed */
+} snp_reset_args;
+
 int snp_abi_version(void);
 const char *snp_last_error(void);
 /* Device properties the host side sizes grids with: sm_count, cc_major, cc_minor, l2_bytes. */
@@ -169,6 +195,8 @@ int snp_device_info(int32_t *out4);
 int snp_step(const snp_crowd *crowd, const snp_step_opts *opts, void *cuda_stream);
 int snp_checks(const snp_crowd *crowd, const snp_step_opts *opts, void *cuda_stream);
 int snp_laser(const snp_laser_args *args, void *cuda_stream);
+/* Rewrites crowd->dyn, stat (radius, mass, desired speed; the safety space is kept), goals, goal_idx, goal_cnt and crowd->robot. */
+int snp_reset(const snp_crowd *crowd, const snp_reset_args *args, void *cuda_stream);
 /* Uses crowd->dyn (current px,py,vx,vy,theta,omega), crowd->stat (radius) and crowd->robot (px,py,r,gx,gy,vd). */
 int snp_lookahead(const snp_crowd *crowd, const snp_lookahead_args *args, void *cuda_stream);
 /* AoS <-> SoA: rows are the reference's 13-wide float64 state rows [E][rows][13] with the robot (if any) as row N. */

@@ -34,7 +34,7 @@ class SnpStepOpts(ctypes.Structure):
                 ("pre_checks", c_int32), ("post_checks", c_int32), ("track_touch", c_int32), ("reserved", c_int32),
                 ("consts", c_double * 6), ("time_now", c_void_p), ("flags", c_void_p), ("checks", c_void_p),
                 ("respawn_bounds", c_double * 2), ("respawn", c_int32), ("robot_type", c_int32), ("robot_params", c_double * 20),
-                ("dyn_out", c_void_p), ("goal_idx_out", c_void_p)]
+                ("dyn_out", c_void_p), ("respawn_envs", c_void_p), ("goal_idx_out", c_void_p)]
 
 
 class SnpLaserArgs(ctypes.Structure):
@@ -50,6 +50,17 @@ class SnpLookaheadArgs(ctypes.Structure):
                 ("next", c_void_p), ("actions", c_void_p), ("dt", c_double), ("rotated", c_void_p), ("rewards", c_void_p)]
 
 
+class SnpResetArgs(ctypes.Structure):
+    _fields_ = [("scenario", c_int32), ("randomize_attributes", c_int32), ("seeds", c_void_p), ("seed0", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32), ("mask", c_void_p), ("circle_radius", c_double), ("robot_radius", c_double),
+                ("traffic_length", c_double), ("traffic_height", c_double), ("human_mass", c_double), ("robot_mass", c_double),
+                ("robot_desired_speed", c_double), ("time_now", c_void_p), ("flags", c_void_p), ("scenario_out", c_void_p),
+                ("draws_out", c_void_p)]
+
+
+RESET_SCENARIOS = {"circle_crossing": 0, "circular_crossing": 0, "parallel_traffic": 1, "circular_crossing_with_static_obstacles": 2,
+                   "ccso_synthetic": 3, "hybrid_scenario": 4}
+
 # every symbol include/snp_b200.h declares, with its ctypes signature
 _SIGNATURES = {
     "snp_abi_version": (ctypes.c_int, []),
@@ -59,6 +70,7 @@ _SIGNATURES = {
     "snp_checks": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpStepOpts), c_void_p]),
     "snp_laser": (ctypes.c_int, [ctypes.POINTER(SnpLaserArgs), c_void_p]),
     "snp_lookahead": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpLookaheadArgs), c_void_p]),
+    "snp_reset": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpResetArgs), c_void_p]),
     "snp_unpack_states": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), c_void_p, c_int32, c_void_p, c_void_p]),
     "snp_pack_states": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), c_void_p, c_int32, c_void_p]),
     "snp_unpack_goals": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), c_void_p, c_void_p, c_void_p]),

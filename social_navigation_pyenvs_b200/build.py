@@ -30,9 +30,14 @@ def _deps_mtime():
     return max(os.path.getmtime(f) for f in files)
 
 
+# The reset kernel replays the reference's scenario generators operation by operation (csrc/snp_reset_core.h): no FMA contraction
+# there, so that a + b * c rounds twice as in NumPy (explicit fma() calls are kept).
+PER_FILE_FLAGS = {"snp_reset.cu": ["-fmad=false"]}
+
+
 def _compile(src, verbose, extra=(), obj_dir=OBJ):
     obj = os.path.join(obj_dir, src[:-3] + ".o")
-    cmd = ["nvcc", *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = ["nvcc", *NVCC_FLAGS, *PER_FILE_FLAGS.get(src, []), *extra, "-c", os.path.join(CSRC, src), "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

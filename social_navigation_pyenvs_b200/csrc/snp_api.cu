@@ -68,7 +68,7 @@ template <typename T> static int build_args(const snp_crowd *c, const snp_step_o
     a.epw = 1; a.gpb = 1;
     a.mapping = (o->reserved >> 2) & 3;  // bits 2-3 of `reserved`: thread mapping override (tests / tuning)
     a.full_pair_loop = o->reserved & 1;  // bit 0 of `reserved`: SNP_OPT_FULL_PAIR_LOOP
-    a.dyn_out = (T *)o->dyn_out; a.goal_idx_out = o->goal_idx_out;
+    a.dyn_out = (T *)o->dyn_out; a.goal_idx_out = o->goal_idx_out; a.respawn_envs = o->respawn_envs;
     if (o->dyn_out && (o->respawn || o->robot_mode == 2)) { set_error("dyn_out (peek) cannot be combined with respawn or robot_mode 2"); return SNP_ERR_INVALID; }
     return SNP_OK;
 }

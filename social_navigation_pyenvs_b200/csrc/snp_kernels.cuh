@@ -48,6 +48,7 @@ template <typename T> struct KArgs {
     int gpb;  // env groups per block (block-packed kernel)
     int mapping;  // 0 auto, 1 warp-packed, 2 block-packed
     int full_pair_loop;  // 1: always evaluate ordered pairs in j-ascending order (the reference's accumulation order)
+    const int *respawn_envs;  // optional per-env respawn switch
     int *goal_idx_out;  // peek: goal index after the update (optional)
     T *dyn_out;  // peek: updated pose / velocities are written here instead of in place (goal index untouched)
 };

@@ -1,0 +1,186 @@
+// snp_reset_core.h -- the reference's scenario generators as host/device code driven by NumPy's own random stream.
+//
+// SocialNavGym.reset (social_gym/social_nav_gym.py:120-225) seeds the GLOBAL np.random with `offset[phase] + case` (:135-137) and
+// calls one of the rejection samplers of social_gym/social_nav_sim.py: :200-299 circular crossing, :301-362 parallel traffic,
+// :364-431 circular crossing with static obstacles; the hybrid scenario first flips np.random.choice between the first two and
+// re-seeds (social_nav_gym.py:155-157).  All of them draw through np.random.random() / np.random.uniform() only, i.e. through
+// MT19937 + random_double of the legacy RandomState.  Reproducing that generator per environment makes an on-device reset
+// consume EXACTLY the reference's draw sequence: same accept / reject decisions, same number of draws, positions equal to the
+// last ulp of cos / sin.  (SURVEY.md 8f-4 expected distribution-level parity only.)
+//
+// The code below is shared by the CUDA kernel (snp_reset.cu, one thread per environment, generator state in shared memory) and by
+// a host harness the CPU tests compile with g++ (tests/reset_core_host.cpp), so the logic is checked against the recorded reference
+// outputs without a GPU.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define SNP_HD __host__ __device__ __forceinline__
+#else
+#define SNP_HD inline
+#endif
+
+namespace snp {
+
+enum { SNP_SCEN_CIRCULAR_CROSSING = 0, SNP_SCEN_PARALLEL_TRAFFIC = 1, SNP_SCEN_CCSO = 2, SNP_SCEN_CCSO_SYNTHETIC = 3, SNP_SCEN_HYBRID = 4 };
+
+// numpy/random/src/mt19937/mt19937.c: mt19937_seed (np.random.seed(int)), mt19937_gen, and random_double of the legacy
+// distributions: (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53.  `stride` lets 32 generators interleave their state words.
+struct Mt19937 {
+    uint32_t *mt;
+    int stride, pos;
+    long long draws;
+    SNP_HD uint32_t &at(int i) { return mt[(size_t)i * stride]; }
+    SNP_HD void seed(uint32_t s) {
+        for (int i = 0; i < 624; ++i) { at(i) = s; s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)(i + 1); }
+        pos = 624;
+    }
+    SNP_HD void twist() {
+        const uint32_t UP = 0x80000000u, LO = 0x7fffffffu, A = 0x9908b0dfu;
+        int kk = 0;
+        uint32_t y;
+        for (; kk < 624 - 397; ++kk) { y = (at(kk) & UP) | (at(kk + 1) & LO); at(kk) = at(kk + 397) ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+        for (; kk < 623; ++kk) { y = (at(kk) & UP) | (at(kk + 1) & LO); at(kk) = at(kk + (397 - 624)) ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+        y = (at(623) & UP) | (at(0) & LO);
+        at(623) = at(396) ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+        pos = 0;
+    }
+    SNP_HD uint32_t next32() {
+        if (pos == 624) twist();
+        uint32_t y = at(pos++);
+        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+        return y;
+    }
+    SNP_HD double random() {  // np.random.random()
+        const uint32_t a = next32() >> 5, b = next32() >> 6;
+        ++draws;
+        return (a * 67108864.0 + b) / 9007199254740992.0;
+    }
+    SNP_HD double uniform(double lo, double hi) { return lo + (hi - lo) * random(); }  // np.random.uniform
+};
+
+struct ResetParams {
+    int scenario, N, randomize_attributes;
+    double circle_radius, robot_radius, traffic_length, traffic_height;
+};
+
+// Scratch of one environment: positions, radii and desired speeds of the humans placed so far (strided like the generator state).
+struct ResetScratch {
+    double *px, *py, *rad, *vd;
+    int stride;
+    SNP_HD double &X(int i) { return px[(size_t)i * stride]; }
+    SNP_HD double &Y(int i) { return py[(size_t)i * stride]; }
+    SNP_HD double &R(int i) { return rad[(size_t)i * stride]; }
+    SNP_HD double &V(int i) { return vd[(size_t)i * stride]; }
+};
+
+SNP_HD double reset_norm(double x, double y) { return sqrt(fma(y, y, x * x)); }  // np.linalg.norm of a length-2 vector
+SNP_HD double reset_bound_angle(double a) {                                         // utils.py:7-13
+    const double pi = 3.141592653589793, two_pi = 2 * pi;
+    if (a >= two_pi) a = fmod(a, two_pi);
+    if (a <= -two_pi) a = fmod(a, -two_pi);
+    if (a > pi) a -= two_pi;
+    if (a < -pi) a += two_pi;
+    return a;
+}
+
+// One human of the result: state-row fields (agent.py:256) that differ from zero, and its goal list.
+struct ResetHuman { double x, y, yaw, radius, vd, g0x, g0y, g1x, g1y; int goal_count; };
+
+// Runs the generator of `p.scenario` for one environment seeded with `seed`; calls emit(i, ResetHuman) for every human in order.
+// Returns the scenario that was generated (the coin of the hybrid scenario, else p.scenario).
+template <class Emit>
+SNP_HD int reset_generate(const ResetParams &p, uint32_t seed, Mt19937 &rng, ResetScratch &w, Emit &emit) {
+    const double pi = 3.141592653589793;
+    const int N = p.N;
+    rng.draws = 0;
+    rng.seed(seed);
+    int scen = p.scenario;
+    if (scen == SNP_SCEN_HYBRID) {  // np.random.choice(['circle_crossing', 'parallel_traffic']); np.random.seed(...) again (gym:155-157)
+        scen = (rng.next32() & 1u) ? SNP_SCEN_PARALLEL_TRAFFIC : SNP_SCEN_CIRCULAR_CROSSING;
+        rng.seed(seed);
+    }
+    // ---- attributes (sim:217-224, :318-326, :381-388) ----
+    if (scen == SNP_SCEN_CCSO || scen == SNP_SCEN_CCSO_SYNTHETIC) {
+        if (scen == SNP_SCEN_CCSO) {
+            for (int i = 0; i < N; ++i) { w.V(i) = i < 3 ? 0.0 : 1.0; w.R(i) = i < 3 ? 1 + (rng.random() - 1) * 0.4 : 0.3; }
+        } else {
+            for (int i = 0; i < N; ++i) { w.V(i) = i < 3 ? 0.0 : 1.0; w.R(i) = 0.3; }
+            for (int i = 0; i < 3 && i < N; ++i) w.R(i) = 1 + (rng.random() - 1) * 0.4;
+        }
+    } else if (p.randomize_attributes) {
+        for (int i = 0; i < N; ++i) { w.V(i) = rng.uniform(0.5, 1.5); w.R(i) = rng.uniform(0.3, 0.5); }
+    } else {
+        for (int i = 0; i < N; ++i) { w.V(i) = 1.0; w.R(i) = 0.3; }
+    }
+    if (scen == SNP_SCEN_PARALLEL_TRAFFIC) {  // sim:330-352
+        const double half = p.traffic_length / 2;
+        const double rx = -half + 1, ry = 0.0;
+        for (int i = 0; i < N; ++i) {
+            double x, y;
+            for (;;) {
+                const double ri = w.R(i);
+                const double a = -half + ri, b = half - ri;
+                x = (b - a) * rng.random() + a;
+                y = (rng.random() - 0.5) * p.traffic_height;
+                bool collide = false;
+                for (int j = 0; j < i; ++j)
+                    if (reset_norm(x - w.X(j), y - w.Y(j)) - ri - w.R(j) - 0.1 < 0) { collide = true; break; }
+                if (reset_norm(x - rx, y - ry) - ri - p.robot_radius - 0.1 < 0) collide = true;
+                if (!collide) break;
+            }
+            w.X(i) = x; w.Y(i) = y;
+            ResetHuman h{x, y, reset_bound_angle(-pi), w.R(i), w.V(i), -half - 3, y, 0.0, 0.0, 1};
+            h.g1x = h.g0x; h.g1y = h.g0y;
+            emit(i, h);
+        }
+        return scen;
+    }
+    // ---- the circular scenarios ----
+    const double R = p.circle_radius, inner = R - 3.0;
+    const double slot = scen == SNP_SCEN_CCSO ? pi / (double)(N / 2) : pi / 4;
+    for (int i = 0; i < N; ++i) {
+        const bool is_static = (scen == SNP_SCEN_CCSO || scen == SNP_SCEN_CCSO_SYNTHETIC) && i < 3;
+        const double ri = w.R(i);
+        double x, y, angle;
+        for (;;) {
+            if (is_static) {                      // sim:393-396
+                angle = slot * (-0.5 + 2 * i + (rng.random() - 0.5) * 0.5);
+                const double n0 = (rng.random() - 0.5) * 0.1, n1 = (rng.random() - 0.5) * 0.1;
+                x = inner * cos(angle) + n0; y = inner * sin(angle) + n1;
+            } else if (scen == SNP_SCEN_CCSO) {   // sim:397-400
+                angle = slot * (0.5 + 2 * i + (rng.random() - 0.5) * 0.5);
+                const double n0 = (rng.random() - 0.5) * 0.7, n1 = (rng.random() - 0.5) * 0.7;
+                x = R * cos(angle) + n0; y = R * sin(angle) + n1;
+            } else {                              // sim:274-276
+                angle = rng.random() * pi * 2;
+                const double n0 = (rng.random() - 0.5) * w.V(i), n1 = (rng.random() - 0.5) * w.V(i);
+                x = R * cos(angle) + n0; y = R * sin(angle) + n1;
+            }
+            bool collide = false;
+            for (int j = 0; j < i; ++j) {
+                const double md = ri + w.R(j) + 0.2;
+                const double ox = w.X(j), oy = w.Y(j);
+                const bool other_static = (scen == SNP_SCEN_CCSO || scen == SNP_SCEN_CCSO_SYNTHETIC) && j < 3;
+                if (reset_norm(x - ox, y - oy) < md) { collide = true; break; }
+                // the synthetic 25-human crowd tests its static humans against positions only (scenarios.py ccso_synthetic)
+                if (!(scen == SNP_SCEN_CCSO_SYNTHETIC && is_static)) {
+                    const double gx = other_static ? ox : -ox, gy = other_static ? oy : -oy;
+                    if (reset_norm(x - gx, y - gy) < md) { collide = true; break; }
+                }
+            }
+            if (!(scen == SNP_SCEN_CCSO_SYNTHETIC && is_static)) {
+                const double rm = ri + p.robot_radius + 0.2;
+                if (reset_norm(x - 0.0, y - (-R)) < rm || reset_norm(x - 0.0, y - R) < rm) collide = true;
+            }
+            if (!collide) break;
+        }
+        w.X(i) = x; w.Y(i) = y;
+        ResetHuman h{x, y, reset_bound_angle(pi + angle), ri, w.V(i), is_static ? x : -x, is_static ? y : -y, x, y, 2};
+        emit(i, h);
+    }
+    return scen;
+}
+
+}  // namespace snp

@@ -555,7 +555,8 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             if (a.respawn) {
                 const int gbase = lane - i;
                 const unsigned gm = (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) << gbase;
-                unsigned pending = __ballot_sync(wmask, np_norm(me.px - me.gx, me.py - me.gy) < T(3));
+                const bool env_on = !a.respawn_envs || a.respawn_envs[env] != 0;
+                unsigned pending = __ballot_sync(wmask, env_on && np_norm(me.px - me.gx, me.py - me.gy) < T(3));
                 if (pending) {
                     T rsmax = seg_max_bcast<T>(me.rs, i, N, gbase, wmask);
                     if (a.consider_robot) rsmax = rrs > rsmax ? rrs : rsmax;

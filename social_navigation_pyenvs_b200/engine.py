@@ -69,6 +69,7 @@ class CrowdEngine:
         # j-ascending order, the reference's own accumulation order (forces.py:145-151).  Same result up to rounding.
         self.full_pair_loop = bool(full_pair_loop)
         self.robot_type, self.robot_params = None, None  # set_robot_motion_model
+        self.respawn_envs = None    # optional int32 [E]: which envs respawn (hybrid scenario); None = all
         self.respawn_bounds = None  # (traffic_length/2, traffic_height/2): parallel-traffic respawn after every update (mmm:407-422)
         self.mapping = 0  # 0 auto, 1 force warp-packed, 2 force block-packed thread mapping (tests / tuning)
         self.params = model_parameters(model) if params is None else np.asarray(params, np.float64).reshape(20)
@@ -88,6 +89,7 @@ class CrowdEngine:
         # discomfort_dist, discomfort_penalty_factor, robot_time_step
         self.consts = [50.0, -0.25, 1.0, 0.2, 0.5, 0.25]
         self._peek_buf, self._peek_idx, self.action_space, self._rotated, self._rewards = None, None, None, None, None
+        self._reset_scen, self._reset_draws = None, None
         self.walls, self.W, self.S, self.walls_per_env = None, 0, 0, 0
         if walls is not None:
             self.set_walls(walls)
@@ -160,6 +162,7 @@ class CrowdEngine:
         if self.respawn_bounds is not None and n_substeps > 0 and post_update:
             o.respawn = 1
             o.respawn_bounds = (ctypes.c_double * 2)(*self.respawn_bounds)
+            o.respawn_envs = None if self.respawn_envs is None else self.respawn_envs.data_ptr()
         return o
 
     # ------------------------------------------------------------------ loading / reading in the reference's layouts
@@ -356,6 +359,48 @@ class CrowdEngine:
         g = self.current_goals(self._peek_idx)  # read before the restore (mmm:705-707): the goal the peeked update arrived at
         return torch.stack([nx[L.DYN_PX], nx[L.DYN_PY], ho[L.DYN_TH], nx[L.DYN_VX], nx[L.DYN_VY], ho[L.DYN_OM], g[..., 0], g[..., 1]],
                            -1).double().cpu().numpy()
+
+    # ------------------------------------------------------------------ on-device reset
+    def reset_scenario(self, scenario, seeds=None, seed0=0, mask=None, randomize_attributes=False, circle_radius=7.0, robot_radius=0.3,
+                       traffic_length=14.0, traffic_height=3.0, human_mass=75.0, robot_mass=80.0, robot_desired_speed=1.0):
+        """SocialNavGym.reset (social_nav_gym.py:120-225) for every env -- or those selected by `mask` [E] bool -- without leaving the
+        device: env e replays the reference's generator for `scenario` on NumPy's MT19937 stream seeded with seeds[e] (default
+        seed0 + e), as np.random.seed(offset[phase] + case) does (:135-137).  Returns (scenario_of_env int32 [E], draws int32 [E])
+        device tensors; parallel-traffic envs get their respawn switched on (mmm:407-422)."""
+        if self.robot is None:
+            raise ValueError("the scenarios place a robot: build the engine with has_robot=True")
+        g = L.SnpResetArgs()
+        g.scenario = L.RESET_SCENARIOS[scenario] if isinstance(scenario, str) else int(scenario)
+        g.randomize_attributes = int(randomize_attributes)
+        dev = self.device
+        if seeds is not None:
+            if torch.is_tensor(seeds):   # device-side seeds (e.g. a running case counter): int32 bit patterns are read as uint32
+                seeds_t = seeds.to(device=dev, dtype=torch.int32).contiguous()
+            else:
+                s32 = (np.asarray(seeds, np.int64) & 0xFFFFFFFF).astype(np.uint32).view(np.int32)
+                seeds_t = torch.from_numpy(np.ascontiguousarray(s32)).to(dev)
+            if seeds_t.numel() != self.E:
+                raise ValueError("seeds must have one entry per env")
+            g.seeds = seeds_t.data_ptr()
+        g.seed0 = int(seed0) & 0xFFFFFFFF
+        mask_t = None
+        if mask is not None:
+            mask_t = torch.as_tensor(mask, device=dev).to(torch.uint8).contiguous()
+            g.mask = mask_t.data_ptr()
+        g.circle_radius, g.robot_radius, g.traffic_length, g.traffic_height = float(circle_radius), float(robot_radius), float(traffic_length), float(traffic_height)
+        g.human_mass, g.robot_mass, g.robot_desired_speed = float(human_mass), float(robot_mass), float(robot_desired_speed)
+        if self._reset_scen is None:
+            self._reset_scen = torch.zeros((self.E,), dtype=torch.int32, device=dev)
+            self._reset_draws = torch.zeros((self.E,), dtype=torch.int32, device=dev)
+        g.time_now, g.flags = self.time_now.data_ptr(), self.flags.data_ptr()
+        g.scenario_out, g.draws_out = self._reset_scen.data_ptr(), self._reset_draws.data_ptr()
+        L.check(self.lib.snp_reset(ctypes.byref(self._crowd()), ctypes.byref(g), _stream()))
+        if g.scenario in (1, 4):   # parallel traffic (all envs, or the coin of the hybrid scenario)
+            self.respawn_bounds = (traffic_length / 2, traffic_height / 2)
+            self.respawn_envs = self._reset_scen if g.scenario == 4 else None
+        elif mask is None:
+            self.respawn_bounds, self.respawn_envs = None, None
+        return self._reset_scen, self._reset_draws
 
     # ------------------------------------------------------------------ policy-side lookahead (SURVEY 8f-3)
     def set_action_space(self, actions):

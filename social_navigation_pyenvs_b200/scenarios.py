@@ -86,22 +86,35 @@ def _map_envs(fn, E, args):
         return pool.starmap(fn, [(e, *args) for e in range(E)], chunksize=max(1, E // 256))
 
 
-def _cc_env(e, N, seed0, circle_radius, robot_radius, mass):
+def _attributes(rs, N, randomize):
+    """humans_des_speed / humans_radius (social_nav_sim.py:217-224): uniform(0.5, 1.5) and uniform(0.3, 0.5) per human, drawn
+    interleaved BEFORE any position, or the fixed 1.0 / 0.3."""
+    if not randomize:
+        return [1.0] * N, [0.3] * N
+    vd, radii = [], []
+    for _ in range(N):
+        vd.append(0.5 + (1.5 - 0.5) * rs.random_sample())   # RandomState.uniform = low + (high - low) * random_sample()
+        radii.append(0.3 + (0.5 - 0.3) * rs.random_sample())
+    return vd, radii
+
+
+def _cc_env(e, N, seed0, circle_radius, robot_radius, mass, randomize_attributes=False):
     rs = np.random.RandomState(seed0 + e)
     st, gl = np.zeros((N, 13)), np.zeros((N, 2, 2))
-    pos_list, radii = [], [0.3] * N
+    vd, radii = _attributes(rs, N, randomize_attributes)
+    pos_list = []
     for i in range(N):
-        pos, angle = _cc_sample(rs, pos_list, 0, i, circle_radius, 1.0, 0.3, radii, robot_radius)
+        pos, angle = _cc_sample(rs, pos_list, 0, i, circle_radius, vd[i], radii[i], radii, robot_radius)
         pos_list.append([pos[0], pos[1]])
-        st[i] = _state_row(pos, bound_angle(math.pi + angle), 0.3, mass, -pos, 1.0)
+        st[i] = _state_row(pos, bound_angle(math.pi + angle), radii[i], mass, -pos, vd[i])
         gl[i, 0], gl[i, 1] = -pos, pos
     return st, gl
 
 
-def circular_crossing(E, N, seed0=2000, circle_radius=7.0, robot_radius=0.3, mass=75.0):
+def circular_crossing(E, N, seed0=2000, circle_radius=7.0, robot_radius=0.3, mass=75.0, randomize_attributes=False):
     """E environments of N humans on a circle, goals at the antipodes and back (G = 2).
     Returns dict(states [E,N,13], goals [E,N,2,2], robot [E,13])."""
-    res = _map_envs(_cc_env, E, (N, seed0, circle_radius, robot_radius, mass))
+    res = _map_envs(_cc_env, E, (N, seed0, circle_radius, robot_radius, mass, randomize_attributes))
     return dict(states=np.stack([r[0] for r in res]), goals=np.stack([r[1] for r in res]),
                 robot=robot_rows(E, circle_radius, robot_radius))
 
@@ -152,38 +165,97 @@ def ccso_synthetic(E, N=25, seed0=2000, circle_radius=7.0, robot_radius=0.3, mas
                 robot=robot_rows(E, circle_radius, robot_radius))
 
 
-def _pt_env(e, N, seed0, traffic_length, traffic_height, robot_radius, mass):
+def _ccso_ref_env(e, N, seed0, circle_radius, robot_radius, mass):
+    """generate_circular_crossing_with_static_obstacles (social_nav_sim.py:364-431), insert_robot=True: humans 0-2 static on the
+    inner circle R-3, the others in angular slots (pi / int(N/2)) (0.5 + 2i + noise) of the circle R."""
+    rs = np.random.RandomState(seed0 + e)
+    st, gl = np.zeros((N, 13)), np.zeros((N, 2, 2))
+    inner = circle_radius - 3.0
+    radii = [(1 + (rs.random_sample() - 1) * 0.4) if i < 3 else 0.3 for i in range(N)]
+    robot_pos, robot_goal = np.array([0.0, -circle_radius]), np.array([0.0, circle_radius])
+    slot = np.pi / int(N / 2)
+    pos_list = []
+    for i in range(N):
+        while True:
+            if i < 3:
+                angle = slot * (-0.5 + 2 * i + (rs.random_sample() - 0.5) * 0.5)
+                n0 = (rs.random_sample() - 0.5) * 0.1
+                n1 = (rs.random_sample() - 0.5) * 0.1
+                pos = np.array([inner * np.cos(angle) + n0, inner * np.sin(angle) + n1])
+            else:
+                angle = slot * (0.5 + 2 * i + (rs.random_sample() - 0.5) * 0.5)
+                n0 = (rs.random_sample() - 0.5) * 0.7
+                n1 = (rs.random_sample() - 0.5) * 0.7
+                pos = np.array([circle_radius * np.cos(angle) + n0, circle_radius * np.sin(angle) + n1])
+            collide = False
+            for j, o in enumerate(pos_list):
+                o = np.asarray(o)
+                og = o if j < 3 else -o
+                md = radii[i] + radii[j] + 0.2
+                if np.linalg.norm(pos - o) < md or np.linalg.norm(pos - og) < md:
+                    collide = True
+                    break
+            rmin = radii[i] + robot_radius + 0.2
+            if np.linalg.norm(pos - robot_pos) < rmin or np.linalg.norm(pos - robot_goal) < rmin:
+                collide = True
+            if not collide:
+                break
+        pos_list.append([pos[0], pos[1]])
+        goal, vd = (pos, 0.0) if i < 3 else (-pos, 1.0)
+        gl[i, 0], gl[i, 1] = goal, pos
+        st[i] = _state_row(pos, bound_angle(math.pi + angle), radii[i], mass, goal, vd)
+    return st, gl
+
+
+def circular_crossing_with_static_obstacles(E, N, seed0=2000, circle_radius=7.0, robot_radius=0.3, mass=75.0):
+    """The reference's own CCSO generator (social_nav_sim.py:364-431); terminates only for small crowds (N <= ~10: the slots of
+    humans 3.. wrap around the circle and collide for larger N)."""
+    res = _map_envs(_ccso_ref_env, E, (N, seed0, circle_radius, robot_radius, mass))
+    return dict(states=np.stack([r[0] for r in res]), goals=np.stack([r[1] for r in res]),
+                robot=robot_rows(E, circle_radius, robot_radius))
+
+
+def _pt_env(e, N, seed0, traffic_length, traffic_height, robot_radius, mass, randomize_attributes=False):
     rs = np.random.RandomState(seed0 + e)
     st, gl = np.zeros((N, 13)), np.zeros((N, 1, 2))
     robot_pos = np.array([-(traffic_length / 2) + 1, 0.0])
+    vd, radii = _attributes(rs, N, randomize_attributes)
+    if sum(math.pi * r ** 2 for r in radii) > traffic_length * traffic_height * 0.4:   # social_nav_sim.py:327-329
+        raise ValueError("Number of humans specified is too big for desided traffic height and length")
     placed = []
     for i in range(N):
         while True:
-            a, b = -(traffic_length / 2) + 0.3, traffic_length / 2 - 0.3
+            a, b = -(traffic_length / 2) + radii[i], traffic_length / 2 - radii[i]
             pos = np.array([(b - a) * rs.random_sample() + a, (rs.random_sample() - 0.5) * traffic_height])
-            if any(np.linalg.norm(pos - o) - 0.3 - 0.3 - 0.1 < 0 for o in placed):
+            if any(np.linalg.norm(pos - o) - radii[i] - radii[j] - 0.1 < 0 for j, o in enumerate(placed)):
                 continue
-            if np.linalg.norm(pos - robot_pos) - 0.3 - robot_radius - 0.1 < 0:
+            if np.linalg.norm(pos - robot_pos) - radii[i] - robot_radius - 0.1 < 0:
                 continue
             break
         placed.append(pos)
         goal = [-(traffic_length / 2) - 3, pos[1]]
-        st[i] = _state_row(pos, bound_angle(-math.pi), 0.3, mass, goal, 1.0)
+        st[i] = _state_row(pos, bound_angle(-math.pi), radii[i], mass, goal, vd[i])
         gl[i, 0] = goal
     return st, gl
 
 
-def parallel_traffic(E, N, seed0=2000, traffic_length=14.0, traffic_height=3.0, robot_radius=0.3, mass=75.0):
+def parallel_traffic(E, N, seed0=2000, traffic_length=14.0, traffic_height=3.0, robot_radius=0.3, mass=75.0, randomize_attributes=False):
     """Parallel-traffic scenario (social_nav_sim.py:301-362, insert_robot=True): humans walk towards x = -L/2 - 3 and are respawned
     at the right end when they get within 3 m of it (motion_model_manager.py:407-422).  Returns states, goals [E,N,1,2], robot rows
     and `respawn_bounds` = (L/2, H/2)."""
-    res = _map_envs(_pt_env, E, (N, seed0, traffic_length, traffic_height, robot_radius, mass))
+    res = _map_envs(_pt_env, E, (N, seed0, traffic_length, traffic_height, robot_radius, mass, randomize_attributes))
     robot = np.zeros((E, 13))
     robot[:, 0] = -(traffic_length / 2) + 1
     robot[:, 8], robot[:, 9], robot[:, 12] = robot_radius, 80.0, 1.0
     robot[:, 10] = (traffic_length / 2) - 1
     return dict(states=np.stack([r[0] for r in res]), goals=np.stack([r[1] for r in res]), robot=robot,
                 respawn_bounds=(traffic_length / 2, traffic_height / 2))
+
+
+def hybrid_choice(seed):
+    """The coin of the hybrid scenario (social_nav_gym.py:155-156): np.random.seed(seed); np.random.choice([cc, pt]) -> 0 / 1.  The
+    legacy choice draws randint(0, 2) = the first 32-bit output of MT19937 masked to one bit."""
+    return int.from_bytes(np.random.RandomState(int(seed)).bytes(4), "little") & 1
 
 
 def jittered_grid_crowd(n_side, pitch=2.0, jitter=0.5, seed=0, mass=75.0):

@@ -31,6 +31,7 @@ class BatchedSocialNavGym:
         self.train_val_sim = self.test_sim = "circle_crossing"
         self.traffic_length, self.traffic_height = 14.0, 3.0
         self.robot_visible = False
+        self.randomize_attributes = False
         self.robot_motion_model_title = None
         self._robot_goals = None
         self.walls = None
@@ -62,17 +63,28 @@ class BatchedSocialNavGym:
     def set_safety_space(self, safety_space):
         self.safety_space = safety_space
 
-    def reset(self, phase="test", test_case=None):
+    def reset(self, phase="test", test_case=None, on_device=True):
+        """SocialNavGym.reset (social_nav_gym.py:120-225) for the whole batch: env e gets case `case_counter + e`, i.e. the seed
+        offset[phase] + case + e (:135-137).  on_device=True generates the scenarios with the reset kernel (snp_reset: the reference's
+        generators on NumPy's MT19937 stream, one thread per env); False builds them on the host (scenarios.py) and uploads."""
         assert phase in ["train", "val", "test"]
         if test_case is not None:
             self.case_counter[phase] = test_case
         offset = {"train": 2000, "val": 0, "test": 1000}[phase]                  # social_nav_gym.py:135
         sim = self.test_sim if phase == "test" else self.train_val_sim
         seed0 = offset + self.case_counter[phase]
+        if on_device:
+            return self._reset_on_device(sim, seed0, phase)
+        if sim == "hybrid_scenario":
+            raise NotImplementedError("the hybrid scenario is generated on the device only (reset(on_device=True))")
         if sim == "circle_crossing":
-            sc = scenarios.circular_crossing(self.E, self.human_num, seed0, self.circle_radius, self.robot_radius)
+            sc = scenarios.circular_crossing(self.E, self.human_num, seed0, self.circle_radius, self.robot_radius,
+                                             randomize_attributes=self.randomize_attributes)
         elif sim == "circular_crossing_with_static_obstacles":
-            sc = scenarios.ccso_synthetic(self.E, self.human_num, seed0, self.circle_radius, self.robot_radius)
+            # the reference's generator (social_nav_sim.py:364-431) only terminates for small crowds; above 10 humans the 3 static
+            # obstacles are combined with the circular-crossing sampler (SURVEY.md 8(d) config 3)
+            gen = scenarios.circular_crossing_with_static_obstacles if self.human_num <= 10 else scenarios.ccso_synthetic
+            sc = gen(self.E, self.human_num, seed0, self.circle_radius, self.robot_radius)
         elif sim == "parallel_traffic":
             sc = scenarios.parallel_traffic(self.E, self.human_num, seed0, self.traffic_length, self.traffic_height, self.robot_radius)
         else:
@@ -92,6 +104,44 @@ class BatchedSocialNavGym:
         if self.safety_space > 0:
             self.engine.set_safety_space(self.safety_space)
         return self.observation(), np.zeros(self.E, int)
+
+    def _reset_on_device(self, sim, seed0, phase, mask=None, seeds=None):
+        e = self.engine
+        fresh = e is None or e.N != self.human_num or e.motion_model_title != self.human_policy or e.consider_robot != self.robot_visible
+        if fresh:
+            e = self.engine = CrowdEngine(self.human_policy, self.E, self.human_num, G=2, dtype=self.dtype, device=self.device,
+                                          consider_robot=self.robot_visible, symmetric=True, walls=self.walls, has_robot=True)
+        e.consts = [float(self.time_limit), self.collision_penalty, self.success_reward, self.discomfort_dist,
+                    self.discomfort_penalty_factor, self.robot_time_step]
+        name = "ccso_synthetic" if (sim == "circular_crossing_with_static_obstacles" and self.human_num > 10) else sim
+        e.reset_scenario(name, seeds=seeds, seed0=seed0, mask=mask, randomize_attributes=self.randomize_attributes,
+                         circle_radius=self.circle_radius, robot_radius=self.robot_radius, traffic_length=self.traffic_length,
+                         traffic_height=self.traffic_height)
+        if mask is None:
+            self.case_counter[phase] += self.E
+        if self.safety_space > 0:
+            e.set_safety_space(self.safety_space)
+        elif fresh:
+            e.stat[L.STAT_SAFETY].zero_()
+        # robot goal list of the reference scenarios: [goal, start] (social_nav_sim.py:237,309)
+        r = e.robot
+        self._robot_goals = torch.stack([torch.stack([r[L.ROBOT_GX], r[L.ROBOT_GY]], -1), torch.stack([r[L.ROBOT_GX2], r[L.ROBOT_GY2]], -1)], 1).double().cpu().numpy()
+        if self.robot_motion_model_title is not None:
+            e.set_robot_motion_model(self.robot_motion_model_title)
+        return self.observation(), np.zeros(self.E, int)
+
+    def reset_finished(self, finished, phase="train"):
+        """Restart only the envs whose episode ended (`finished` [E] bool: terminated | truncated), each with the next unused case
+        of `phase` -- the vectorised form of calling reset() again on those envs.  Stays on the device."""
+        fin = torch.as_tensor(finished, device=self.device).bool()
+        offset = {"train": 2000, "val": 0, "test": 1000}[phase]
+        order = torch.cumsum(fin.int(), 0) - 1
+        seeds = (offset + self.case_counter[phase] + order).to(torch.int32)
+        n = int(fin.sum().item())
+        sim = self.test_sim if phase == "test" else self.train_val_sim
+        self._reset_on_device(sim, 0, phase, mask=fin, seeds=seeds)
+        self.case_counter[phase] += n
+        return self.observation()
 
     def observation(self, theta_and_omega_visible=False):
         e = self.engine

@@ -342,6 +342,64 @@ def lookahead_case():
     print("lookahead ->", os.path.getsize(path), "B")
 
 
+def scenario_cases():
+    """The reference's scenario generators (social_nav_sim.py:200-431) on many seeds, through SocialNavSim's own entry point, with the
+    number of uniforms each one consumed (read back from the global MT19937 position) and the hybrid scenario's coin
+    (social_nav_gym.py:155-156 np.random.choice).  Pins scenarios.py and the on-device reset (snp_reset)."""
+    out = {}
+
+    def rows(sim):
+        st = np.array([h.get_safe_state() for h in sim.humans])
+        return st, pack_goals(sim.humans)
+
+    counter = [0]
+    real_random, real_uniform = np.random.random, np.random.uniform
+
+    def counting_random(*a, **k):
+        counter[0] += 1
+        return real_random(*a, **k)
+
+    def counting_uniform(*a, **k):
+        counter[0] += 1
+        return real_uniform(*a, **k)
+
+    np.random.random, np.random.uniform = counting_random, counting_uniform   # the generators draw through these two only
+
+    cases = [("cc", 5, False), ("cc", 25, False), ("cc", 7, True), ("pt", 5, False), ("pt", 12, True), ("ccso", 6, False), ("ccso", 8, False)]
+    for kind, n, rand in cases:
+        seeds = np.arange(3000, 3000 + (6 if n == 25 else 16))
+        S, G, D = [], [], []
+        for seed in seeds:
+            np.random.seed(int(seed))
+            counter[0] = 0
+            base = {"insert_robot": True, "human_policy": "hsfm_farina", "headless": True, "runge_kutta": False, "robot_visible": False,
+                    "robot_radius": 0.3, "n_actors": n}
+            if kind == "cc":
+                sim = SocialNavSim({**base, "circle_radius": 7, "randomize_human_positions": True, "randomize_human_attributes": rand},
+                                   scenario="circular_crossing", parallelize_humans=False)
+            elif kind == "pt":
+                sim = SocialNavSim({**base, "traffic_length": 14, "traffic_height": 3, "randomize_human_attributes": rand},
+                                   scenario="parallel_traffic", parallelize_humans=False)
+            else:
+                sim = SocialNavSim({**base, "circle_radius": 7, "randomize_human_positions": True},
+                                   scenario="circular_crossing_with_static_obstacles", parallelize_humans=False)
+            D.append(counter[0])
+            st, gl = rows(sim)
+            S.append(st); G.append(gl)
+        key = f"{kind}{n}{'_randattr' if rand else ''}"
+        out[key + "_seeds"], out[key + "_states"], out[key + "_goals"], out[key + "_draws"] = seeds, np.stack(S), np.stack(G), np.array(D)
+        print("scenario", key, "draws", D[:6])
+    np.random.random, np.random.uniform = real_random, real_uniform
+    coins = []
+    for seed in range(3000, 3064):
+        np.random.seed(seed)
+        coins.append(["circle_crossing", "parallel_traffic"].index(np.random.choice(["circle_crossing", "parallel_traffic"])))
+    out["hybrid_seeds"], out["hybrid_choice"] = np.arange(3000, 3064), np.array(coins)
+    path = os.path.join(HERE, "scenarios.npz")
+    np.savez_compressed(path, **out)
+    print("scenarios ->", os.path.getsize(path), "B")
+
+
 def numba_cases():
     """Second witness: the reference's Numba operator update_humans_parallel (forces_parallel.py:184)."""
     out = {}
@@ -556,7 +614,7 @@ def gym_case():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["traj", "pt", "il", "lookahead", "numba", "peek", "flags", "laser", "gym"]
+    which = sys.argv[1:] or ["traj", "pt", "il", "lookahead", "scenarios", "numba", "peek", "flags", "laser", "gym"]
     if "traj" in which:
         traj_cases()
     if "pt" in which:
@@ -565,6 +623,8 @@ if __name__ == "__main__":
         robot_model_cases()
     if "lookahead" in which:
         lookahead_case()
+    if "scenarios" in which:
+        scenario_cases()
     if "numba" in which:
         numba_cases()
     if "peek" in which:

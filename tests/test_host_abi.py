@@ -37,7 +37,8 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
     corrupt every call)."""
     import subprocess
     from social_navigation_pyenvs_b200 import _lib as L
-    structs = {"snp_crowd": L.SnpCrowd, "snp_step_opts": L.SnpStepOpts, "snp_laser_args": L.SnpLaserArgs, "snp_lookahead_args": L.SnpLookaheadArgs}
+    structs = {"snp_crowd": L.SnpCrowd, "snp_step_opts": L.SnpStepOpts, "snp_laser_args": L.SnpLaserArgs, "snp_lookahead_args": L.SnpLookaheadArgs,
+               "snp_reset_args": L.SnpResetArgs}
     lines = []
     for cname, cls in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

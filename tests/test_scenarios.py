@@ -56,3 +56,63 @@ def test_ccso_synthetic_respects_clearances():
     p = crowd["states"][0, :, 0:2]
     d = np.linalg.norm(p[:, None] - p[None], axis=-1)
     assert d[np.triu_indices(256, 1)].min() > 0.6                                # nobody overlaps at the start
+
+
+def _golden_cases():
+    z = np.load(os.path.join(GOLDEN, "scenarios.npz"))
+    return z, [("cc5", 0), ("cc25", 0), ("cc7_randattr", 0), ("pt5", 1), ("pt12_randattr", 1), ("ccso6", 2), ("ccso8", 2)]
+
+
+def test_host_generators_match_the_reference_on_many_seeds():
+    """scenarios.py against tests/golden/scenarios.npz (recorded from the live reference's generators, social_nav_sim.py:200-431):
+    every seed, bit for bit -- including randomized attributes and the reference's own static-obstacle generator."""
+    z, cases = _golden_cases()
+    for key, scen in cases:
+        S, G, seeds = z[key + "_states"], z[key + "_goals"], z[key + "_seeds"]
+        n, rand = S.shape[1], "randattr" in key
+        for e, seed in enumerate(seeds):
+            if scen == 0:
+                sc = scenarios.circular_crossing(1, n, seed0=int(seed), randomize_attributes=rand)
+            elif scen == 1:
+                sc = scenarios.parallel_traffic(1, n, seed0=int(seed), randomize_attributes=rand)
+            else:
+                sc = scenarios.circular_crossing_with_static_obstacles(1, n, seed0=int(seed))
+            assert np.array_equal(sc["states"][0], S[e]), (key, seed)
+            assert np.array_equal(sc["goals"][0], G[e], equal_nan=True), (key, seed)
+    assert [scenarios.hybrid_choice(s) for s in z["hybrid_seeds"]] == list(z["hybrid_choice"])
+
+
+def test_reset_core_replays_numpy_stream_and_reference_generators(tmp_path):
+    """csrc/snp_reset_core.h -- the code every thread of the CUDA reset kernel runs -- compiled for the host: MT19937 + random_double
+    as NumPy's legacy RandomState, and the generators consuming exactly the reference's draws (count recorded from the live
+    reference) with bit-identical results."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "reset_core_host"
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-I", os.path.join(root, "social_navigation_pyenvs_b200", "csrc"),
+                    os.path.join(root, "tests", "reset_core_host.cpp"), "-o", str(exe)], check=True)
+
+    def run(scen, n, rand, seed0, count):
+        out = subprocess.run([str(exe), str(scen), str(n), str(int(rand)), str(seed0), str(count)], capture_output=True, text=True, check=True).stdout.split("\n")
+        envs, k = [], 0
+        for _ in range(count):
+            _, _, sc, dr = out[k].split()
+            rows = np.array([[float(x) for x in out[k + 1 + i].split()] for i in range(n)])
+            k += n + 1
+            envs.append((int(sc), int(dr), rows))
+        return envs
+
+    z, cases = _golden_cases()
+    for key, scen in cases:
+        S, G, D, seeds = z[key + "_states"], z[key + "_goals"], z[key + "_draws"], z[key + "_seeds"]
+        envs = run(scen, S.shape[1], "randattr" in key, int(seeds[0]), len(seeds))
+        for e, (sc, draws, rows) in enumerate(envs):
+            assert sc == scen and draws == D[e], (key, e)
+            ref = np.stack([S[e, :, 0], S[e, :, 1], S[e, :, 2], S[e, :, 8], S[e, :, 12], G[e, :, 0, 0], G[e, :, 0, 1]], 1)
+            assert np.array_equal(rows[:, :7], ref), (key, e)
+            if G.shape[2] > 1:
+                assert np.array_equal(rows[:, 7:9], G[e, :, 1]), (key, e)
+    assert [e[0] for e in run(4, 5, False, 3000, 64)] == list(z["hybrid_choice"])
+    sc = scenarios.ccso_synthetic(3, 25, seed0=2000)
+    for e, (_, _, rows) in enumerate(run(3, 25, False, 2000, 3)):
+        assert np.array_equal(rows[:, :2], sc["states"][e, :, 0:2]) and np.array_equal(rows[:, 3], sc["states"][e, :, 8])
