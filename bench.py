@@ -126,6 +126,21 @@ def measured_traffic(args):
         return None
 
 
+def issue_model(key, clocks, measured_ms):
+    """Issue-port bound of the dominant kernel: warp instructions of ONE launch from the committed ncu capture of this workload
+    (profiles/issue_model.json, written by tools/issue_cost.py), an FP64 instruction costing 2 issue cycles of its SMSP with nothing
+    issuing in its shadow (profiles/r01_pipe_microbench.txt), at the SM clock sampled during the timed region."""
+    try:
+        m = json.load(open(os.path.join(ROOT, "profiles", "issue_model.json")))[key]
+        mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
+        bound_ms = m["issue_cycles_per_smsp"] / (mhz * 1e3)
+        return {"bound_ms": bound_ms, "frac": bound_ms / measured_ms, "fp64_warp_instructions": m["fp64_warp_instructions"],
+                "other_warp_instructions": m["other_warp_instructions"], "fp64_issue_cycles": m["fp64_issue_cycles"], "sm_mhz": mhz,
+                "source": "profiles/issue_model.json (" + m["source"] + ")"}
+    except (OSError, KeyError, ValueError, TypeError):
+        return None
+
+
 def oracle_rate(inp, n_envs, threads, substeps, repeats=1):
     """The reference's algorithm on the host: C restatement (oracle/snp_oracle.c, serial semantics), OpenMP over envs."""
     import oracle
@@ -326,7 +341,7 @@ def run_laser(args, rank, world, local_rank):
                 "e2e": {"value": world * E * samples * reps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": int(humans.nbytes + pose_h.nbytes),
                         "d2h_bytes_per_step": int(E * samples * 12), "api": "sensors.scan_batch (snp_laser_host)", "steps": reps},
                 "roofline": {"bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": ach, "peak": pipe.value, "unit": "TFLOP/s",
-                             "frac": ach / pipe.value, "traffic": None, "kernel": "snp::k_laser_rays", "flops_per_ray": flops_per_ray,
+                             "frac": ach / pipe.value, "traffic": measured_traffic(args), "kernel": "snp::k_laser_rays", "flops_per_ray": flops_per_ray,
                              "hbm": {"achieved_gbs": bytes_per_launch / per_s / 1e9, "bytes_per_ray": bytes_per_launch / (E * samples)}}}
         print(json.dumps(line))
     if world > 1:
@@ -417,7 +432,7 @@ def run_lookahead(args, rank, world, local_rank):
                 "e2e": {"value": world * rows * reps / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(robot_host.numel() * robot_host.element_size()),
                         "d2h_bytes_per_step": int(rew_host.numel() * 8), "api": "CrowdEngine.lookahead: pinned H2D robot state, peek + lookahead, D2H rewards "
                         "(rotated states stay on the device for the value network)", "steps": reps},
-                "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": measured_traffic(args),
                              "kernel": "snp::k_lookahead", "bytes_per_row": (out_bytes + in_bytes) / rows, "peak_source": hbm_src}}
         print(json.dumps(line))
     if world > 1:
@@ -575,7 +590,8 @@ def main():
                 "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": hbm_peak, "frac": ach_gbs / hbm_peak, "peak_source": hbm_src,
                         "bytes_per_agent_step": cost["words"] * wbytes / SUBSTEPS},
                 "sfu": {"achieved_gops": ach_sfu, "peak_gops": mufu.value, "frac": ach_sfu / mufu.value if args.dtype == "f32" else None,
-                        "ops_per_agent_substep": cost["sfu"]}}
+                        "ops_per_agent_substep": cost["sfu"]},
+                "issue": issue_model(f"{args.workload}:{args.dtype}", clocks.summary(), total_ms / args.steps)}
 
     line = {"metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
