@@ -1,9 +1,11 @@
 // snp_reset.cu -- SocialNavGym.reset for a whole batch on the device: every environment replays the reference's
 // scenario generator (social_gym/social_nav_sim.py:200-431, chosen and seeded as social_gym/social_nav_gym.py:135-167 does) on its
-// own copy of NumPy's MT19937 stream -- see snp_reset_core.h.  One thread per environment (the rejection sampler is a sequential,
-// data-dependent loop), 32 environments per CTA with the generator state interleaved in shared memory (word i of lane l at
-// [i][l]: conflict-free); results are scattered straight into the crowd's structure-of-arrays buffers.  Reset is not the hot path:
-// the point is that 4096 environments restart in well under a millisecond without leaving the GPU, instead of seconds on the host.
+// own copy of NumPy's MT19937 stream -- see snp_reset_core.h.  A WARP per environment: the rejection sampler is a sequential,
+// data-dependent loop, so all 32 lanes walk it in lock step with identical values, and share what is parallel inside it -- the
+// distance tests of a candidate against the humans already placed (one lane per placed human, ballot) and the 624-word twist of
+// the generator (batches of 32 words).  Generator state and the placed humans live in the warp's slice of shared memory; results are
+// written straight into the crowd's structure-of-arrays buffers.  Reset is not the hot path, but asynchronous episode ends make
+// masked restarts frequent in an RL loop: 4096 envs x 25 humans restart in a fraction of a step's time, without leaving the GPU.
 #include "snp_kernels.cuh"
 #include "snp_reset_core.h"
 
@@ -25,20 +27,30 @@ template <typename T> struct ResetArgs {
     int32_t *scenario_out, *draws_out;
 };
 
-template <typename T> __global__ void __launch_bounds__(32) k_reset(const ResetArgs<T> a) {
+constexpr int kResetWarps = 4;
+
+struct WarpGroup {
+    SNP_HD int lane() const { return threadIdx.x & 31; }
+    SNP_HD int size() const { return 32; }
+    __device__ __forceinline__ bool any(bool v) const { return __any_sync(0xffffffffu, v) != 0; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+
+template <typename T> __global__ void __launch_bounds__(kResetWarps * 32) k_reset(const ResetArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *mt = reinterpret_cast<uint32_t *>(smem_raw);                      // [624][32]
-    double *scr = reinterpret_cast<double *>(smem_raw + 624 * 32 * sizeof(uint32_t));  // [4][N][32]
-    const int lane = threadIdx.x;
-    const long long env = (long long)blockIdx.x * 32 + lane;
-    if (env >= a.E) return;
+    const int N = a.N, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t per_warp = 624 * sizeof(uint32_t) + (size_t)4 * N * sizeof(double);
+    uint32_t *mt = reinterpret_cast<uint32_t *>(smem_raw + warp * per_warp);     // [624]
+    double *scr = reinterpret_cast<double *>(mt + 624);                          // [4][N]
+    const long long env = (long long)blockIdx.x * kResetWarps + warp;
+    if (env >= a.E) return;                       // whole warps leave together: the group operations below stay full-warp
     if (a.mask && !a.mask[env]) return;
-    const int N = a.N;
-    Mt19937 rng{mt + lane, 32, 624, 0};
-    ResetScratch w{scr + lane, scr + (size_t)N * 32 + lane, scr + (size_t)2 * N * 32 + lane, scr + (size_t)3 * N * 32 + lane, 32};
+    Mt19937<WarpGroup> rng{mt, 624, 0, WarpGroup{}};
+    ResetScratch w{scr, scr + N, scr + 2 * N, scr + 3 * N};
     const long long EN = a.EN, base = env * N;
     const T mass = (T)a.mass;
     auto emit = [&](int i, const ResetHuman &h) {
+        if (lane != 0) return;
         const long long k = base + i;
         a.dyn[SNP_DYN_PX * EN + k] = (T)h.x; a.dyn[SNP_DYN_PY * EN + k] = (T)h.y; a.dyn[SNP_DYN_TH * EN + k] = (T)h.yaw;
         a.dyn[SNP_DYN_VX * EN + k] = T(0); a.dyn[SNP_DYN_VY * EN + k] = T(0); a.dyn[SNP_DYN_BVX * EN + k] = T(0);
@@ -52,6 +64,7 @@ template <typename T> __global__ void __launch_bounds__(32) k_reset(const ResetA
     };
     const uint32_t seed = a.seeds ? a.seeds[env] : a.seed0 + (uint32_t)env;
     const int scen = reset_generate(a.p, seed, rng, w, emit);
+    if (lane != 0) return;
     if (a.robot) {  // sim:237 / :314: the robot of the scenario, at rest (social_nav_gym.py:213 robot.set(..., vx = 0, vy = 0))
         const long long E = a.E;
         T *r = a.robot + env;
@@ -82,11 +95,11 @@ template <typename T> int launch_reset(const snp_crowd *c, const snp_reset_args 
     a.p.traffic_length = g->traffic_length; a.p.traffic_height = g->traffic_height;
     a.mass = g->human_mass; a.robot_mass = g->robot_mass; a.robot_vd = g->robot_desired_speed;
     a.time_now = g->time_now; a.flags = g->flags; a.scenario_out = g->scenario_out; a.draws_out = g->draws_out;
-    const size_t smem = 624 * 32 * sizeof(uint32_t) + (size_t)4 * c->N * 32 * sizeof(double);
+    const size_t smem = kResetWarps * (624 * sizeof(uint32_t) + (size_t)4 * c->N * sizeof(double));
     if (smem > 200 * 1024) { set_error("snp_reset: %d humans per env do not fit the generator's shared-memory scratch", c->N); return SNP_ERR_UNSUPPORTED; }
     auto kern = k_reset<T>;
-    SNP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)((c->E + 31) / 32), 32, smem, st>>>(a);
+    if (smem > 48 * 1024) SNP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)((c->E + kResetWarps - 1) / kResetWarps), kResetWarps * 32, smem, st>>>(a);
     count_launch();
     SNP_CUDA_OK(cudaGetLastError());
     return SNP_OK;

@@ -8,9 +8,11 @@
 // consume EXACTLY the reference's draw sequence: same accept / reject decisions, same number of draws, positions equal to the
 // last ulp of cos / sin.  (SURVEY.md 8f-4 expected distribution-level parity only.)
 //
-// The code below is shared by the CUDA kernel (snp_reset.cu, one thread per environment, generator state in shared memory) and by
-// a host harness the CPU tests compile with g++ (tests/reset_core_host.cpp), so the logic is checked against the recorded reference
-// outputs without a GPU.
+// The code below is shared by the CUDA kernel (snp_reset.cu) and by a host harness the CPU tests compile with g++
+// (tests/reset_core_host.cpp), so the logic is checked against the recorded reference outputs without a GPU.  It is written for a
+// GROUP of cooperating lanes that all execute it in lock step with identical values: the group splits the generator's twist and
+// the distance tests of a candidate against the humans already placed, and agrees on the outcome with `any`.  On the host the group
+// is one lane (SoloGroup) and the code is the plain sequential algorithm; on the device it is a warp per environment.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -26,24 +28,43 @@ namespace snp {
 enum { SNP_SCEN_CIRCULAR_CROSSING = 0, SNP_SCEN_PARALLEL_TRAFFIC = 1, SNP_SCEN_CCSO = 2, SNP_SCEN_CCSO_SYNTHETIC = 3, SNP_SCEN_HYBRID = 4 };
 
 // numpy/random/src/mt19937/mt19937.c: mt19937_seed (np.random.seed(int)), mt19937_gen, and random_double of the legacy
-// distributions: (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53.  `stride` lets 32 generators interleave their state words.
-struct Mt19937 {
+// distributions: (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53.
+struct SoloGroup {  // one lane: the sequential algorithm
+    SNP_HD int lane() const { return 0; }
+    SNP_HD int size() const { return 1; }
+    SNP_HD bool any(bool v) const { return v; }
+    SNP_HD void sync() const {}
+};
+
+template <class Group> struct Mt19937 {
     uint32_t *mt;
-    int stride, pos;
+    int pos;
     long long draws;
-    SNP_HD uint32_t &at(int i) { return mt[(size_t)i * stride]; }
-    SNP_HD void seed(uint32_t s) {
-        for (int i = 0; i < 624; ++i) { at(i) = s; s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)(i + 1); }
+    Group g;
+    SNP_HD uint32_t &at(int i) { return mt[i]; }
+    SNP_HD void seed(uint32_t s) {  // sequential recurrence: one lane writes, everybody waits
+        g.sync();                   // nobody is still reading the previous state
+        if (g.lane() == 0)
+            for (int i = 0; i < 624; ++i) { at(i) = s; s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)(i + 1); }
+        g.sync();
         pos = 624;
     }
+    // mt19937_gen's regeneration of all 624 words.  Word kk needs the OLD words kk, kk+1 and, for kk < 227, the OLD word kk+397,
+    // else the NEW word kk-227 (and the new word 0 for kk = 623): a batch of `size` consecutive words reads everything it needs
+    // before any of them is written, and what it reads as new was written by an earlier batch.
     SNP_HD void twist() {
         const uint32_t UP = 0x80000000u, LO = 0x7fffffffu, A = 0x9908b0dfu;
-        int kk = 0;
-        uint32_t y;
-        for (; kk < 624 - 397; ++kk) { y = (at(kk) & UP) | (at(kk + 1) & LO); at(kk) = at(kk + 397) ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
-        for (; kk < 623; ++kk) { y = (at(kk) & UP) | (at(kk + 1) & LO); at(kk) = at(kk + (397 - 624)) ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
-        y = (at(623) & UP) | (at(0) & LO);
-        at(623) = at(396) ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+        for (int base = 0; base < 624; base += g.size()) {
+            const int kk = base + g.lane();
+            uint32_t v = 0;
+            if (kk < 624) {
+                const uint32_t y = (at(kk) & UP) | (at(kk + 1 == 624 ? 0 : kk + 1) & LO);
+                v = at(kk < 624 - 397 ? kk + 397 : kk - (624 - 397)) ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+            }
+            g.sync();
+            if (kk < 624) at(kk) = v;
+            g.sync();
+        }
         pos = 0;
     }
     SNP_HD uint32_t next32() {
@@ -65,14 +86,14 @@ struct ResetParams {
     double circle_radius, robot_radius, traffic_length, traffic_height;
 };
 
-// Scratch of one environment: positions, radii and desired speeds of the humans placed so far (strided like the generator state).
+// Scratch of one environment: positions, radii and desired speeds of the humans placed so far.  Every lane of the group writes the
+// same value to the same slot (benign), reads happen after a group sync.
 struct ResetScratch {
     double *px, *py, *rad, *vd;
-    int stride;
-    SNP_HD double &X(int i) { return px[(size_t)i * stride]; }
-    SNP_HD double &Y(int i) { return py[(size_t)i * stride]; }
-    SNP_HD double &R(int i) { return rad[(size_t)i * stride]; }
-    SNP_HD double &V(int i) { return vd[(size_t)i * stride]; }
+    SNP_HD double &X(int i) { return px[i]; }
+    SNP_HD double &Y(int i) { return py[i]; }
+    SNP_HD double &R(int i) { return rad[i]; }
+    SNP_HD double &V(int i) { return vd[i]; }
 };
 
 SNP_HD double reset_norm(double x, double y) { return sqrt(fma(y, y, x * x)); }  // np.linalg.norm of a length-2 vector
@@ -90,8 +111,9 @@ struct ResetHuman { double x, y, yaw, radius, vd, g0x, g0y, g1x, g1y; int goal_c
 
 // Runs the generator of `p.scenario` for one environment seeded with `seed`; calls emit(i, ResetHuman) for every human in order.
 // Returns the scenario that was generated (the coin of the hybrid scenario, else p.scenario).
-template <class Emit>
-SNP_HD int reset_generate(const ResetParams &p, uint32_t seed, Mt19937 &rng, ResetScratch &w, Emit &emit) {
+template <class Group, class Emit>
+SNP_HD int reset_generate(const ResetParams &p, uint32_t seed, Mt19937<Group> &rng, ResetScratch &w, Emit &emit) {
+    const Group g = rng.g;
     const double pi = 3.141592653589793;
     const int N = p.N;
     rng.draws = 0;
@@ -114,6 +136,7 @@ SNP_HD int reset_generate(const ResetParams &p, uint32_t seed, Mt19937 &rng, Res
     } else {
         for (int i = 0; i < N; ++i) { w.V(i) = 1.0; w.R(i) = 0.3; }
     }
+    g.sync();
     if (scen == SNP_SCEN_PARALLEL_TRAFFIC) {  // sim:330-352
         const double half = p.traffic_length / 2;
         const double rx = -half + 1, ry = 0.0;
@@ -124,13 +147,14 @@ SNP_HD int reset_generate(const ResetParams &p, uint32_t seed, Mt19937 &rng, Res
                 const double a = -half + ri, b = half - ri;
                 x = (b - a) * rng.random() + a;
                 y = (rng.random() - 0.5) * p.traffic_height;
-                bool collide = false;
-                for (int j = 0; j < i; ++j)
+                bool collide = false;  // the lanes share the humans placed so far; any hit rejects (the reference's `break` only ends its loop)
+                for (int j = g.lane(); j < i; j += g.size())
                     if (reset_norm(x - w.X(j), y - w.Y(j)) - ri - w.R(j) - 0.1 < 0) { collide = true; break; }
                 if (reset_norm(x - rx, y - ry) - ri - p.robot_radius - 0.1 < 0) collide = true;
-                if (!collide) break;
+                if (!g.any(collide)) break;
             }
             w.X(i) = x; w.Y(i) = y;
+            g.sync();
             ResetHuman h{x, y, reset_bound_angle(-pi), w.R(i), w.V(i), -half - 3, y, 0.0, 0.0, 1};
             h.g1x = h.g0x; h.g1y = h.g0y;
             emit(i, h);
@@ -159,7 +183,7 @@ SNP_HD int reset_generate(const ResetParams &p, uint32_t seed, Mt19937 &rng, Res
                 x = R * cos(angle) + n0; y = R * sin(angle) + n1;
             }
             bool collide = false;
-            for (int j = 0; j < i; ++j) {
+            for (int j = g.lane(); j < i; j += g.size()) {
                 const double md = ri + w.R(j) + 0.2;
                 const double ox = w.X(j), oy = w.Y(j);
                 const bool other_static = (scen == SNP_SCEN_CCSO || scen == SNP_SCEN_CCSO_SYNTHETIC) && j < 3;
@@ -174,9 +198,10 @@ SNP_HD int reset_generate(const ResetParams &p, uint32_t seed, Mt19937 &rng, Res
                 const double rm = ri + p.robot_radius + 0.2;
                 if (reset_norm(x - 0.0, y - (-R)) < rm || reset_norm(x - 0.0, y - R) < rm) collide = true;
             }
-            if (!collide) break;
+            if (!g.any(collide)) break;
         }
         w.X(i) = x; w.Y(i) = y;
+        g.sync();
         ResetHuman h{x, y, reset_bound_angle(pi + angle), ri, w.V(i), is_static ? x : -x, is_static ? y : -y, x, y, 2};
         emit(i, h);
     }

@@ -16,8 +16,8 @@ int main(int argc, char **argv) {
     std::vector<uint32_t> state(624);
     std::vector<double> scratch(4 * p.N);
     for (int e = 0; e < count; ++e) {
-        snp::Mt19937 rng{state.data(), 1, 624, 0};
-        snp::ResetScratch w{scratch.data(), scratch.data() + p.N, scratch.data() + 2 * p.N, scratch.data() + 3 * p.N, 1};
+        snp::Mt19937<snp::SoloGroup> rng{state.data(), 624, 0, snp::SoloGroup{}};
+        snp::ResetScratch w{scratch.data(), scratch.data() + p.N, scratch.data() + 2 * p.N, scratch.data() + 3 * p.N};
         std::vector<snp::ResetHuman> out(p.N);
         auto emit = [&](int i, const snp::ResetHuman &h) { out[i] = h; };
         const int scen = snp::reset_generate(p, seed0 + e, rng, w, emit);
