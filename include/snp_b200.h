@@ -26,6 +26,7 @@
  *                                                   social_nav_gym.py:252-274 imitation_learning_step
  *   snp_lookahead (+ dyn_out peek of snp_step)    <- crowd_nav/policy/cadrl.py:42-83 compute_rotated_states_and_reward, :13-40;
  *                                                   motion_model_manager.py:691-709 get_next_human_observable_states
+ *   snp_robot_push_out                            <- src/robot_agent.py:35-48 RobotAgent.check_collisions (social_nav_sim.py:509)
  *   snp_reset                                     <- social_nav_gym.py:120-225 reset, social_nav_sim.py:200-431 scenario generators
  *   snp_pack_states / snp_unpack_states           <- src/agent.py:256-266 get_safe_state / set_state row layout
  *   snp_large_step                                <- same update for one very large crowd (tiled all-pairs)
@@ -195,6 +196,9 @@ int snp_device_info(int32_t *out4);
 int snp_step(const snp_crowd *crowd, const snp_step_opts *opts, void *cuda_stream);
 int snp_checks(const snp_crowd *crowd, const snp_step_opts *opts, void *cuda_stream);
 int snp_laser(const snp_laser_args *args, void *cuda_stream);
+/* RobotAgent.check_collisions (src/robot_agent.py:35-48): crowd->robot's position is pushed out of the humans it overlaps (in index
+ * order), then out of the wall polygons it overlaps; sequential per env, bit-identical to the reference for fp64 state. */
+int snp_robot_push_out(const snp_crowd *crowd, void *cuda_stream);
 /* Rewrites crowd->dyn, stat (radius, mass, desired speed; the safety space is kept), goals, goal_idx, goal_cnt and crowd->robot. */
 int snp_reset(const snp_crowd *crowd, const snp_reset_args *args, void *cuda_stream);
 /* Uses crowd->dyn (current px,py,vx,vy,theta,omega), crowd->stat (radius) and crowd->robot (px,py,r,gx,gy,vd). */

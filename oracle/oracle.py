@@ -72,6 +72,8 @@ def _load():
         _lib.orc_imitation_steps.restype = None
         _lib.orc_lookahead.argtypes = [ctypes.c_int] * 4 + [dp, dp, dp, dp, ctypes.c_double, dp, dp, ctypes.c_int]
         _lib.orc_lookahead.restype = None
+        _lib.orc_robot_push_out.argtypes = [ctypes.c_int] * 4 + [dp, dp, dp]
+        _lib.orc_robot_push_out.restype = None
         _lib.orc_checks.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, dp, dp]
         _lib.orc_checks.restype = None
         _lib.orc_laser.argtypes = [ctypes.c_int] * 5 + [dp, dp, dp, ctypes.c_double, ctypes.c_int, ctypes.c_double, dp,
@@ -159,6 +161,21 @@ def lookahead(cur, nxt, robot, actions, dt, visible=False, n_threads=1):
     rewards = np.zeros((E, A))
     lib.orc_lookahead(E, N, A, int(visible), _dp(cur), _dp(nxt), _dp(robot), _dp(actions), float(dt), _dp(rotated), _dp(rewards), int(n_threads))
     return rotated, rewards
+
+
+def robot_push_out(humans, walls, robot):
+    """RobotAgent.check_collisions (robot_agent.py:35-48): humans [E,n,3] = x,y,r; walls [W,S,2,2] NaN padded or None;
+    robot [E,3] = x,y,r.  Returns the pushed-out robot positions [E,2]."""
+    lib = _load()
+    humans, rb = _c(humans), _c(robot).copy()
+    E, n, _ = humans.shape
+    if walls is None or np.asarray(walls).size == 0:
+        W, S, wl = 0, 0, np.zeros(4)
+    else:
+        wl = _c(np.asarray(walls, np.float64).reshape(walls.shape[0], walls.shape[1], 4))
+        W, S = wl.shape[0], wl.shape[1]
+    lib.orc_robot_push_out(E, n, W, S, _dp(humans), _dp(wl), _dp(rb))
+    return rb[:, :2]
 
 
 def checks(states, n_humans, robot, action, time_now, consts):

@@ -580,4 +580,34 @@ void orc_lookahead(int E, int N, int A, int visible, const double *cur, const do
     }
 }
 
+/* src/robot_agent.py:35-48 RobotAgent.check_collisions: the robot is pushed out of every human it overlaps, in list
+ * order, then out of every wall polygon it overlaps (closest point of obstacle.py:53-66), each push seeing the previous ones.
+ * humans [E][n][3] = x,y,r; walls [W][S][4] NaN padded (shared by the envs); robot [E][3] = x,y,r, position updated in place. */
+void orc_robot_push_out(int E, int n, int W, int S, const double *humans, const double *walls, double *robot) {
+    for (int e = 0; e < E; ++e) {
+        double *rb = robot + 3 * (size_t)e;
+        for (int j = 0; j < n; ++j) {
+            const double *h = humans + ((size_t)e * n + j) * 3;
+            const double dx = rb[0] - h[0], dy = rb[1] - h[1];
+            const double dist = np_norm(1, dx, dy);
+            if (dist < h[2] + rb[2]) {
+                const double ux = dx / dist, uy = dy / dist, sum = h[2] + rb[2];
+                rb[0] = h[0] + ux * sum; rb[1] = h[1] + uy * sum;
+            }
+        }
+        for (int w = 0; w < W; ++w) {
+            double cx, cy;
+            closest_point(walls + (size_t)w * S * 4, S, rb[0], rb[1], 0, &cx, &cy);
+            int any = 0;
+            for (int s = 0; s < S; ++s) any |= !isnan(walls[((size_t)w * S + s) * 4]);
+            const double dist = any ? np_norm(1, cx - rb[0], cy - rb[1]) : 10000.0;   /* min_distance of obstacle.py:54,64 */
+            if (dist < rb[2]) {
+                const double nn = np_norm(1, cx - rb[0], cy - rb[1]);
+                const double ux = (rb[0] - cx) / nn, uy = (rb[1] - cy) / nn;
+                rb[0] = cx + ux * rb[2]; rb[1] = cy + uy * rb[2];
+            }
+        }
+    }
+}
+
 int orc_abi_version(void) { return 1; }

@@ -295,6 +295,11 @@ class CrowdEngine:
                     info=(f >> L.FLAG_INFO_SHIFT) & 7, actual_collision=(f & L.FLAG_ACTUAL_COLLISION) != 0, actual_dmin=c[:, 2],
                     actual_goal=(f & L.FLAG_ACTUAL_GOAL) != 0, touched=(f & L.FLAG_TOUCHED) != 0)
 
+    def robot_check_collisions(self):
+        """RobotAgent.check_collisions(humans, walls) (robot_agent.py:35-48) for every env: the robot is pushed out of the humans it
+        overlaps (in index order), then out of the walls; updates self.robot's position in place."""
+        L.check(self.lib.snp_robot_push_out(ctypes.byref(self._crowd()), _stream()))
+
     def check_actual_collisions_and_goal(self):
         r = self.run_checks(pre=False, post=True)
         return r["actual_collision"], r["actual_dmin"], r["actual_goal"]

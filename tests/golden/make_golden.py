@@ -400,6 +400,42 @@ def scenario_cases():
     print("scenarios ->", os.path.getsize(path), "B")
 
 
+def push_out_case():
+    """RobotAgent.check_collisions (robot_agent.py:35-48): the robot pushed out of the humans and walls it overlaps, through the
+    reference's own method on the reference's own objects (7 humans + 3 wall polygons of the dense example, and a wall-free
+    circular crossing), from 48 + 16 start positions placed on / near humans and wall edges."""
+    out = {}
+    rng = np.random.RandomState(5)
+    for name, sim in [("walls", custom_sim(dense_example_data(), "hsfm_farina", robot_visible=True)), ("cc", cc_sim("sfm_helbing", 2003, 6, robot_visible=True))]:
+        humans = np.array([[h.position[0], h.position[1], h.radius] for h in sim.humans])
+        walls = list(sim.walls)
+        starts, ends = [], []
+        n_cases = 48 if name == "walls" else 16
+        for k in range(n_cases):
+            if k % 3 == 0 and walls:
+                w = walls[rng.randint(len(walls))]
+                seg = list(w.segments.values())[rng.randint(len(w.segments))]
+                t = rng.uniform(0, 1)
+                p = np.array(seg[0]) * (1 - t) + np.array(seg[1]) * t + rng.uniform(-0.35, 0.35, 2)
+            elif k % 3 == 1:
+                h = sim.humans[rng.randint(len(sim.humans))]
+                p = h.position + rng.uniform(-0.5, 0.5, 2)
+            else:
+                i, j = rng.choice(len(sim.humans), 2, replace=False)
+                p = 0.5 * (sim.humans[i].position + sim.humans[j].position) + rng.uniform(-0.3, 0.3, 2)
+            sim.robot.position = np.array(p, dtype=np.float64)
+            starts.append(sim.robot.position.copy())
+            sim.robot.check_collisions(sim.humans, sim.walls)
+            ends.append(np.array(sim.robot.position, dtype=np.float64))
+        out[name + "_humans"], out[name + "_walls"] = humans, pack_walls(sim.walls)
+        out[name + "_radius"] = np.float64(sim.robot.radius)
+        out[name + "_start"], out[name + "_end"] = np.array(starts), np.array(ends)
+        print("push_out", name, "moved", int((np.abs(np.array(starts) - np.array(ends)).sum(1) > 0).sum(), ), "of", n_cases)
+    path = os.path.join(HERE, "push_out.npz")
+    np.savez_compressed(path, **out)
+    print("push_out ->", os.path.getsize(path), "B")
+
+
 def numba_cases():
     """Second witness: the reference's Numba operator update_humans_parallel (forces_parallel.py:184)."""
     out = {}
@@ -614,7 +650,7 @@ def gym_case():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["traj", "pt", "il", "lookahead", "scenarios", "numba", "peek", "flags", "laser", "gym"]
+    which = sys.argv[1:] or ["traj", "pt", "il", "lookahead", "scenarios", "push_out", "numba", "peek", "flags", "laser", "gym"]
     if "traj" in which:
         traj_cases()
     if "pt" in which:
@@ -625,6 +661,8 @@ if __name__ == "__main__":
         lookahead_case()
     if "scenarios" in which:
         scenario_cases()
+    if "push_out" in which:
+        push_out_case()
     if "numba" in which:
         numba_cases()
     if "peek" in which:

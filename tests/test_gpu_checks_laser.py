@@ -162,3 +162,35 @@ def test_peek_next_observable_states_vs_reference_golden():
         obs8 = eng.get_next_human_observable_states(0.25, theta_and_omega_visible=True)
         assert rel_err(obs8[0], z[model + "_obs8"]).max() < 1e-9
         assert rel_err(eng.desired_force()[0], z[model + "_after"][:, 10:12], scale=100.0).max() < 1e-9
+
+
+def test_robot_push_out_vs_reference_golden_and_oracle():
+    """RobotAgent.check_collisions (robot_agent.py:35-48) on the device: one env per recorded start position, bit-exact
+    against the live reference's result; a seeded 512-env batch with per-env humans against the oracle; fp32 state to 1e-6."""
+    from social_navigation_pyenvs_b200 import CrowdEngine, scenarios
+    z = np.load(os.path.join(GOLDEN, "push_out.npz"))
+    for name in ("walls", "cc"):
+        H, st, en, r = z[name + "_humans"], z[name + "_start"], z[name + "_end"], float(z[name + "_radius"])
+        E, n = len(st), len(H)
+        rows = np.zeros((E, n, 13))
+        rows[:, :, 0:2], rows[:, :, 8], rows[:, :, 9] = H[None, :, 0:2], H[None, :, 2], 75.0
+        robot = np.zeros((E, 13))
+        robot[:, 0:2], robot[:, 8], robot[:, 9] = st, r, 80.0
+        walls = z[name + "_walls"]
+        for dtype, tol in [(torch.float64, 0.0), (torch.float32, 2e-6)]:
+            eng = CrowdEngine.from_reference_arrays("sfm_helbing", rows, np.zeros((E, n, 1, 2)), walls=walls if walls.size else None,
+                                                    consider_robot=False, robot=robot, dtype=dtype)
+            eng.robot_check_collisions()
+            got = eng.robot_rows()[0][:, 0:2]
+            assert np.abs(got - en).max() <= tol, (name, dtype)
+    E, n = 512, 25
+    sc = scenarios.ccso_synthetic(E, n, 77)
+    rng = np.random.RandomState(3)
+    robot = sc["robot"].copy()
+    robot[:, 0:2] = sc["states"][np.arange(E), rng.randint(n, size=E), 0:2] + rng.uniform(-0.6, 0.6, (E, 2))
+    walls = scenarios.pack_walls(scenarios.EXAMPLE_WALLS)
+    eng = CrowdEngine.from_reference_arrays("hsfm_farina", sc["states"], sc["goals"], walls=walls, consider_robot=False, robot=robot)
+    eng.robot_check_collisions()
+    ref = oracle.robot_push_out(sc["states"][:, :, [0, 1, 8]], walls, robot[:, [0, 1, 8]])
+    got = eng.robot_rows()[0][:, 0:2]
+    assert np.array_equal(got, ref) and (np.abs(ref - robot[:, 0:2]).sum(1) > 0).sum() > 100

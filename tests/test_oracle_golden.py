@@ -144,6 +144,19 @@ def test_lookahead_rewards_and_rotated_states():
     assert seen == {-1.0, 0.0, 1.0}
 
 
+def test_robot_push_out_bit_exact():
+    """RobotAgent.check_collisions (robot_agent.py:35-48) from 64 start positions recorded from the live reference: bit for bit."""
+    z = np.load(os.path.join(GOLDEN, "push_out.npz"))
+    moved = 0
+    for name in ("walls", "cc"):
+        H, st, en, r = z[name + "_humans"], z[name + "_start"], z[name + "_end"], float(z[name + "_radius"])
+        rb = np.concatenate([st, np.full((len(st), 1), r)], 1)
+        out = oracle.robot_push_out(np.tile(H, (len(st), 1, 1)), z[name + "_walls"], rb)
+        assert np.array_equal(out, en), name
+        moved += int((np.abs(st - en).sum(1) > 0).sum())
+    assert moved >= 30
+
+
 def test_numba_operator_semantics():
     """Second witness: numba_compat=1 reproduces forces_parallel.update_humans_parallel (fp:184), including the
     Guo wall force divided by the wall count (fp:161) and '<=' goal switching (fp:226)."""
