@@ -489,6 +489,7 @@ def main():
                                                  robot=None if inp["robot_visible"] else inp["robot"])
 
     eng = make_engine(tdtype)
+    eng.mapping = int(os.environ.get("SNP_MAPPING", "0"))  # tuning: 1 force warp-packed, 2 force block-packed thread mapping
     action_host = torch.tensor(np.tile([[0.0], [1.0]], (1, E)), dtype=tdtype).pin_memory()  # [2,E] holonomic action
     eng.action.copy_(action_host)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2

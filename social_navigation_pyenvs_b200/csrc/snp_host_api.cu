@@ -301,7 +301,7 @@ int snp_laser_host(int32_t E, int32_t N, const double *humans, const double *wal
 int snp_measure_pipe_peak(int32_t kind, double *out) {
     if (!out || kind < 0 || kind > 2) { set_error("snp_measure_pipe_peak: kind must be 0 (fp32 FMA), 1 (fp64 FMA) or 2 (MUFU.EX2)"); return SNP_ERR_INVALID; }
     const int sms = device_sm_count();
-    const int blocks = sms * 8, threads = 256, iters = kind == 1 ? 1 << 14 : 1 << 16;
+    const int blocks = sms * 8, threads = 256, iters = kind == 1 ? 1 << 14 : (kind == 0 ? 1 << 15 : 1 << 13);  // ~2 ms per launch each
     void *buf = nullptr;
     SNP_CUDA_OK(cudaMalloc(&buf, 64));
     cudaEvent_t e0, e1;

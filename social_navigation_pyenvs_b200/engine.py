@@ -407,6 +407,18 @@ class CrowdEngine:
             self.respawn_bounds, self.respawn_envs = None, None
         return self._reset_scen, self._reset_draws
 
+    def onestep_lookahead(self, action, time_step=0.25, theta_and_omega_visible=False):
+        """SocialNavSim.onestep_lookahead (social_nav_sim.py:1031-1049), the per-action form the policies use when they do not
+        batch the action space: swept collision / goal test and reward of `action` [E,2] over `time_step` on the current state,
+        and the humans' observable states one `time_step` ahead (query_env).  Returns (ob [E,N,4|8], reward [E])."""
+        keep = self.consts[5]
+        self.consts[5] = float(time_step)
+        try:
+            reward = self.run_checks(action, pre=True, post=False)["reward"]
+        finally:
+            self.consts[5] = keep
+        return self.get_next_human_observable_states(time_step, theta_and_omega_visible), reward
+
     # ------------------------------------------------------------------ policy-side lookahead (SURVEY 8f-3)
     def set_action_space(self, actions):
         """actions [A,2] holonomic velocities shared by all envs (crowd_nav/policy/cadrl.py build_action_space)."""

@@ -102,6 +102,24 @@ def test_lookahead_vs_oracle_batch(dtype, tol, n):
         assert torch.equal(rot2, rot3) and torch.equal(rew2, rew3)
 
 
+def test_onestep_lookahead_equals_the_batched_lookahead_per_action():
+    """SocialNavSim.onestep_lookahead (social_nav_sim.py:1031-1049) -- one action at a time: its reward is the batched operator's
+    reward for that action (same swept test, cadrl.py:56-72 vs sim:949-1029 at global time 0) and its observation the peek."""
+    from social_navigation_pyenvs_b200 import CrowdEngine
+    E, n = 48, 12
+    sc, S, R = _batch(E, n, 31)
+    eng = CrowdEngine.from_reference_arrays("hsfm_new_guo", S, sc["goals"], consider_robot=False, all_params_equal=True, robot=R)
+    acts = _actions()
+    eng.set_action_space(acts)
+    rot, rew = eng.lookahead(0.25)
+    rew = rew.cpu().numpy()
+    nxt = eng.get_next_human_observable_states(0.25)
+    for k in (0, 7, 33, 80):
+        ob, r = eng.onestep_lookahead(np.tile(acts[k], (E, 1)), 0.25)
+        assert np.array_equal(r, rew[:, k]), k
+        assert np.array_equal(ob, nxt)
+
+
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_lookahead_full_size_properties(dtype):
     """BASELINE size (4096 envs x 81 actions x 25 humans): the rotation is an isometry, shared columns agree, rewards take

@@ -34,22 +34,38 @@ def launches():
     agg = collections.OrderedDict()
     for r in rows[1:]:
         agg.setdefault(r[ki], []).append(float(r[vi].replace(",", "")))
-    total = sum(sum(v) for v in agg.values())
+    def phase(name):
+        if "_peak" in name:
+            return "after the timed region: roofline denominators (snp_measure_pipe_peak)"
+        if "k_unpack" in name or "FillFunctor<double>" in name or "FillFunctor<int>" in name:
+            return "setup"
+        if "FillFunctor<unsigned char>" in name:
+            return "timed loop, outside the event pairs: 256 MiB L2 flush between steps"
+        return "step"
+    step_total = sum(sum(v) for k, v in agg.items() if phase(k) == "step")
     with open(os.path.join(OUT, f"{R}_launches_bench.csv"), "w") as f:
         w = csv.writer(f)
-        w.writerow(["kernel", "launches", "mean_us", "total_us", "share_of_captured_gpu_time"])
+        w.writerow(["kernel", "launches", "mean_us", "total_us", "phase", "share_of_step_gpu_time"])
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-            w.writerow([k[:110], len(v), round(sum(v) / len(v) / 1e3, 2), round(sum(v) / 1e3, 1), round(sum(v) / total, 4)])
+            w.writerow([k[:110], len(v), round(sum(v) / len(v) / 1e3, 2), round(sum(v) / 1e3, 1), phase(k),
+                        round(sum(v) / step_total, 4) if phase(k) == "step" else ""])
 
 
 def metrics():
     reps = sorted({f[:-8] + ".ncu-rep" for f in os.listdir(SRC) if f.startswith(R + "_k_") and f.endswith(".raw.csv")} |
                   {f for f in os.listdir(SRC) if f.startswith(R + "_k_") and f.endswith(".ncu-rep")})
     cols, names = [], []
+    SCALE = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+    units = {}
     for f in reps:
         rows = ncu_csv(os.path.join(SRC, f), "raw")
-        cols.append(dict(zip(rows[0], rows[2])))
-        units = dict(zip(rows[0], rows[1]))
+        col, unit = dict(zip(rows[0], rows[2])), dict(zip(rows[0], rows[1]))
+        for m in WANT:  # ncu picks a unit per capture: bring times to us and sizes to Mbyte so that a row reads across kernels
+            if m in col and unit.get(m) in SCALE and col[m]:
+                col[m] = "%.6g" % (float(col[m].replace(",", "")) * SCALE[unit[m]])
+                unit[m] = "us" if unit[m] in ("ns", "us", "ms", "s") else "Mbyte"
+        cols.append(col)
+        units.update({m: unit.get(m, "") for m in WANT})
         names.append(f[len(R) + 1:-8] + " :: " + cols[-1].get("Kernel Name", "")[:60])
     with open(os.path.join(OUT, f"{R}_ncu_metrics.csv"), "w") as f:
         w = csv.writer(f)
