@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256) k_mufu_peak(float *out, int iters) {
 }
 
 __global__ void k_debug_exp(const double *x, double *y, int n) {
-    __shared__ double tbl[64];
+    __shared__ __align__(16) double tbl[kExpN];
     exp_table_init(tbl);
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,6 +265,7 @@ extern "C" {
 
 int snp_debug_exp(const double *x_dev, double *y_dev, int32_t n, void *stream) {
     if (!x_dev || !y_dev || n <= 0) { set_error("snp_debug_exp: bad argument"); return SNP_ERR_INVALID; }
+    SNP_CUDA_OK(ensure_exp_table());
     k_debug_exp<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x_dev, y_dev, n);
     count_launch();
     SNP_CUDA_OK(cudaGetLastError());

@@ -94,16 +94,17 @@ __device__ __forceinline__ void pair_force(const Params<T> &P, const double *tbl
     if (__any_sync(vote_mask, rd > T(0))) pair_eval<T, SOC, true>(P, tbl, x1, y1, vx1, vy1, rs1, x2, y2, vx2, vy2, rs2, fx, fy);
 }
 
-// One wall-segment slot staged in shared memory: a, e = b - a, 1/|e|^2.  ax is NaN for padding slots.
+// One wall-segment slot staged in shared memory: a, -e = a - b, -1/|e|^2.  ax is NaN for padding slots.  (Negated so that
+// t = ((p-a).(-e)) * (-1/|e|^2) and p - h = (p-a) + t (-e) need no sign flip inside the search loop: same bits, one DADD less.)
 // Padded to six words and 16-byte aligned so that a segment is fetched with three LDS.128 (fp64) / LDS.64 + LDS.128 (fp32)
 // instead of five scalar loads.
-template <typename T> struct alignas(16) Seg { T ax, ay, ex, ey, inv_len2, pad; };
+template <typename T> struct alignas(16) Seg { T ax, ay, nex, ney, ninv_len2, pad; };
 
 template <typename T> __device__ __forceinline__ Seg<T> make_seg(T ax, T ay, T bx, T by) {
     Seg<T> s;
-    s.ax = ax; s.ay = ay; s.ex = bx - ax; s.ey = by - ay;
-    const T len = np_norm(s.ex, s.ey);
-    s.inv_len2 = Real<T>::rcp_(len * len);
+    s.ax = ax; s.ay = ay; s.nex = ax - bx; s.ney = ay - by;
+    const T len = np_norm(s.nex, s.ney);
+    s.ninv_len2 = -Real<T>::rcp_(len * len);
     s.pad = T(0);
     return s;
 }
@@ -119,10 +120,10 @@ __device__ __forceinline__ void closest_point_impl(const Seg<T> *segs, int cnt, 
     for (int s = 0; s < cnt; ++s) {
         const Seg<T> g = segs[s];
         const T qx = px - g.ax, qy = py - g.ay;
-        T t = np_dot(qx, qy, g.ex, g.ey) * g.inv_len2;
+        T t = np_dot(qx, qy, g.nex, g.ney) * g.ninv_len2;
         t = max0(t);
         t = t < T(1) ? t : T(1);
-        const T ux = fma_<T>(-t, g.ex, qx), uy = fma_<T>(-t, g.ey, qy);  // p - h,  h = a + t e
+        const T ux = fma_<T>(t, g.nex, qx), uy = fma_<T>(t, g.ney, qy);  // p - h,  h = a + t e
         const T d = np_sq(ux, uy);
         const bool take = FIRST_WINS ? (d < best) : (d <= best);
         best = take ? d : best; dxb = take ? ux : dxb; dyb = take ? uy : dyb;

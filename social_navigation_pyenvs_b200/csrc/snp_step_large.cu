@@ -73,7 +73,7 @@ template <typename T, int SOC>
 __global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
     __shared__ __align__(16) unsigned char tile_raw[sizeof(Ent<T>) * kTile];
     __shared__ T tile_rs[kTile];
-    __shared__ double exp_tbl_s[64];
+    __shared__ __align__(16) double exp_tbl_s[kExpN];
     __shared__ T sbox[20];
     Ent<T> *tile = reinterpret_cast<Ent<T> *>(tile_raw);
     const KArgs<T> &a = la.k;
@@ -152,8 +152,9 @@ __global__ void __launch_bounds__(kTile) k_large_finish(const LargeArgs<T> la) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nseg = a.W * a.S;
     double *exp_tbl_s = reinterpret_cast<double *>(smem_raw);
-    Seg<T> *segs = reinterpret_cast<Seg<T> *>(smem_raw + 512);
-    int *seg_cnt = reinterpret_cast<int *>(smem_raw + 512 + ((sizeof(Seg<T>) * (size_t)nseg + 15) & ~size_t(15)));
+    constexpr size_t kTbl = sizeof(double) * kExpN;
+    Seg<T> *segs = reinterpret_cast<Seg<T> *>(smem_raw + kTbl);
+    int *seg_cnt = reinterpret_cast<int *>(smem_raw + kTbl + ((sizeof(Seg<T>) * (size_t)nseg + 15) & ~size_t(15)));
     if (sizeof(T) == 8) exp_table_init(exp_tbl_s);
     for (int k = threadIdx.x; k < nseg; k += blockDim.x) {
         const T *w = a.walls + (size_t)k * 4;
@@ -243,11 +244,12 @@ template <typename T> __global__ void k_large_publish(const T *dyn, const T *sta
 template <typename T, int SOC, int OBS, int HEADED> int launch_large(const LargeArgs<T> &la, cudaStream_t st) {
     const long long N = la.k.EN;
     const int nseg = la.k.W * la.k.S;
+    if (sizeof(T) == 8) SNP_CUDA_OK(ensure_exp_table());
     k_tile_boxes<T><<<(unsigned)la.n_tiles, kTile, 0, st>>>(la.others, la.M, la.boxes);
     const long long per_block = (long long)kTile * kAgentsPerThread;
     dim3 grid((unsigned)((N + per_block - 1) / per_block), (unsigned)la.J);
     k_large_pairs<T, SOC><<<grid, kTile, 0, st>>>(la);
-    const size_t smem = 512 + ((sizeof(Seg<T>) * (size_t)nseg + 15) & ~size_t(15)) + sizeof(int) * (la.k.W + 1) + 16;
+    const size_t smem = sizeof(double) * kExpN + ((sizeof(Seg<T>) * (size_t)nseg + 15) & ~size_t(15)) + sizeof(int) * (la.k.W + 1) + 16;
     auto fin = k_large_finish<T, OBS, HEADED>;
     if (smem > 48 * 1024) SNP_CUDA_OK(cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fin<<<(unsigned)((N + kTile - 1) / kTile), kTile, smem, st>>>(la);

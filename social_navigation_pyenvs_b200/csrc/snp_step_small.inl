@@ -44,7 +44,7 @@ template <typename T> struct SmemLayout {
     int slots;
     __host__ __device__ SmemLayout(int nseg, int seg_groups, int W, int slots_, int red_doubles, int xchg_vec2 = 0, int groups = 0,
                                    int robot_groups = 0) : slots(slots_) {
-        size_t off = sizeof(T) == 8 ? 64 * sizeof(double) : 0;  // exp table (fp64 only)
+        size_t off = sizeof(T) == 8 ? kExpN * sizeof(double) : 0;  // exp table (fp64 only)
         segs = off; off += sizeof(Seg<T>) * (size_t)nseg * seg_groups;
         off = (off + 15) & ~size_t(15);
         seg_cnt = off; off += sizeof(int) * (size_t)(W > 0 ? W : 1) * seg_groups;
@@ -675,6 +675,7 @@ template <typename T, int SOC, int OBS, int HEADED>
 int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
     KArgs<T> a = a_in;
     const int nseg = a.W * a.S;
+    if (sizeof(T) == 8) SNP_CUDA_OK(ensure_exp_table());
     if (a.N > 512) { set_error("snp_step handles N <= 512 humans per env (got %d); use snp_large_step", a.N); return SNP_ERR_UNSUPPORTED; }
     const bool per_agent = a.agent_params != nullptr;
     // pairs evaluated once per warp / block whenever the law is antisymmetric (see social_force_halved)
