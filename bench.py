@@ -166,7 +166,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     inp = build_inputs(args.workload, 2000)
-    threads = os.cpu_count() or 1
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     n_envs = min(inp["E"], max(threads * 4, 128))
     for _ in range(args.warmup):
         oracle_rate(inp, n_envs, threads, 2)
@@ -177,7 +177,7 @@ def run_reference(args, rank, world):
     total = sum(times)
     value = n_envs * inp["N"] * SUBSTEPS * args.steps / total
     sample = f"{n_envs} of {inp['E']} envs x {SUBSTEPS} sub-steps per step, C restatement of the serial Python/NumPy path, OpenMP over envs"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": 0, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "substeps_per_step": SUBSTEPS, "dt": DT, "sample": sample},
@@ -607,7 +607,7 @@ def main():
             "roofline": roofline, "wall_s_timed_region": wall}
 
     if not args.no_cpu_baseline and world == 1:
-        threads = os.cpu_count() or 1
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
         n_envs = min(E, max(threads * 4, 128))
         oracle_rate(inp, n_envs, threads, 2)
         reps, spent, done = 0, 0.0, 0
