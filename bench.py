@@ -546,12 +546,8 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-        eng.action.copy_(action_host, non_blocking=True)
-        one_step()
-        obs_host.copy_(eng.dyn[:4], non_blocking=True)
-        flags_host.copy_(eng.flags, non_blocking=True)
-        checks_host.copy_(eng.checks, non_blocking=True)
-        torch.cuda.synchronize()
+        # ONE C-ABI call with host buffers (snp_gym_step_host): H2D action, fused launch, D2H observation + flags + checks, sync
+        eng.step_host(action_host, obs_host, flags_host, checks_host, DT, n_substeps=SUBSTEPS, pre_checks=True, post_checks=False, track_touch=True)
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -603,7 +599,7 @@ def main():
                        "timing": "sum of per-step CUDA-event pairs on the launch stream, max over ranks"},
             "clocks": clocks.summary(), "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "CrowdEngine.step(action): pinned H2D action, fused launch, D2H observation + flags + reward", "steps": e2e_steps},
+                    "api": "CrowdEngine.step_host -> snp_gym_step_host (C ABI, host buffers): pinned H2D action, fused launch, D2H observation + flags + reward, sync", "steps": e2e_steps},
             "roofline": roofline, "wall_s_timed_region": wall}
 
     if not args.no_cpu_baseline and world == 1:

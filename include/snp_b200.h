@@ -16,6 +16,7 @@
  *                                                   shadows: motion_model_manager.py:354-373,424-459 + src/forces.py
  *   fused sub-step loop + robot motion            <- social_nav_gym.py:240-245 (20 x robot.step + update_humans),
  *                                                   src/robot_agent.py:126-136
+ *   snp_gym_step_host                             <- social_nav_gym.py:227-250 SocialNavGym.step with host action / observation buffers
  *   snp_checks (+ fused into snp_step)            <- social_nav_sim.py:949-984 collision_detection_and_reaching_goal,
  *                                                   :986-1029 compute_reward_and_infos, :702-703;
  *                                                   social_nav_gym.py:107-118 check_actual_collisions_and_goal
@@ -244,6 +245,13 @@ int snp_update_humans_parallel_host(int32_t type, int32_t E, int32_t N, int32_t 
                                     const double *safety_space, int32_t all_params_equal, int32_t last_is_robot,
                                     int32_t numba_compat, int32_t dtype, int32_t n_substeps, double *desired_force,
                                     double *out_state);
+/* SocialNavGym.step (social_gym/social_nav_gym.py:227-250) for a crowd that stays RESIDENT on the device, with host buffers for what
+ * crosses the boundary every step: `action_host` [2][E] (crowd dtype; copied into opts->action), then snp_step, then the observation
+ * `obs_host` [4][E*N] = px, py, vx, vy of every human (crowd dtype), `flags_host` [E] and `checks_host` [E][4] (dmin, reward, actual
+ * dmin, -) are copied back and the stream is synchronised.  Pass pinned host memory for asynchronous copies; any of the host
+ * pointers may be NULL. */
+int snp_gym_step_host(const snp_crowd *crowd, const snp_step_opts *opts, const void *action_host, void *obs_host, int32_t *flags_host,
+                      double *checks_host, void *cuda_stream);
 /* LaserSensor.get_laser_measurements over E sensors: humans [E][N][3] = x,y,r; walls [W][S][2][2]; pose [E][3];
  * ranges [E][samples]; hits [E][samples] or NULL. */
 int snp_laser_host(int32_t E, int32_t N, const double *humans, const double *walls, int32_t W, int32_t S, const double *pose,

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "snp_last_error": (ctypes.c_char_p, []),
     "snp_device_info": (ctypes.c_int, [ctypes.POINTER(c_int32)]),
     "snp_step": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpStepOpts), c_void_p]),
+    "snp_gym_step_host": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpStepOpts), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "snp_checks": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpStepOpts), c_void_p]),
     "snp_laser": (ctypes.c_int, [ctypes.POINTER(SnpLaserArgs), c_void_p]),
     "snp_lookahead": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpLookaheadArgs), c_void_p]),

@@ -117,6 +117,24 @@ int snp_checks(const snp_crowd *crowd, const snp_step_opts *opts, void *stream) 
     return snp_step(crowd, &o, stream);
 }
 
+int snp_gym_step_host(const snp_crowd *crowd, const snp_step_opts *opts, const void *action_host, void *obs_host, int32_t *flags_host,
+                      double *checks_host, void *stream) {
+    if (!crowd || !opts) { set_error("null descriptor"); return SNP_ERR_INVALID; }
+    if (!opts->action) { set_error("snp_gym_step_host: opts->action must be the device action buffer [2][E]"); return SNP_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t w = crowd->dtype == SNP_F64 ? 8 : 4;
+    const size_t E = (size_t)crowd->E, EN = E * (size_t)crowd->N;
+    if (action_host) SNP_CUDA_OK(cudaMemcpyAsync(const_cast<void *>(opts->action), action_host, 2 * E * w, cudaMemcpyHostToDevice, st));
+    const int rc = snp_step(crowd, opts, stream);
+    if (rc) return rc;
+    // px, py, vx, vy are the first four fields of dyn: one contiguous block
+    if (obs_host) SNP_CUDA_OK(cudaMemcpyAsync(obs_host, crowd->dyn, 4 * EN * w, cudaMemcpyDeviceToHost, st));
+    if (flags_host && opts->flags) SNP_CUDA_OK(cudaMemcpyAsync(flags_host, opts->flags, E * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (checks_host && opts->checks) SNP_CUDA_OK(cudaMemcpyAsync(checks_host, opts->checks, E * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SNP_CUDA_OK(cudaStreamSynchronize(st));
+    return SNP_OK;
+}
+
 int64_t snp_launch_count(int32_t reset) {
     long long v = reset ? g_launches.exchange(0) : g_launches.load();
     return (int64_t)v;

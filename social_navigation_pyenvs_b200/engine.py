@@ -277,6 +277,16 @@ class CrowdEngine:
         o = self._opts(dt, n_substeps, robot_mode=1, pre_checks=pre_checks, post_checks=post_checks, track_touch=track_touch, advance_time=True)
         L.check(self.lib.snp_step(ctypes.byref(self._crowd()), ctypes.byref(o), _stream()))
 
+    def step_host(self, action_host, obs_host, flags_host, checks_host, dt=0.0125, n_substeps=20, pre_checks=True, post_checks=False,
+                  track_touch=False):
+        """The same gym step through ONE C-ABI call with host buffers (snp_gym_step_host): `action_host` [2,E] is copied in, the
+        fused step runs, observation [4,E,N] (px,py,vx,vy), flags [E] int32 and checks [E,4] float64 are copied back and the stream
+        is synchronised.  The buffers are CPU tensors (pinned for asynchronous copies) or NumPy arrays of the engine's dtype."""
+        o = self._opts(dt, n_substeps, robot_mode=1, pre_checks=pre_checks, post_checks=post_checks, track_touch=track_touch, advance_time=True)
+        hp = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr() if torch.is_tensor(t) else t.ctypes.data)
+        L.check(self.lib.snp_gym_step_host(ctypes.byref(self._crowd()), ctypes.byref(o), hp(action_host), hp(obs_host), hp(flags_host),
+                                           hp(checks_host), _stream()))
+
     def run_checks(self, action=None, pre=True, post=True):
         """collision_detection_and_reaching_goal + compute_reward_and_infos (social_nav_sim.py:949-1029) and
         check_actual_collisions_and_goal (social_nav_gym.py:107-118) on the current state, without stepping."""
