@@ -1,9 +1,9 @@
 // snp_reset.cu -- SocialNavGym.reset for a whole batch on the device: every environment replays the reference's
 // scenario generator (social_gym/social_nav_sim.py:200-431, chosen and seeded as social_gym/social_nav_gym.py:135-167 does) on its
 // own copy of NumPy's MT19937 stream -- see snp_reset_core.h.  A WARP per environment: the rejection sampler is a sequential,
-// data-dependent loop, so all 32 lanes walk it in lock step with identical values, and share what is parallel inside it -- the
-// distance tests of a candidate against the humans already placed (one lane per placed human, ballot) and the 624-word twist of
-// the generator (batches of 32 words).  Generator state and the placed humans live in the warp's slice of shared memory; results are
+// data-dependent loop, so the 32 lanes SPECULATE on it -- lane l evaluates the l-th next attempt (the generator's block of 624
+// words is random access), the first accepted one wins and the stream advances exactly as far as a sequential run would have -- and
+// they share the 624-word twist of the generator (batches of 32 words).  Generator state and the placed humans live in the warp's slice of shared memory; results are
 // written straight into the crowd's structure-of-arrays buffers.  Reset is not the hot path, but asynchronous episode ends make
 // masked restarts frequent in an RL loop: 4096 envs x 25 humans restart in a fraction of a step's time, without leaving the GPU.
 #include "snp_kernels.cuh"
@@ -32,7 +32,8 @@ constexpr int kResetWarps = 4;
 struct WarpGroup {
     SNP_HD int lane() const { return threadIdx.x & 31; }
     SNP_HD int size() const { return 32; }
-    __device__ __forceinline__ bool any(bool v) const { return __any_sync(0xffffffffu, v) != 0; }
+    __device__ __forceinline__ int first(bool v) const { return __ffs(__ballot_sync(0xffffffffu, v)) - 1; }
+    __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 
