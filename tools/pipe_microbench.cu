@@ -13,6 +13,8 @@ __global__ void bench(double *out, long long *cyc, double seed) {
     float f0 = (float)seed, f1 = f0 + 1, f2 = f0 + 2, f3 = f0 + 3;
     int i0 = threadIdx.x, i1 = i0 + 1, i2 = i0 + 2, i3 = i0 + 3;
     const double b = 1.0000001, c = 1e-9;
+    unsigned long long p0 = 0x3f8000013f800001ull + threadIdx.x, p1 = p0 + 1, p2 = p0 + 2, p3 = p0 + 3, p4 = p0 + 4, p5 = p0 + 5, p6 = p0 + 6, p7 = p0 + 7;
+    const unsigned long long pk = 0x3f8000013f800001ull;
     __syncthreads();
     const long long t0 = clock64();
 #pragma unroll 1
@@ -56,6 +58,23 @@ __global__ void bench(double *out, long long *cyc, double seed) {
             asm volatile("fma.rn.f32 %0,%0,%4,%4; fma.rn.f32 %1,%1,%4,%4; fma.rn.f32 %2,%2,%4,%4; fma.rn.f32 %3,%3,%4,%4;"
                          "fma.rn.f32 %0,%0,%4,%4; fma.rn.f32 %1,%1,%4,%4; fma.rn.f32 %2,%2,%4,%4; fma.rn.f32 %3,%3,%4,%4;"
                          : "+f"(f0), "+f"(f1), "+f"(f2), "+f"(f3) : "f"(1.0001f));
+        } else if (MODE == 9) {  // 8 independent packed FFMA2 (fma.rn.f32x2: two FP32 FMAs per instruction, 64-bit register pairs)
+            asm volatile("fma.rn.f32x2 %0,%0,%8,%8; fma.rn.f32x2 %1,%1,%8,%8; fma.rn.f32x2 %2,%2,%8,%8; fma.rn.f32x2 %3,%3,%8,%8;"
+                         "fma.rn.f32x2 %4,%4,%8,%8; fma.rn.f32x2 %5,%5,%8,%8; fma.rn.f32x2 %6,%6,%8,%8; fma.rn.f32x2 %7,%7,%8,%8;"
+                         : "+l"(p0), "+l"(p1), "+l"(p2), "+l"(p3), "+l"(p4), "+l"(p5), "+l"(p6), "+l"(p7) : "l"(pk));
+        } else if (MODE == 10) {  // 8 FFMA2 + 8 IMAD interleaved
+            asm volatile("fma.rn.f32x2 %0,%0,%12,%12; mad.lo.s32 %8,%8,%13,%13; fma.rn.f32x2 %1,%1,%12,%12; mad.lo.s32 %9,%9,%13,%13;"
+                         "fma.rn.f32x2 %2,%2,%12,%12; mad.lo.s32 %10,%10,%13,%13; fma.rn.f32x2 %3,%3,%12,%12; mad.lo.s32 %11,%11,%13,%13;"
+                         "fma.rn.f32x2 %4,%4,%12,%12; mad.lo.s32 %8,%8,%13,%13; fma.rn.f32x2 %5,%5,%12,%12; mad.lo.s32 %9,%9,%13,%13;"
+                         "fma.rn.f32x2 %6,%6,%12,%12; mad.lo.s32 %10,%10,%13,%13; fma.rn.f32x2 %7,%7,%12,%12; mad.lo.s32 %11,%11,%13,%13;"
+                         : "+l"(p0), "+l"(p1), "+l"(p2), "+l"(p3), "+l"(p4), "+l"(p5), "+l"(p6), "+l"(p7), "+r"(i0), "+r"(i1), "+r"(i2), "+r"(i3)
+                         : "l"(pk), "r"(3));
+        } else if (MODE == 11) {  // 8 FFMA + 8 IMAD interleaved (reference for MODE 10)
+            asm volatile("fma.rn.f32 %0,%0,%8,%8; mad.lo.s32 %4,%4,%9,%9; fma.rn.f32 %1,%1,%8,%8; mad.lo.s32 %5,%5,%9,%9;"
+                         "fma.rn.f32 %2,%2,%8,%8; mad.lo.s32 %6,%6,%9,%9; fma.rn.f32 %3,%3,%8,%8; mad.lo.s32 %7,%7,%9,%9;"
+                         "fma.rn.f32 %0,%0,%8,%8; mad.lo.s32 %4,%4,%9,%9; fma.rn.f32 %1,%1,%8,%8; mad.lo.s32 %5,%5,%9,%9;"
+                         "fma.rn.f32 %2,%2,%8,%8; mad.lo.s32 %6,%6,%9,%9; fma.rn.f32 %3,%3,%8,%8; mad.lo.s32 %7,%7,%9,%9;"
+                         : "+f"(f0), "+f"(f1), "+f"(f2), "+f"(f3), "+r"(i0), "+r"(i1), "+r"(i2), "+r"(i3) : "f"(1.0001f), "r"(3));
         } else if (MODE == 8) {  // 8 independent shuffles of a 64-bit value (2 SHFL each) -> 16 SHFL
             a0 = __shfl_sync(0xffffffffu, a0, (threadIdx.x + 1) & 31); a1 = __shfl_sync(0xffffffffu, a1, (threadIdx.x + 2) & 31);
             a2 = __shfl_sync(0xffffffffu, a2, (threadIdx.x + 3) & 31); a3 = __shfl_sync(0xffffffffu, a3, (threadIdx.x + 4) & 31);
@@ -65,7 +84,8 @@ __global__ void bench(double *out, long long *cyc, double seed) {
     }
     const long long t1 = clock64();
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + f0 + f1 + f2 + f3 + i0 + i1 + i2 + i3;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + f0 + f1 + f2 + f3 + i0 + i1 + i2 + i3 +
+                                                 (double)(p0 ^ p1 ^ p2 ^ p3 ^ p4 ^ p5 ^ p6 ^ p7);
 }
 
 template <int MODE> void run(const char *name, int per_iter, int warps) {
@@ -91,6 +111,9 @@ int main() {
         run<2>("8 DFMA + 16 IMAD interleaved", 24, w);
         run<7>("8 FFMA", 8, w);
         run<8>("16 SHFL (8 x 64-bit)", 16, w);
+        run<9>("8 FFMA2 (packed fp32x2)", 8, w);
+        run<10>("8 FFMA2 + 8 IMAD interleaved", 16, w);
+        run<11>("8 FFMA + 8 IMAD interleaved", 16, w);
     }
     run<3>("dependent DFMA chain (latency)", 8, 4);
     run<5>("dependent MUFU.RSQ64H + DFMA (latency of pair)", 4, 4);
