@@ -412,6 +412,19 @@ def run_lookahead(args, rank, world, local_rank):
         rew_host.copy_(rew, non_blocking=True)
         torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0, "cuda", world)
+    # a write-only reference on the same buffer: what a plain fill of the output achieves on this GPU (the copy peak of
+    # MEASURED_PEAKS.json is read + write traffic; a pure write stream tops out lower)
+    rot_buf = eng._rotated
+    fill_ms = []
+    for _ in range(6):
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.fill_(3)
+        a_.record(stream)
+        rot_buf.fill_(1.0)
+        b_.record(stream)
+        torch.cuda.synchronize()
+        fill_ms.append(a_.elapsed_time(b_))
+    write_only_gbs = rot_buf.numel() * rot_buf.element_size() / (min(fill_ms[1:]) * 1e-3) / 1e9
     if rank == 0:
         w = 8 if args.dtype == "f64" else 4
         rows = E * A * N
@@ -433,7 +446,9 @@ def run_lookahead(args, rank, world, local_rank):
                         "d2h_bytes_per_step": int(rew_host.numel() * 8), "api": "CrowdEngine.lookahead: pinned H2D robot state, peek + lookahead, D2H rewards "
                         "(rotated states stay on the device for the value network)", "steps": reps},
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": measured_traffic(args),
-                             "kernel": "snp::k_lookahead", "bytes_per_row": (out_bytes + in_bytes) / rows, "peak_source": hbm_src}}
+                             "kernel": "snp::k_lookahead", "bytes_per_row": (out_bytes + in_bytes) / rows, "peak_source": hbm_src,
+                             "write_only": {"fill_gbs": write_only_gbs, "frac": ach / write_only_gbs,
+                                            "how": "torch fill_ of the same output buffer, best of 5, CUDA events, L2 flushed"}}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
