@@ -42,7 +42,7 @@ template <typename T> struct LookSmem {
     __host__ __device__ LookSmem(int N, int OW, int chunk, int aper) {
         size_t off = (sizeof(T) * 11 * (size_t)N + 15) & ~size_t(15);
         pa = off; off = (off + sizeof(PerAction<T>) * (size_t)aper + 15) & ~size_t(15);
-        dist = off; off = (off + 2 * sizeof(double) * (size_t)chunk * N + 15) & ~size_t(15);
+        dist = off; off = (off + sizeof(double) * (size_t)aper * N + 15) & ~size_t(15);  // swept distances of the CTA's whole action range
         tile = off;
         tile_stride = ((size_t)chunk * N * OW * sizeof(T) + 16 + 15) & ~size_t(15);  // + 16: room for the alignment offset
         total = off + 2 * tile_stride;
@@ -108,7 +108,6 @@ __global__ void __launch_bounds__(kLookThreads, sizeof(T) == 4 ? 4 : 3) k_lookah
 
     const size_t row_words = (size_t)N * OW;
     const int nchunks = (acnt + a.chunk - 1) / a.chunk;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     // A thread keeps the same (action slot k, human j) in every tile (a tile holds at most blockDim pairs unless N > blockDim):
     // the human's state and everything of the swept test that does not depend on the action stay in registers across tiles.
     const int k_own = threadIdx.x / N, j_own = threadIdx.x - k_own * N;
@@ -149,7 +148,7 @@ __global__ void __launch_bounds__(kLookThreads, sizeof(T) == 4 ? 4 : 3) k_lookah
         const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(gdst) & 15);
         // the tile sits in shared memory at the same offset modulo 16 as its destination: both sides of the copy 16-byte aligned
         T *tile = reinterpret_cast<T *>(smem_raw + lay.tile + (size_t)(c & 1) * lay.tile_stride + mis);
-        double *dist = dist_all + (size_t)(c & 1) * a.chunk * N;
+        double *dist = dist_all + (size_t)k0 * N;
 
         // ---- a thread per (action, human) ----
         if (own && k_own < na) do_pair(mine, pa[k0 + k_own], dist + threadIdx.x, tile + (size_t)threadIdx.x * OW);
@@ -195,29 +194,30 @@ __global__ void __launch_bounds__(kLookThreads, sizeof(T) == 4 ? 4 : 3) k_lookah
             __syncthreads();  // single-phase fallback: the tile is reused two iterations later, the dist buffer too
         }
 
-        // ---- rewards of this tile (cadrl.py:56-72) by the lanes of one warp (a different one per tile); `break` in the reference
-        //      only cuts the loop short: collision = some swept distance < 0, else dmin = the smallest one ----
-        if (warp == c % nwarps) {
-            for (int k = lane; k < na; k += 32) {
-                bool collision = false;
-                double dmin = 9223372036854775807.0;  // np.iinfo(np.int64).max
+    }
+
+    // ---- rewards (cadrl.py:56-72), once per CTA: a thread per action over the swept distances of all its humans.  (Doing this per
+    //      tile made one warp late for every tile barrier: barrier stalls were the top stall reason of the first version.)  `break` in
+    //      the reference only cuts its loop short: collision = some swept distance < 0, else dmin = the smallest one ----
+    __syncthreads();
+    for (int k = threadIdx.x; k < acnt; k += blockDim.x) {
+        bool collision = false;
+        double dmin = 9223372036854775807.0;  // np.iinfo(np.int64).max
 #pragma unroll 5
-                for (int j = 0; j < N; ++j) {
-                    const double d = dist[k * N + j];
-                    collision |= d < 0;
-                    dmin = (d >= 0 && d < dmin) ? d : dmin;
-                }
-                const PerAction<T> q = pa[k0 + k];
-                const double npx = __dadd_rn((double)rpx, __dmul_rn(q.axd, a.dt)), npy = __dadd_rn((double)rpy, __dmul_rn(q.ayd, a.dt));
-                const bool reached = xnorm_plain(__dsub_rn(npx, (double)rgx), __dsub_rn(npy, (double)rgy)) < (double)rr;
-                double rew;
-                if (collision) rew = -0.25;
-                else if (reached) rew = 1.0;
-                else if (dmin < 0.2) rew = __dmul_rn(__dmul_rn(__dsub_rn(dmin, 0.2), 0.5), a.dt);
-                else rew = 0.0;
-                a.rewards[(size_t)e * a.A + abeg + k0 + k] = rew;
-            }
+        for (int j = 0; j < N; ++j) {
+            const double d = dist_all[k * N + j];
+            collision |= d < 0;
+            dmin = (d >= 0 && d < dmin) ? d : dmin;
         }
+        const PerAction<T> q = pa[k];
+        const double npx = __dadd_rn((double)rpx, __dmul_rn(q.axd, a.dt)), npy = __dadd_rn((double)rpy, __dmul_rn(q.ayd, a.dt));
+        const bool reached = xnorm_plain(__dsub_rn(npx, (double)rgx), __dsub_rn(npy, (double)rgy)) < (double)rr;
+        double rew;
+        if (collision) rew = -0.25;
+        else if (reached) rew = 1.0;
+        else if (dmin < 0.2) rew = __dmul_rn(__dmul_rn(__dsub_rn(dmin, 0.2), 0.5), a.dt);
+        else rew = 0.0;
+        a.rewards[(size_t)e * a.A + abeg + k] = rew;
     }
     if (a.bulk && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // tiles must outlive the copies' reads
 }
@@ -233,9 +233,12 @@ template <typename T> int launch_lookahead(LookArgs a, cudaStream_t st) {
     const int sms = device_sm_count();
     int splits = 1;
     while (splits < a.A && (long long)a.E * splits < 8LL * 3 * sms) ++splits;
-    a.aper = (a.A + splits - 1) / splits;
-    const int tiles = (a.aper + per - 1) / per;
-    a.chunk = (a.aper + tiles - 1) / tiles;
+    for (;; ++splits) {  // ... and until the CTA's swept distances (aper x N doubles) and tiles fit in shared memory
+        a.aper = (a.A + splits - 1) / splits;
+        const int tiles = (a.aper + per - 1) / per;
+        a.chunk = (a.aper + tiles - 1) / tiles;
+        if (LookSmem<T>(N, OW, a.chunk, a.aper).total <= 200 * 1024 || a.aper == 1) break;
+    }
     const LookSmem<T> lay(N, OW, a.chunk, a.aper);
     if (lay.total > 200 * 1024) { set_error("snp_lookahead: %d humans x %d values do not fit a shared-memory tile", N, OW); return SNP_ERR_UNSUPPORTED; }
     auto kern = k_lookahead<T>;
