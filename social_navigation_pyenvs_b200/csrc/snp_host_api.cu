@@ -41,7 +41,13 @@ struct Workspace {
         return SNP_OK;
     }
 };
-Workspace g_ws;
+// one workspace per device: buffers and the stream belong to the device that was current when they were created
+Workspace g_ws_per_device[64];
+Workspace &current_workspace() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return g_ws_per_device[(dev >= 0 && dev < 64) ? dev : 0];
+}
 
 // out[c*rows + r] = in[r*cols + c]
 template <typename T> __global__ void k_aos_to_soa(const double *__restrict__ in, long long rows, int cols, T *__restrict__ out) {
@@ -67,7 +73,7 @@ template <typename T>
 int update_host(int type, int E, int N, int G, double *agents_state, double *goals, const double *obstacles, int W, int S,
                 const double *agents_params, double dt, const double *safety_space, int all_params_equal, int last_is_robot,
                 int numba_compat, int n_substeps, double *desired_force, double *out_state) {
-    Workspace &ws = g_ws;
+    Workspace &ws = current_workspace();
     std::lock_guard<std::mutex> lock(ws.mu);
     int rc = ws.init();
     if (rc) return rc;
@@ -183,7 +189,7 @@ int update_host(int type, int E, int N, int G, double *agents_state, double *goa
 template <typename T>
 int laser_host(int E, int N, const double *humans, const double *walls, int W, int S, const double *pose, double range, int samples,
                double max_distance, double robot_radius, double *ranges, int32_t *hits) {
-    Workspace &ws = g_ws;
+    Workspace &ws = current_workspace();
     std::lock_guard<std::mutex> lock(ws.mu);
     int rc = ws.init();
     if (rc) return rc;
