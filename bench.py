@@ -32,6 +32,8 @@ WORKLOADS = {
     "4096x25_hsfm_ccso_walls_robot": ("hsfm_farina", 4096, 25, True, True),
     "4096x25_hsfm_ccso_robot": ("hsfm_farina", 4096, 25, False, True),
     "4096x5_sfm_helbing_cc": ("sfm_helbing", 4096, 5, False, False),
+    # the same crowd at a batch size that fills the GPU's warp slots (4096 x 5 occupies 683 of 2368 resident warps: latency-bound)
+    "32768x5_sfm_helbing_cc": ("sfm_helbing", 32768, 5, False, False),
     # BASELINE configs[4]: ONE crowd of 65536 humans, sharded by agent across the GPUs (strong scaling, all-gather per sub-step)
     "65536_hsfm_single_crowd": ("hsfm_farina", 1, 65536, False, False),
     # BASELINE configs[3]: 4096 envs x 360-ray laser over 25 humans + 14 wall segments (metric: rays/s)
