@@ -2,7 +2,7 @@
 // desired / torque / Euler epilogue as the small-crowd kernel.  One sub-step = three launches on one stream:
 //
 //   k_tile_boxes   bounding box (+ max r+safety) of every 128-entity tile of the `others` view  [5][M] = x, y, vx, vy, r+s
-//   k_large_pairs  grid (i-blocks of 256 agents, j-chunks of 4096 entities): every agent accumulates the force of the
+//   k_large_pairs  grid (i-blocks of 256 agents, j-chunks of 512 entities): every agent accumulates the force of the
 //                  chunk's entities in ascending j from shared-memory tiles and writes ONE partial sum per chunk.
 //                  A tile is skipped when its box is farther from the i-block's box than the distance at which the pair
 //                  law is identically zero in the arithmetic in use (exp underflow: r_i+s_i+r_j+s_j + 700 B in fp64,
@@ -11,7 +11,11 @@
 //                  crowd is sharded over GPUs), goal switch, wall force, desired force, torque, Euler; writes the state in
 //                  place and the agent's entry of the NEXT entity view (what the other ranks all-gather).
 //
-// The chunking gives (N/256) x (M/4096) CTAs -- 4096 at 65536 humans on one GPU, 512 per GPU at 8 GPUs -- instead of N/256.
+// The chunking gives (N/256) x (M/512) CTAs -- 32768 at 65536 humans on one GPU, 4096 per GPU at 8 GPUs -- instead of N/256.  Small
+// chunks matter once culling is on: the CTAs of far chunks exit at once and only the near ones work, so with 4096-entity chunks a
+// quarter of 4096 CTAs ran long serial loops at low occupancy (measured: 2.6 ms per sub-step and no gain from a second GPU; with
+// 512-entity chunks 2.0 ms on one GPU, 1.1 ms on two).  The price is J = M/512 partial sums per agent (134 MB written and read
+// per sub-step at 65536 humans in fp64, ~45 us of HBM time).
 // Reference: same as snp_step_small.cu (motion_model_manager.py:354-373,424-459; forces.py:63-151).
 #include "snp_kernels.cuh"
 
@@ -20,7 +24,10 @@ namespace {
 
 constexpr int kTile = 128;           // entities per shared-memory tile == threads per block
 constexpr int kAgentsPerThread = 2;  // register tiling: every staged entity is used for two agents
-constexpr int kChunk = 4096;         // entities per j-chunk (one partial sum each); fixed so results are sharding-independent
+#ifndef SNP_LARGE_CHUNK
+#define SNP_LARGE_CHUNK 512
+#endif
+constexpr int kChunk = SNP_LARGE_CHUNK;  // entities per j-chunk (one partial sum each); fixed so results are sharding-independent
 
 template <typename T> struct LargeArgs {
     KArgs<T> k;
