@@ -26,8 +26,8 @@ if cb:
     c = cb[0]["cpu_baseline"]
     out.append(f"\ncpu_baseline of the default workload: {c['value']:.3e} {c['unit']} on {c['cores']} host threads ({c['kind']}).\n")
 out.append("Scaling (env-sharded, no data-path collective; fp64 default workload, earlier boxes of this round): 1 GPU 7.6e9, 2 GPUs 1.46e10, 4 GPUs 3.01e10 "
-           "agent-steps/s;\n65 536-human crowd sharded by agent with peer (NVLink) stores fused into the producer kernel: 3.3e7 (1 GPU), 5.8e7 (2 GPUs) fp64 with 512-entity chunks\n(4096-entity chunks, earlier in the round: 2.4e7, 2.8e7, 4.2e7 on 1, 2, 4 GPUs) -- "
-           "`tools/multi_gpu_check.py` OK on 2 and 4 ranks.\n")
+           "agent-steps/s;\n65 536-human crowd sharded by agent with peer (NVLink) stores fused into the producer kernel: 3.3e7 (1 GPU), 5.8e7 (2), 1.04e8 (4) fp64 with 512-entity chunks; every ordered pair evaluated: 8.5 / 4.3 / 2.2 ms per sub-step\n(4096-entity chunks, earlier in the round: 2.4e7, 2.8e7, 4.2e7 on 1, 2, 4 GPUs) -- "
+           "`tools/multi_gpu_check.py` (sharded == single GPU, bit for bit) OK on 2 and 4 ranks.\n")
 out += ["## Issue-port model (`issue_model.json`, `r01_pipe_microbench.txt`)\n",
         "An FP64 instruction holds its SMSP's issue port for 2 cycles and nothing issues in its shadow (8 DFMA + 8 FFMA take the sum of their\n"
         "issue times), so `cycles >= 2 N_fp64 + N_other` per SMSP.  Per launch, from the per-SASS-instruction execution counts:\n",
