@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
     __shared__ T sbox[20];
     Ent<T> *tile = reinterpret_cast<Ent<T> *>(tile_raw);
     const KArgs<T> &a = la.k;
-    if (sizeof(T) == 8) exp_table_init(exp_tbl_s);
+    bool have_tbl = false;  // the 16 kB exp table is staged only by CTAs that evaluate at least one tile (most are culled)
 
     const long long N = a.EN, M = la.M;
     const Params<T> &P = a.P;
@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
             const T reach = ibox[4] + b[4] + la.cull_margin;
             if (fma_<T>(gx, gx, gy * gy) > reach * reach) continue;
         }
+        if (sizeof(T) == 8 && !have_tbl) { exp_table_init(exp_tbl_s); have_tbl = true; }
         __syncthreads();
         const long long j = j0 + threadIdx.x;
         if (j < j_end) {
@@ -129,18 +130,52 @@ __global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
             const Ent<T> o = tile[t];
             const T rsj = tile_rs[t];
             const long long jj = j0 + t - la.self_offset;  // index of the entity in this crowd's numbering
+            // the self pair (jj == idx[q]) contributes exactly zero by construction (tiny_ in pair_eval)
+            if constexpr (sizeof(T) == 4) {
+                // the evaluations of the thread's agents are independent and branch-free; ONE vote covers the rare contact
+                // re-evaluation of all of them
+                T fx[kAgentsPerThread], fy[kAgentsPerThread];
+                bool contact = false;
 #pragma unroll
-            for (int q = 0; q < kAgentsPerThread; ++q) {
-                T fx, fy;  // the self pair (jj == idx[q]) contributes exactly zero by construction (tiny_ in pair_force)
-                if (SOC == 2) {
-                    const bool sw = sym && jj < idx[q];
-                    pair_force<T, SOC>(P, exp_tbl_s, 0xffffffffu, sw ? o.x : mx[q], sw ? o.y : my[q], sw ? o.vx : mvx[q], sw ? o.vy : mvy[q], sw ? rsj : mrs[q],
-                                       sw ? mx[q] : o.x, sw ? my[q] : o.y, sw ? mvx[q] : o.vx, sw ? mvy[q] : o.vy, sw ? mrs[q] : rsj, fx, fy);
-                    fx = sw ? -fx : fx; fy = sw ? -fy : fy;
-                } else {
-                    pair_force<T, SOC>(P, exp_tbl_s, 0xffffffffu, mx[q], my[q], mvx[q], mvy[q], mrs[q], o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+                for (int q = 0; q < kAgentsPerThread; ++q) {
+                    const bool sw = SOC == 2 && sym && jj < idx[q];
+                    if (SOC == 2) {
+                        contact |= pair_eval<T, SOC, false>(P, exp_tbl_s, sw ? o.x : mx[q], sw ? o.y : my[q], sw ? o.vx : mvx[q], sw ? o.vy : mvy[q], sw ? rsj : mrs[q],
+                                                            sw ? mx[q] : o.x, sw ? my[q] : o.y, sw ? mvx[q] : o.vx, sw ? mvy[q] : o.vy, sw ? mrs[q] : rsj, fx[q], fy[q]) > T(0);
+                        fx[q] = sw ? -fx[q] : fx[q]; fy[q] = sw ? -fy[q] : fy[q];
+                    } else {
+                        contact |= pair_eval<T, SOC, false>(P, exp_tbl_s, mx[q], my[q], mvx[q], mvy[q], mrs[q], o.x, o.y, o.vx, o.vy, rsj, fx[q], fy[q]) > T(0);
+                    }
                 }
-                fsx[q] += fx; fsy[q] += fy;
+                if (__any_sync(0xffffffffu, contact)) {
+#pragma unroll
+                    for (int q = 0; q < kAgentsPerThread; ++q) {
+                        const bool sw = SOC == 2 && sym && jj < idx[q];
+                        if (SOC == 2) {
+                            pair_eval<T, SOC, true>(P, exp_tbl_s, sw ? o.x : mx[q], sw ? o.y : my[q], sw ? o.vx : mvx[q], sw ? o.vy : mvy[q], sw ? rsj : mrs[q],
+                                                    sw ? mx[q] : o.x, sw ? my[q] : o.y, sw ? mvx[q] : o.vx, sw ? mvy[q] : o.vy, sw ? mrs[q] : rsj, fx[q], fy[q]);
+                            fx[q] = sw ? -fx[q] : fx[q]; fy[q] = sw ? -fy[q] : fy[q];
+                        } else {
+                            pair_eval<T, SOC, true>(P, exp_tbl_s, mx[q], my[q], mvx[q], mvy[q], mrs[q], o.x, o.y, o.vx, o.vy, rsj, fx[q], fy[q]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kAgentsPerThread; ++q) { fsx[q] += fx[q]; fsy[q] += fy[q]; }
+            } else {  // fp64: one evaluation at a time (the grouped form costs registers the 80-register budget does not have)
+#pragma unroll
+                for (int q = 0; q < kAgentsPerThread; ++q) {
+                    T fx, fy;
+                    if (SOC == 2) {
+                        const bool sw = sym && jj < idx[q];
+                        pair_force<T, SOC>(P, exp_tbl_s, 0xffffffffu, sw ? o.x : mx[q], sw ? o.y : my[q], sw ? o.vx : mvx[q], sw ? o.vy : mvy[q], sw ? rsj : mrs[q],
+                                           sw ? mx[q] : o.x, sw ? my[q] : o.y, sw ? mvx[q] : o.vx, sw ? mvy[q] : o.vy, sw ? mrs[q] : rsj, fx, fy);
+                        fx = sw ? -fx : fx; fy = sw ? -fy : fy;
+                    } else {
+                        pair_force<T, SOC>(P, exp_tbl_s, 0xffffffffu, mx[q], my[q], mvx[q], mvy[q], mrs[q], o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+                    }
+                    fsx[q] += fx; fsy[q] += fy;
+                }
             }
         }
     }
