@@ -14,6 +14,7 @@ Multi-GPU (torchrun): every rank steps its own 4096 envs (no data-path collectiv
 import argparse
 import json
 import os
+import tempfile
 import statistics
 import subprocess
 import sys
@@ -46,7 +47,8 @@ WORKLOADS = {
 def build_inputs(workload, seed0):
     from social_navigation_pyenvs_b200 import scenarios
     model, E, N, with_walls, robot_visible = WORKLOADS[workload]
-    cache = os.path.join(ROOT, "gpurun_out", f"scenario_{workload}_{seed0}.npz")
+    # per-box scratch (several ranks / several bench runs on one box share it); NOT under gpurun_out/, whose size is capped
+    cache = os.path.join(tempfile.gettempdir(), "snp_b200_scenarios", f"scenario_{workload}_{seed0}.npz")
     if os.path.exists(cache):
         z = np.load(cache)
         sc = dict(states=z["states"], goals=z["goals"], robot=z["robot"])
@@ -54,7 +56,9 @@ def build_inputs(workload, seed0):
         sc = scenarios.ccso_synthetic(E, N, seed0) if "ccso" in workload else scenarios.circular_crossing(E, N, seed0)
         try:
             os.makedirs(os.path.dirname(cache), exist_ok=True)
-            np.savez(cache, **sc)
+            tmp = f"{cache}.{os.getpid()}.npz"   # ranks of one job race for the same file: write aside, publish atomically
+            np.savez(tmp, **sc)
+            os.replace(tmp, cache)
         except OSError:
             pass
     walls = scenarios.pack_walls(scenarios.EXAMPLE_WALLS) if with_walls else None
