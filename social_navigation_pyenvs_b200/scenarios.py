@@ -258,6 +258,23 @@ def hybrid_choice(seed):
     return int.from_bytes(np.random.RandomState(int(seed)).bytes(4), "little") & 1
 
 
+def spatial_order(positions, block=256):
+    """Permutation that numbers the agents of ONE large crowd patch by patch: the crowd is cut into sqrt(n / block) vertical
+    strips of equal head count (sorted by x) and every strip is walked in y, so that a run of consecutive agents (a 128-entity
+    tile, a 256-agent block of the tiled all-pairs kernels) covers a compact patch of the plane instead of a long strip.  The
+    exact far-tile culling of snp_large_step tests bounding boxes of such runs and skips ~2x more of them.  The numbering of
+    the agents is the caller's (the reference keeps humans in insertion order, social_nav_sim.py:271-295, and no force depends
+    on it), so this is applied to the rows BEFORE they are handed to LargeCrowd; `np.argsort(perm)` undoes it."""
+    pos = np.asarray(positions, np.float64).reshape(-1, 2)
+    n = len(pos)
+    strips = max(1, int(round(math.sqrt(n / float(block)))))
+    by_x = np.argsort(pos[:, 0], kind="stable")
+    out = []
+    for s in np.array_split(by_x, strips):
+        out.append(s[np.argsort(pos[s, 1], kind="stable")])
+    return np.concatenate(out) if out else by_x
+
+
 def jittered_grid_crowd(n_side, pitch=2.0, jitter=0.5, seed=0, mass=75.0):
     """n_side x n_side jittered grid, every goal mirrored through the crowd centre (G = 2)."""
     rs = np.random.RandomState(seed)

@@ -159,15 +159,21 @@ def test_large_crowd_tiled_kernel_vs_oracle():
         assert rel_err(got[:, :8], ref[0, :, :8]).max() < tol, model
 
 
+@pytest.mark.parametrize("order", ["row_major", "patch"])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_large_crowd_chunked_sums_and_exact_culling(dtype):
+def test_large_crowd_chunked_sums_and_exact_culling(dtype, order):
     """5184 humans (two j-chunks, 41 tiles, a 72 m wide crowd): the chunked partial sums stay within 1e-9 of the oracle's single
-    j-ascending sum, and skipping tiles beyond the exp-underflow distance changes NOTHING (bit-identical on/off)."""
+    j-ascending sum, and skipping tiles beyond the exp-underflow distance changes NOTHING (bit-identical on/off) -- with the
+    humans numbered row by row (long thin tiles) or patch by patch (scenarios.spatial_order: compact tiles, more of them culled)."""
     from social_navigation_pyenvs_b200 import scenarios
     from social_navigation_pyenvs_b200.large import LargeCrowd
     sc = scenarios.jittered_grid_crowd(72, pitch=1.0, jitter=0.3, seed=3)
     S, G = sc["states"], sc["goals"]
     n = S.shape[1]
+    if order == "patch":
+        perm = scenarios.spatial_order(S[0, :, 0:2])
+        assert np.array_equal(np.sort(perm), np.arange(n))
+        S, G = np.ascontiguousarray(S[:, perm]), np.ascontiguousarray(G[:, perm])
     rng = np.random.RandomState(1)
     S[0, :, 5:7] = rng.uniform(-0.6, 0.6, (n, 2))
     if dtype == torch.float32:
