@@ -38,6 +38,7 @@ template <typename T> struct LargeArgs {
     int n_peers;
     T *partial;   // [J][2][N_local]
     T *boxes;     // [n_tiles][5] xmin, xmax, ymin, ymax, max(r+s)
+    unsigned char *live;  // [i-blocks][J]: 1 when the (i-block, chunk) CTA evaluated at least one tile and wrote its partial sums
     int J, n_tiles;
     T cull_margin;  // distance beyond r+s sums at which the pair law is exactly zero; < 0 disables culling
 };
@@ -88,6 +89,35 @@ __global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
 
     const long long N = a.EN, M = la.M;
     const Params<T> &P = a.P;
+    const long long j_begin = (long long)blockIdx.y * kChunk;
+    const long long j_end = min(M, j_begin + kChunk);
+    unsigned char *live_flag = la.live + (size_t)blockIdx.x * la.J + blockIdx.y;
+    if (la.cull_margin >= T(0) && la.self_offset % kTile == 0) {
+        // Most CTAs of a wide crowd are far from their chunk: decide that from the tile boxes alone -- the i-block's agents are
+        // the entities of kAgentsPerThread consecutive tiles, whose union box contains them -- before any state is loaded or
+        // any barrier is reached.  A culled CTA leaves its partial sums unwritten and says so in `live`.
+        const long long t0 = (la.self_offset + (long long)blockIdx.x * kAgentsPerThread * kTile) / kTile;
+        const T inf = Real<T>::inf();
+        T u0 = inf, u1 = -inf, u2 = inf, u3 = -inf, u4 = T(0);
+#pragma unroll
+        for (int q = 0; q < kAgentsPerThread; ++q)
+            if (t0 + q < la.n_tiles) {
+                const T *b = la.boxes + (size_t)(t0 + q) * 5;
+                u0 = min(u0, b[0]); u1 = max(u1, b[1]); u2 = min(u2, b[2]); u3 = max(u3, b[3]); u4 = max(u4, b[4]);
+            }
+        bool near = false;
+        for (long long j0 = j_begin; j0 < j_end; j0 += kTile) {
+            const T *b = la.boxes + (size_t)(j0 / kTile) * 5;
+            const T gx = max(T(0), max(u0 - b[1], b[0] - u1));
+            const T gy = max(T(0), max(u2 - b[3], b[2] - u3));
+            const T reach = u4 + b[4] + la.cull_margin;
+            near |= !(fma_<T>(gx, gx, gy * gy) > reach * reach);
+        }
+        if (!near) {  // uniform across the CTA
+            if (threadIdx.x == 0) *live_flag = 0;
+            return;
+        }
+    }
     T mx[kAgentsPerThread], my[kAgentsPerThread], mvx[kAgentsPerThread], mvy[kAgentsPerThread], mrs[kAgentsPerThread];
     long long idx[kAgentsPerThread];
     T fsx[kAgentsPerThread], fsy[kAgentsPerThread];
@@ -106,8 +136,7 @@ __global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
     block_box<T>(bx0, bx1, by0, by1, brs, sbox, ibox);
 
     const bool sym = a.symmetric != 0;
-    const long long j_begin = (long long)blockIdx.y * kChunk;
-    const long long j_end = min(M, j_begin + kChunk);
+    bool any_tile = false;
     for (long long j0 = j_begin; j0 < j_end; j0 += kTile) {
         if (la.cull_margin >= T(0)) {  // uniform across the CTA
             const T *b = la.boxes + (size_t)(j0 / kTile) * 5;
@@ -117,6 +146,7 @@ __global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
             if (fma_<T>(gx, gx, gy * gy) > reach * reach) continue;
         }
         if (sizeof(T) == 8 && !have_tbl) { exp_table_init(exp_tbl_s); have_tbl = true; }
+        any_tile = true;
         __syncthreads();
         const long long j = j0 + threadIdx.x;
         if (j < j_end) {
@@ -179,6 +209,8 @@ __global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
             }
         }
     }
+    if (threadIdx.x == 0) *live_flag = any_tile ? 1 : 0;
+    if (!any_tile) return;  // every tile was culled: the chunk contributes exactly zero and the finish kernel skips it
 #pragma unroll
     for (int q = 0; q < kAgentsPerThread; ++q)
         if (idx[q] < N) {
@@ -232,7 +264,9 @@ __global__ void __launch_bounds__(kTile) k_large_finish(const LargeArgs<T> la) {
     const int gcnt = a.goal_cnt[i];
     m.gx = a.goals[((size_t)gidx * 2 + 0) * N + i]; m.gy = a.goals[((size_t)gidx * 2 + 1) * N + i];
     T fsx = T(0), fsy = T(0);
-    for (int p = 0; p < la.J; ++p) { fsx += la.partial[((size_t)p * 2 + 0) * N + i]; fsy += la.partial[((size_t)p * 2 + 1) * N + i]; }
+    const unsigned char *lv = la.live + (size_t)(i / (kTile * kAgentsPerThread)) * la.J;  // the same flags for the whole CTA
+    for (int p = 0; p < la.J; ++p)
+        if (lv[p]) { fsx += la.partial[((size_t)p * 2 + 0) * N + i]; fsy += la.partial[((size_t)p * 2 + 1) * N + i]; }
 
     const T dg = np_norm(m.gx - m.px, m.gy - m.py);
     if (a.numba ? (dg <= m.r) : (dg < m.r)) {
@@ -302,6 +336,7 @@ template <typename T, int SOC, int OBS, int HEADED> int launch_large(const Large
 
 inline long long large_J(long long M) { return (M + kChunk - 1) / kChunk; }
 inline long long large_tiles(long long M) { return (M + kTile - 1) / kTile; }
+inline long long large_iblocks(long long N) { return (N + (long long)kTile * kAgentsPerThread - 1) / ((long long)kTile * kAgentsPerThread); }
 
 template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, const void *others, long long M, long long self_offset,
                                     void *next_view, const void *const *peer_views, int n_peers, void *scratch, long long scratch_bytes,
@@ -319,10 +354,11 @@ template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, 
     a.time_now = nullptr; a.flags = nullptr; a.checks = nullptr; a.epw = 1; a.gpb = 1; a.mapping = 0; a.full_pair_loop = 1; a.respawn = 0; a.robot_type = 0; a.RP = a.P;
     la.others = (const T *)others; la.M = M; la.self_offset = self_offset; la.next_view = (T *)next_view;
     la.J = (int)large_J(M); la.n_tiles = (int)large_tiles(M);
-    const long long need = (long long)sizeof(T) * ((long long)la.J * 2 * a.EN + (long long)la.n_tiles * 5);
+    const long long need = (long long)sizeof(T) * ((long long)la.J * 2 * a.EN + (long long)la.n_tiles * 5) + large_iblocks(a.EN) * la.J;
     if (!scratch || scratch_bytes < need) { set_error("snp_large_step: scratch of %lld bytes needed, %lld given", need, scratch_bytes); return SNP_ERR_INVALID; }
     la.partial = (T *)scratch;
     la.boxes = la.partial + (size_t)la.J * 2 * a.EN;
+    la.live = reinterpret_cast<unsigned char *>(la.boxes + (size_t)la.n_tiles * 5);
     // exact culling distance beyond the r+s sums: where exp(rd/B) is identically zero in the arithmetic in use
     const int soc = o->type % 3;
     const double under = sizeof(T) == 8 ? 700.0 : 88.0;
@@ -356,7 +392,7 @@ extern "C" {
 
 int64_t snp_large_scratch_bytes(int64_t n_local, int64_t M, int32_t dtype) {
     const long long w = dtype == SNP_F64 ? 8 : 4;
-    return w * (large_J(M) * 2 * n_local + large_tiles(M) * 5) + 64;
+    return w * (large_J(M) * 2 * n_local + large_tiles(M) * 5) + large_iblocks(n_local) * large_J(M) + 64;
 }
 
 int snp_large_step(const snp_crowd *c, const snp_step_opts *o, const void *others, int64_t M, int64_t self_offset, void *next_view,
