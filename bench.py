@@ -100,11 +100,13 @@ class ClockSampler:
             h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
 
+            period = float(os.environ.get("SNP_CLOCK_POLL_MS", "4")) * 1e-3
+
             def poll():
                 while not self.stop:
                     self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                     self.bits |= pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                    time.sleep(0.004)
+                    time.sleep(period)
             self.thread = threading.Thread(target=poll, daemon=True)
             self.thread.start()
         except Exception:
