@@ -116,3 +116,25 @@ def test_reset_core_replays_numpy_stream_and_reference_generators(tmp_path):
     sc = scenarios.ccso_synthetic(3, 25, seed0=2000)
     for e, (_, _, rows) in enumerate(run(3, 25, False, 2000, 3)):
         assert np.array_equal(rows[:, :2], sc["states"][e, :, 0:2]) and np.array_equal(rows[:, 3], sc["states"][e, :, 8])
+
+
+def test_spatial_order_is_a_permutation_with_compact_runs():
+    """scenarios.spatial_order: every human exactly once, and runs of 256 consecutive humans of the 65536-human benchmark crowd
+    cover a ~31 m x 31 m patch (row-by-row numbering: a 510 m x 1 m strip) -- what the exact far-tile culling feeds on.  Also on
+    a non-uniform crowd and on sizes that do not divide evenly."""
+    sc = scenarios.jittered_grid_crowd(256, pitch=2.0, jitter=0.5, seed=0)
+    pos = sc["states"][0, :, 0:2]
+    perm = scenarios.spatial_order(pos)
+    assert np.array_equal(np.sort(perm), np.arange(len(pos)))
+    runs = pos[perm].reshape(-1, 256, 2)
+    ext = runs.max(1) - runs.min(1)
+    assert ext.max() < 32.0
+    rows = pos.reshape(-1, 256, 2)
+    assert (rows.max(1) - rows.min(1))[:, 1].min() > 500.0
+    inv = np.argsort(perm)
+    assert np.array_equal(pos[perm][inv], pos)
+    rng = np.random.RandomState(0)
+    for n in (1, 7, 513, 5000):
+        p = rng.normal(0.0, 30.0, (n, 2)) ** 3 / 900.0   # heavy-tailed, clustered near the origin
+        q = scenarios.spatial_order(p)
+        assert np.array_equal(np.sort(q), np.arange(n))
