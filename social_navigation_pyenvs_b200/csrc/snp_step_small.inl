@@ -34,7 +34,10 @@ namespace {
 #endif
 
 constexpr int kPairUnroll = SNP_PAIR_UNROLL;
-constexpr int kWarpsPerBlock = 4;
+#ifndef SNP_WPB
+#define SNP_WPB 4
+#endif
+constexpr int kWarpsPerBlock = SNP_WPB;  // warp-packed mapping: warps (= independent env groups) per CTA
 constexpr int kRobotParamWords = 24;  // Params<T> of the robot staged in shared memory (21 values, padded)
 constexpr int kSlotsPerWarp = 64;  // >= epw * (N + 1) for every N <= 32
 
