@@ -25,8 +25,10 @@ cb = [d for d in lines if d.get("cpu_baseline") and d.get("impl") != "reference"
 if cb:
     c = cb[0]["cpu_baseline"]
     out.append(f"\ncpu_baseline of the default workload: {c['value']:.3e} {c['unit']} on {c['cores']} host threads ({c['kind']}).\n")
-out.append("Scaling (env-sharded, no data-path collective; fp64 default workload, earlier boxes of this round): 1 GPU 7.6e9, 2 GPUs 1.46e10, 4 GPUs 3.01e10 "
-           "agent-steps/s;\n65 536-human crowd sharded by agent with peer (NVLink) stores fused into the producer kernel: 3.3e7 (1 GPU), 5.8e7 (2), 1.04e8 (4) fp64 with 512-entity chunks; every ordered pair evaluated: 8.5 / 4.3 / 2.2 ms per sub-step\n(4096-entity chunks, earlier in the round: 2.4e7, 2.8e7, 4.2e7 on 1, 2, 4 GPUs) -- "
+out.append("Scaling (`r01_scale_lines.jsonl`; env-sharded, no data-path collective; fp64 default workload): 1 GPU 7.7e9, 2 GPUs 1.53e10, 4 GPUs 3.01e10, "
+           "8 GPUs 6.11e10 agent-steps/s;\n65 536-human crowd sharded by agent with peer (NVLink) stores fused into the producer kernel, humans numbered patch by patch "
+           "(`scenarios.spatial_order`), fp64: 7.7e7 (1 GPU), 1.28e8 (2), 1.72e8 (8) agent-steps/s = 0.85 / 0.51 / 0.38 ms per sub-step; every ordered pair evaluated: "
+           "8.5 / 4.3 / 1.16 ms\n(row-by-row numbering, earlier in the round: 3.3e7, 5.8e7, 1.04e8 on 1, 2, 4 GPUs) -- "
            "`tools/multi_gpu_check.py` (sharded == single GPU, bit for bit) OK on 2 and 4 ranks.\n")
 out += ["## Issue-port model (`issue_model.json`, `r01_pipe_microbench.txt`)\n",
         "An FP64 instruction holds its SMSP's issue port for 2 cycles and nothing issues in its shadow (8 DFMA + 8 FFMA take the sum of their\n"
