@@ -188,7 +188,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "substeps_per_step": SUBSTEPS, "dt": DT, "sample": sample},
+            "config": {"workload": args.workload, "envs_per_gpu": inp["E"], "humans": inp["N"], "motion_model": inp["model"],
+                       "substeps_per_step": SUBSTEPS, "dt": DT, "walls": 0 if inp["walls"] is None else int(inp["walls"].shape[0]),
+                       "robot_visible": inp["robot_visible"], "sample": sample},
             "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -268,7 +270,7 @@ def run_large_crowd(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": n * steps / (total_ms * 1e-3), "unit": "agent-steps/s", "n_gpus": world, "steps": steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": args.workload, "humans": n, "model": "hsfm_farina", "substeps_per_step": 1, "dt": DT,
+                "config": {"workload": args.workload, "humans": n, "motion_model": "hsfm_farina", "substeps_per_step": 1, "dt": DT,
                            "sharding": f"by agent over {world} GPU(s); entity view [5,N] exchanged per sub-step via " +
                                        ("peer (NVLink) stores fused into the producer kernel + barrier" if crowd.exchange == "p2p" else "NCCL all-gather"),
                            "culling": "exact far-tile culling on for `value` (tiles beyond the exp-underflow distance contribute exactly 0); "
@@ -622,7 +624,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": args.workload, "envs_per_gpu": E, "humans": N, "model": inp["model"], "substeps_per_step": SUBSTEPS,
+            "config": {"workload": args.workload, "envs_per_gpu": E, "humans": N, "motion_model": inp["model"], "substeps_per_step": SUBSTEPS,
                        "dt": DT, "walls": 0 if inp["walls"] is None else int(inp["walls"].shape[0]), "robot_visible": inp["robot_visible"],
                        "checks": "swept collision/goal/reward + per-sub-step touch", "l2": "256 MiB flush write between timed steps",
                        "timing": "sum of per-step CUDA-event pairs on the launch stream, max over ranks"},
