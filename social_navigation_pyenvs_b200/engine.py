@@ -297,6 +297,18 @@ class CrowdEngine:
         L.check(self.lib.snp_checks(ctypes.byref(self._crowd()), ctypes.byref(o), _stream()))
         return self.decode_flags()
 
+    def collision_detection_and_reaching_goal(self, action, time_step=None):
+        """SocialNavSim.collision_detection_and_reaching_goal(action, time_step) (social_nav_sim.py:949-984) for every env at once:
+        (collision, dmin, reaching_goal) of the swept test over one robot step with `action` [E,2]; humans keep their last velocity."""
+        keep = self.consts[5]
+        if time_step is not None:
+            self.consts[5] = float(time_step)
+        try:
+            r = self.run_checks(action, pre=True, post=False)
+        finally:
+            self.consts[5] = keep
+        return r["collision"], r["dmin"], r["reaching_goal"]
+
     def decode_flags(self):
         f = self.flags.cpu().numpy()
         c = self.checks.cpu().numpy()

@@ -43,6 +43,9 @@ def test_flags_bit_exact_vs_reference_golden(dtype):
     assert np.array_equal(out["actual_collision"], ref[:, 7] != 0) and np.array_equal(out["actual_goal"], ref[:, 9] != 0)
     assert np.array_equal(out["dmin"], ref[:, 1]) and np.array_equal(out["reward"], ref[:, 3]) and np.array_equal(out["actual_dmin"], ref[:, 8])
     assert out["collision"].sum() > 50 and (out["info"] == 4).sum() > 20
+    # the same swept test under the reference's own name and return convention (sim:949)
+    col, dmin, goal = eng.collision_detection_and_reaching_goal(A, CONSTS[5])
+    assert np.array_equal(col, ref[:, 0] != 0) and np.array_equal(dmin, ref[:, 1]) and np.array_equal(goal, ref[:, 2] != 0)
 
 
 def test_gym_step_sequence_vs_reference_golden():
