@@ -70,6 +70,9 @@ def _load():
         _lib.orc_imitation_steps.argtypes = [ctypes.POINTER(_Cfg), ctypes.c_int, dp, dp, dp, dp, dp, dp, ctypes.c_double, ctypes.c_int, dp, dp,
                                              ctypes.c_int, dp, dp, ctypes.c_int, dp, ctypes.c_int]
         _lib.orc_imitation_steps.restype = None
+        _lib.orc_sim_update_steps.argtypes = [ctypes.POINTER(_Cfg), ctypes.c_int, dp, dp, dp, dp, dp, dp, ctypes.c_double, ctypes.c_int, dp, dp,
+                                              ctypes.c_int, dp, dp, ctypes.c_int, dp, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+        _lib.orc_sim_update_steps.restype = None
         _lib.orc_lookahead.argtypes = [ctypes.c_int] * 4 + [dp, dp, dp, dp, ctypes.c_double, dp, dp, ctypes.c_int]
         _lib.orc_lookahead.restype = None
         _lib.orc_robot_push_out.argtypes = [ctypes.c_int] * 4 + [dp, dp, dp]
@@ -147,6 +150,34 @@ def imitation_steps(cfg: OracleConfig, states, goals, walls, params, safety, des
     lib.orc_imitation_steps(ctypes.byref(c), E, _dp(states), _dp(goals), _dp(walls_c), _dp(params), _dp(safety), _dp(desired), float(dt),
                             int(n_steps), _dp(robot), _dp(robot_goals), robot_goals.shape[1], _dp(robot_desired), _dp(_c(robot_params)),
                             int(robot_type), _dp(rsaf), int(n_threads))
+    return states, goals, desired, robot, robot_goals, robot_desired
+
+
+def sim_update_steps(cfg: OracleConfig, states, goals, walls, params, safety, desired, dt, n_steps, robot, robot_goals, robot_desired,
+                     robot_params, robot_type, every, robot_dt, phase=0, robot_safety=None, n_threads=1):
+    """n_steps x SocialNavSim.update with a model-driven robot (social_nav_sim.py:476-529): pose advance every update, velocity
+    refresh (update_robot, just_velocities=True, dt = robot_dt) every `every` updates -- or a full update_robot(dt) when
+    every <= 1 -- and humans that see the robot's previous state.  Same arrays and return value as imitation_steps."""
+    lib = _load()
+    states, goals, desired = _c(states).copy(), _c(goals).copy(), _c(desired).copy()
+    robot, robot_goals, robot_desired = _c(robot).copy(), _c(robot_goals).copy(), _c(robot_desired).copy()
+    params, safety = _c(params), _c(safety)
+    E, rows, _ = states.shape
+    n = goals.shape[1]
+    assert rows == n + int(cfg.consider_robot)
+    if walls is None or np.size(walls) == 0 or walls.shape[-4] == 0:
+        W, S, per_env, walls_c = 0, 1, 0, np.zeros(4)
+    else:
+        walls_c = _c(walls)
+        per_env = int(walls_c.ndim == 5)
+        W, S = walls_c.shape[-4], walls_c.shape[-3]
+    rb = cfg.respawn_bounds
+    c = _Cfg(cfg.type, n, goals.shape[2], W, S, int(cfg.consider_robot), int(cfg.symmetric), int(cfg.numba_compat), per_env,
+             int(rb is not None), (ctypes.c_double * 2)(*(rb if rb is not None else (0.0, 0.0))))
+    rsaf = np.zeros(E) if robot_safety is None else _c(robot_safety)
+    lib.orc_sim_update_steps(ctypes.byref(c), E, _dp(states), _dp(goals), _dp(walls_c), _dp(params), _dp(safety), _dp(desired), ctypes.c_double(dt),
+                             int(n_steps), _dp(robot), _dp(robot_goals), robot_goals.shape[1], _dp(robot_desired), _dp(_c(robot_params)),
+                             int(robot_type), _dp(rsaf), int(every), ctypes.c_double(robot_dt), int(phase), int(n_threads))
     return states, goals, desired, robot, robot_goals, robot_desired
 
 

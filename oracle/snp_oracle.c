@@ -346,7 +346,7 @@ void orc_update_humans(const orc_cfg *c, int E, double *states, double *goals, c
  * rp: the robot's 20 parameters, rtype: its model (0..8), rs: its safety space.  Humans exert force on it through the
  * per-agent path compute_social_force_*(index = len(humans), ..., consider_robot = False) (mmm:608, forces.py:153-218). */
 static void update_robot_env(const orc_cfg *c, double *rb, double *rgoals, int rg, double *rdes, const double *rp, int rtype, double rs,
-                             const double *st, const double *safety, const double *walls, double dt, double *scratch) {
+                             const double *st, const double *safety, const double *walls, double dt, double *scratch, int just_velocities) {
     const int n = c->n, W = c->n_walls, fm = 1;
     const int soc = rtype % 3, obs = (rtype == 1 || rtype == 4 || rtype == 7) ? 1 : 0, headed = rtype / 3;
     double *cp = scratch;
@@ -379,7 +379,7 @@ static void update_robot_env(const orc_cfg *c, double *rb, double *rgoals, int r
         pair_force(soc, fm, rb, rs, st + NS * j, safety[j], rp, f);
         fs0 += f[0]; fs1 += f[1];
     }
-    rb[0] += rb[3] * dt; rb[1] += rb[4] * dt;
+    if (!just_velocities) { rb[0] += rb[3] * dt; rb[1] += rb[4] * dt; } /* mmm:73,80 */
     if (!headed) { /* mmm:609,628 */
         double g0 = rdes[0] + fo[0] + fs0, g1 = rdes[1] + fo[1] + fs1;
         rb[3] += (g0 / rb[9]) * dt; rb[4] += (g1 / rb[9]) * dt;
@@ -390,7 +390,7 @@ static void update_robot_env(const orc_cfg *c, double *rb, double *rgoals, int r
         double tq = (headed == 1) ? torque_force(fm, rb, inertia, rdes[0], rdes[1], rp) : torque_force(fm, rb, inertia, sx, sy, rp);
         double g0 = np_dot(fm, sx, sy, cs, sn);
         double g1 = rp[P_KO] * np_dot(fm, fo[0] + fs0, fo[1] + fs1, -sn, cs) - rp[P_KD] * rb[6];
-        rb[2] = bound_angle(rb[2] + rb[7] * dt);
+        if (!just_velocities) rb[2] = bound_angle(rb[2] + rb[7] * dt); /* mmm:81 */
         rb[5] += (g0 / rb[9]) * dt; rb[6] += (g1 / rb[9]) * dt;
         rb[7] += (tq / inertia) * dt;
         clip_norm(fm, &rb[5], &rb[6], rb[12]);
@@ -417,10 +417,53 @@ void orc_imitation_steps(const orc_cfg *c, int E, double *states, double *goals,
             double *rb = robot + (size_t)e * NS;
             for (int s = 0; s < n_steps; ++s) {
                 update_robot_env(c, rb, robot_goals + (size_t)e * rg * 2, rg, robot_desired + 2 * e, robot_params, robot_type, robot_safety[e],
-                                 st, safety + (size_t)e * rows, walls + e * wstride, dt, scratch);
+                                 st, safety + (size_t)e * rows, walls + e * wstride, dt, scratch, 0);
                 if (c->consider_robot) memcpy(st + NS * c->n, rb, sizeof(double) * NS);
                 update_env(c, st, goals + (size_t)e * c->n * c->g * 2, walls + e * wstride, params + (size_t)e * c->n * NP,
                            safety + (size_t)e * rows, desired + (size_t)e * c->n * 2, dt, NULL, scratch);
+            }
+        }
+        free(scratch);
+    }
+}
+
+/* n_steps x SocialNavSim.update (sim:476-492) with the robot driven by a motion model through control_robot (sim:500-529):
+ * every update the pose advances with the last velocity (update_robot_pose, mmm:655-657: yaw is NOT wrapped) and, when the update
+ * index is a multiple of `every` (is_multiple(sim_t, ROBOT_SAMPLING_TIME), sim:501), the velocities are refreshed by
+ * update_robot(sim_t, robot_dt, just_velocities=True) (sim:523-524); with every <= 1 (equal sampling times, sim:521)
+ * update_robot(sim_t, dt) moves the robot.  The humans are then updated seeing the robot's state from BEFORE control_robot
+ * (get_safe_state / set_state around it, sim:484-491; the goal list is not part of that state).  `phase` = index of the first update. */
+void orc_sim_update_steps(const orc_cfg *c, int E, double *states, double *goals, const double *walls, const double *params,
+                          const double *safety, double *desired, double dt, int n_steps, double *robot, double *robot_goals, int rg,
+                          double *robot_desired, const double *robot_params, int robot_type, const double *robot_safety, int every,
+                          double robot_dt, int phase, int n_threads) {
+    const int rows = c->n + (c->consider_robot ? 1 : 0);
+    const size_t wstride = c->walls_per_env ? (size_t)c->n_walls * c->n_segs * 4 : 0;
+#pragma omp parallel num_threads(n_threads > 0 ? n_threads : 1)
+    {
+        double *scratch = (double *)malloc(sizeof(double) * scratch_doubles(c));
+#pragma omp for schedule(static)
+        for (int e = 0; e < E; ++e) {
+            double *st = states + (size_t)e * rows * NS;
+            double *rb = robot + (size_t)e * NS;
+            for (int s = 0; s < n_steps; ++s) {
+                double before[8], after[8];
+                memcpy(before, rb, sizeof(before));
+                if (every <= 1) {
+                    update_robot_env(c, rb, robot_goals + (size_t)e * rg * 2, rg, robot_desired + 2 * e, robot_params, robot_type, robot_safety[e],
+                                     st, safety + (size_t)e * rows, walls + e * wstride, dt, scratch, 0);
+                } else {
+                    rb[0] += rb[3] * dt; rb[1] += rb[4] * dt; rb[2] += rb[7] * dt;
+                    if ((phase + s) % every == 0)
+                        update_robot_env(c, rb, robot_goals + (size_t)e * rg * 2, rg, robot_desired + 2 * e, robot_params, robot_type,
+                                         robot_safety[e], st, safety + (size_t)e * rows, walls + e * wstride, robot_dt, scratch, 1);
+                }
+                memcpy(after, rb, sizeof(after));
+                memcpy(rb, before, sizeof(before));
+                if (c->consider_robot) memcpy(st + NS * c->n, rb, sizeof(double) * NS);
+                update_env(c, st, goals + (size_t)e * c->n * c->g * 2, walls + e * wstride, params + (size_t)e * c->n * NP,
+                           safety + (size_t)e * rows, desired + (size_t)e * c->n * 2, dt, NULL, scratch);
+                memcpy(rb, after, sizeof(after));
             }
         }
         free(scratch);

@@ -297,6 +297,58 @@ def robot_model_cases():
     print("il_robot ->", os.path.getsize(path), "B")
 
 
+def sim_update_cases():
+    """Robot driven by a human motion model inside SocialNavSim.update (social_nav_sim.py:476-492 -> control_robot :500-529), the
+    loop behind run_k_steps: every update the robot pose advances with its last velocity (update_robot_pose, mmm:655), every
+    ROBOT_SAMPLING_TIME its velocities are refreshed by update_robot(..., just_velocities=True) with dt = ROBOT_SAMPLING_TIME
+    (mmm:615; euler_*_single_agent_update mmm:72-85), or -- equal sampling times -- update_robot(dt) moves it; the humans are then
+    updated seeing the robot's PREVIOUS state (sim:484-491).  Produced by calling sim.update() itself.  Fixture sim_update.npz."""
+    out = {}
+    confs = [("cc5_hsfm_farina__hsfm_new_guo_rt20", lambda: cc_sim("hsfm_farina", 1002, 5, True), "hsfm_new_guo", 0.25, 300),
+             ("cc6_sfm_helbing__sfm_guo_invisible_rt4", lambda: cc_sim("sfm_helbing", 2003, 6, False), "sfm_guo", 0.05, 300),
+             ("walls7_hsfm_farina__hsfm_farina_rt1", lambda: custom_sim(dense_example_data(), "hsfm_farina", True), "hsfm_farina", DT, 200),
+             ("cc5_near_goal_hsfm_guo__hsfm_guo_rt20", lambda: _near_goal(cc_sim("hsfm_guo", 31, 5, True)), "hsfm_guo", 0.25, 400)]
+    for key, mk, robot_model, robot_dt, n_steps in confs:
+        sim = mk()
+        mm = sim.motion_model_manager
+        if len(sim.robot.goals) == 1:
+            sim.robot.goals = [list(sim.robot.goals[0]), [float(sim.robot.position[0]), float(sim.robot.position[1])]]
+        sim.set_time_step(DT)
+        sim.set_robot_time_step(robot_dt)
+        sim.set_robot_policy(policy_name=robot_model, runge_kutta=False)
+        assert sim.robot_env_same_timestep == (robot_dt == DT)
+        humans, robot = sim.humans, sim.robot
+        model = mm.motion_model_title
+        out[key + "_type"] = np.int64(SFMS.index(model))
+        out[key + "_robot_type"] = np.int64(SFMS.index(robot_model))
+        out[key + "_robot_dt"] = np.float64(robot_dt)
+        out[key + "_every"] = np.int64(round(robot_dt / DT))
+        out[key + "_states0"] = np.array([h.get_safe_state() for h in humans])
+        out[key + "_goals0"] = pack_goals(humans)
+        out[key + "_walls"] = pack_walls(mm.walls)
+        out[key + "_params"] = np.array([h.get_parameters(model) for h in humans])
+        out[key + "_robot_params"] = robot.get_parameters(robot_model)
+        out[key + "_robot0"] = robot.get_safe_state()
+        out[key + "_robot_goals"] = np.array(robot.goals, np.float64)
+        out[key + "_flags"] = np.array([int(mm.consider_robot), int(mm.all_equal_humans)], np.int64)
+        steps, traj, rtraj = [0], [np.array([human_row(h) for h in humans])], [human_row(robot)]
+        for s in range(1, n_steps + 1):
+            sim.update()
+            if s <= 25 or s % 10 == 0:
+                steps.append(s)
+                traj.append(np.array([human_row(h) for h in humans]))
+                rtraj.append(human_row(robot))
+        out[key + "_steps"] = np.array(steps, np.int64)
+        out[key + "_traj"] = np.array(traj)
+        out[key + "_robot_traj"] = np.array(rtraj)
+        rt = np.array(rtraj)
+        print("sim_update", key, "robot goal switches:", int((np.abs(np.diff(rt[:, 8:10], axis=0)).sum(1) > 0).sum()), "final robot pos", rt[-1, :2],
+              "yaw", rt[-1, 2])
+    path = os.path.join(HERE, "sim_update.npz")
+    np.savez_compressed(path, **out)
+    print("sim_update ->", os.path.getsize(path), "B")
+
+
 def lookahead_case():
     """The policy-side operator the CrowdNav value-network policies call once per decision (crowd_nav/policy/cadrl.py:42-83
     compute_rotated_states_and_reward, used by CADRL.predict :235-276): peek of the humans at dt = 0.25
@@ -650,13 +702,15 @@ def gym_case():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["traj", "pt", "il", "lookahead", "scenarios", "push_out", "numba", "peek", "flags", "laser", "gym"]
+    which = sys.argv[1:] or ["traj", "pt", "il", "sim_update", "lookahead", "scenarios", "push_out", "numba", "peek", "flags", "laser", "gym"]
     if "traj" in which:
         traj_cases()
     if "pt" in which:
         pt_cases()
     if "il" in which:
         robot_model_cases()
+    if "sim_update" in which:
+        sim_update_cases()
     if "lookahead" in which:
         lookahead_case()
     if "scenarios" in which:

@@ -129,6 +129,36 @@ def test_robot_driven_by_motion_model():
     assert (np.abs(np.diff(rt[:, 8:10], axis=0)).sum(1) > 0).sum() == 1   # the robot's goal list rotated once
 
 
+def test_sim_update_with_model_driven_robot():
+    """SocialNavSim.update with a model-driven robot (sim:476-529), recorded by calling sim.update() of the live reference: pose advance every
+    update (unwrapped yaw), update_robot(just_velocities=True) every ROBOT_SAMPLING_TIME with that dt -- or a full update_robot when the
+    sampling times are equal -- and humans that see the robot's PREVIOUS state.  4 runs: 20 / 4 / 1 updates per robot step, robot visible or
+    not, walls, a robot goal switch, a run whose unwrapped yaw reaches -500 rad."""
+    z = np.load(os.path.join(GOLDEN, "sim_update.npz"))
+    keys = sorted(k[:-len("_robot_type")] for k in z.files if k.endswith("_robot_type"))
+    assert len(keys) == 4
+    for key in keys:
+        vis, equal = (bool(v) for v in z[key + "_flags"])
+        S, G, rb = z[key + "_states0"], z[key + "_goals0"][None], z[key + "_robot0"][None].copy()
+        n = S.shape[0]
+        S = (np.concatenate([S, rb], 0) if vis else S)[None]
+        cfg = OracleConfig(int(z[key + "_type"]), vis, equal, False)
+        D, rD, rG = np.zeros((1, n, 2)), np.zeros((1, 2)), z[key + "_robot_goals"][None].copy()
+        cur = 0
+        for k, s_ in enumerate(z[key + "_steps"]):
+            if s_ > cur:
+                S, G, D, rb, rG, rD = oracle.sim_update_steps(cfg, S, G, z[key + "_walls"], z[key + "_params"][None], np.zeros((1, S.shape[1])), D,
+                                                              0.0125, int(s_ - cur), rb, rG, rD, z[key + "_robot_params"], int(z[key + "_robot_type"]),
+                                                              int(z[key + "_every"]), float(z[key + "_robot_dt"]), phase=int(cur))
+                cur = s_
+            got_h = np.concatenate([S[0, :n, :8], S[0, :n, 10:12], D[0]], 1)
+            got_r = np.concatenate([rb[0, :8], rb[0, 10:12], rD[0]])
+            assert rel_err(got_h, z[key + "_traj"][k]).max() < 1e-9, (key, int(s_))
+            assert rel_err(got_r, z[key + "_robot_traj"][k]).max() < 1e-9, (key, int(s_), got_r, z[key + "_robot_traj"][k])
+    rt = z["cc5_near_goal_hsfm_guo__hsfm_guo_rt20_robot_traj"]
+    assert (np.abs(np.diff(rt[:, 8:10], axis=0)).sum(1) > 0).sum() == 1 and np.abs(rt[:, 2]).max() > 100.0
+
+
 def test_lookahead_rewards_and_rotated_states():
     """compute_rotated_states_and_reward (cadrl.py:42-83) for 81 actions: rewards bit-exact, rotated states to 1e-13."""
     z = np.load(os.path.join(GOLDEN, "lookahead.npz"))
