@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SNP_ABI_VERSION 1
+#define SNP_ABI_VERSION 2
 
 typedef enum snp_status {
     SNP_OK = 0,
@@ -134,6 +134,13 @@ typedef struct snp_step_opts {
     const int32_t *respawn_envs; /* optional [E], with respawn: only envs with a non-zero entry respawn (hybrid scenario: the parallel-traffic
                                  envs of a mixed batch; snp_reset's scenario_out works as is) */
     int32_t *goal_idx_out;    /* optional [E*N], with dyn_out: the goal index the update arrived at (the peek reports the goal after it) */
+    int32_t robot_every;      /* robot_mode 2 only.  0: SocialNavGym.imitation_learning_step order (update_robot, then humans that see the
+                                 moved robot).  >= 1: SocialNavSim.update / control_robot (social_nav_sim.py:476-529): the humans see the
+                                 robot's state from BEFORE its update (:484-491); 1 = equal sampling times, update_robot(dt) every
+                                 sub-step (:521); k > 1 = the pose advances every sub-step with the last velocity, yaw unwrapped
+                                 (update_robot_pose, motion_model_manager.py:655-657) and every k-th sub-step the velocities are refreshed
+                                 by update_robot(..., consts[5] = ROBOT_SAMPLING_TIME, just_velocities=True) (:523-524, mmm:72-85) */
+    int32_t robot_phase;      /* robot_every > 1: index of this launch's first sub-step in that schedule (n_updates of the simulator) */
 } snp_step_opts;
 
 typedef struct snp_laser_args {

@@ -34,7 +34,8 @@ class SnpStepOpts(ctypes.Structure):
                 ("pre_checks", c_int32), ("post_checks", c_int32), ("track_touch", c_int32), ("reserved", c_int32),
                 ("consts", c_double * 6), ("time_now", c_void_p), ("flags", c_void_p), ("checks", c_void_p),
                 ("respawn_bounds", c_double * 2), ("respawn", c_int32), ("robot_type", c_int32), ("robot_params", c_double * 20),
-                ("dyn_out", c_void_p), ("respawn_envs", c_void_p), ("goal_idx_out", c_void_p)]
+                ("dyn_out", c_void_p), ("respawn_envs", c_void_p), ("goal_idx_out", c_void_p),
+                ("robot_every", c_int32), ("robot_phase", c_int32)]
 
 
 class SnpLaserArgs(ctypes.Structure):

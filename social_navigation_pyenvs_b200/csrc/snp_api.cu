@@ -69,6 +69,8 @@ template <typename T> static int build_args(const snp_crowd *c, const snp_step_o
     a.mapping = (o->reserved >> 2) & 3;  // bits 2-3 of `reserved`: thread mapping override (tests / tuning)
     a.full_pair_loop = o->reserved & 1;  // bit 0 of `reserved`: SNP_OPT_FULL_PAIR_LOOP
     a.dyn_out = (T *)o->dyn_out; a.goal_idx_out = o->goal_idx_out; a.respawn_envs = o->respawn_envs;
+    a.robot_every = o->robot_mode == 2 ? o->robot_every : 0; a.robot_phase = o->robot_phase; a.robot_dt = (T)o->consts[5];
+    if (a.robot_every < 0 || (a.robot_every > 1 && o->robot_phase < 0)) { set_error("robot_every / robot_phase must be >= 0"); return SNP_ERR_INVALID; }
     if (o->dyn_out && (o->respawn || o->robot_mode == 2)) { set_error("dyn_out (peek) cannot be combined with respawn or robot_mode 2"); return SNP_ERR_INVALID; }
     return SNP_OK;
 }

@@ -51,6 +51,8 @@ template <typename T> struct KArgs {
     const int *respawn_envs;  // optional per-env respawn switch
     int *goal_idx_out;  // peek: goal index after the update (optional)
     T *dyn_out;  // peek: updated pose / velocities are written here instead of in place (goal index untouched)
+    int robot_every, robot_phase;  // robot_mode 2: SocialNavSim.update schedule (0 = imitation-learning order), see snp_step_opts
+    T robot_dt;  // consts[5] in the crowd's dtype
 };
 
 // Host-side launchers implemented per translation unit.

@@ -351,7 +351,7 @@ template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, 
     a.walls = (const T *)c->walls; a.W = c->W; a.S = c->W > 0 ? c->S : 0; a.walls_per_env = 0;
     a.consider_robot = 0; a.symmetric = o->symmetric; a.numba = o->numba_compat; a.n_substeps = 1; a.robot_mode = 0;
     a.dt = (T)o->dt; a.dt_d = o->dt; a.action = nullptr; a.pre_checks = a.post_checks = a.track_touch = 0;
-    a.time_now = nullptr; a.flags = nullptr; a.checks = nullptr; a.epw = 1; a.gpb = 1; a.mapping = 0; a.full_pair_loop = 1; a.respawn = 0; a.robot_type = 0; a.RP = a.P;
+    a.time_now = nullptr; a.flags = nullptr; a.checks = nullptr; a.epw = 1; a.gpb = 1; a.mapping = 0; a.full_pair_loop = 1; a.respawn = 0; a.robot_type = 0; a.RP = a.P; a.robot_every = 0; a.robot_phase = 0; a.robot_dt = T(0);
     la.others = (const T *)others; la.M = M; la.self_offset = self_offset; la.next_view = (T *)next_view;
     la.J = (int)large_J(M); la.n_tiles = (int)large_tiles(M);
     const long long need = (long long)sizeof(T) * ((long long)la.J * 2 * a.EN + (long long)la.n_tiles * 5) + large_iblocks(a.EN) * la.J;

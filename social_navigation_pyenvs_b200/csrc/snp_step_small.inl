@@ -194,7 +194,7 @@ __device__ __noinline__ void robot_pair(int soc, const Params<T> *RP, const doub
 // compute_robot_forces + Euler (mmm:593-629) by ONE lane, given the summed force of the humans (fsx, fsy).
 template <typename T>
 __device__ __noinline__ void robot_update(int rtype, const Params<T> *RPp, const double *tbl, const Seg<T> *segs, const int *seg_cnt, int W, int S,
-                                          T *rb, T fsx, T fsy, T dt) {
+                                          T *rb, T fsx, T fsy, T dt, bool just_velocities) {
     using R = Real<T>;
     const Params<T> &RP = *RPp;
     const int obs = (rtype == 1 || rtype == 4 || rtype == 7) ? 1 : 0, headed = rtype / 3;
@@ -218,9 +218,18 @@ __device__ __noinline__ void robot_update(int rtype, const Params<T> *RPp, const
         else obstacle_force<T, 1>(RP, tbl, self, segs, seg_cnt, W, S, false, m.px, m.py, m.vx, m.vy, m.rs, fox, foy);
     }
     desired_force<T>(RP, m, false);
+    const T px0 = m.px, py0 = m.py, th0 = m.th, cs0 = m.cs, sn0 = m.sn;
     if (headed == 0) integrate<T, 0>(RP, m, fox, foy, fsx, fsy, dt);
     else if (headed == 1) integrate<T, 1>(RP, m, fox, foy, fsx, fsy, dt);
     else integrate<T, 2>(RP, m, fox, foy, fsx, fsy, dt);
+    if (just_velocities) {  // mmm:73,79-81: position and yaw stay; v = R(yaw) bv with the UNCHANGED yaw (mmm:85)
+        m.px = px0; m.py = py0;
+        if (headed) {
+            m.th = th0;
+            m.vx = np_mv(cs0, -sn0, m.bvx, m.bvy);
+            m.vy = np_mv(sn0, cs0, m.bvx, m.bvy);
+        }
+    }
     rb[SNP_ROBOT_PX] = m.px; rb[SNP_ROBOT_PY] = m.py; rb[SNP_ROBOT_VX] = m.vx; rb[SNP_ROBOT_VY] = m.vy; rb[SNP_ROBOT_TH] = m.th;
     rb[SNP_ROBOT_BVX] = m.bvx; rb[SNP_ROBOT_BVY] = m.bvy; rb[SNP_ROBOT_OM] = m.om; rb[SNP_ROBOT_DFX] = m.dfx; rb[SNP_ROBOT_DFY] = m.dfy;
     rb[SNP_ROBOT_GX] = m.gx; rb[SNP_ROBOT_GY] = m.gy;
@@ -361,8 +370,8 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
         if constexpr (ROBOT2) if (leader) {  // the robot's full state lives in shared memory (one lane updates it)
 #pragma unroll
             for (int f = 0; f < SNP_ROBOT_FIELDS; ++f) rb[f] = a.robot[(size_t)f * E + env];
-            if (a.robot_type >= 3) {  // headed robot: linear velocity = R(yaw) bv (mmm:605)
-                T sn, cs;
+            if (a.robot_type >= 3 && a.robot_every <= 1) {  // headed robot: linear velocity = R(yaw) bv (mmm:605); with robot_every > 1
+                T sn, cs;                                   // the velocity of the last refresh is what moves the pose (mmm:655-657)
                 R::sincos_(rb[SNP_ROBOT_TH], &sn, &cs);
                 rb[SNP_ROBOT_VX] = np_mv(cs, -sn, rb[SNP_ROBOT_BVX], rb[SNP_ROBOT_BVY]);
                 rb[SNP_ROBOT_VY] = np_mv(sn, cs, rb[SNP_ROBOT_BVX], rb[SNP_ROBOT_BVY]);
@@ -431,8 +440,32 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             // update_robot first (gym:262): every human lane evaluates its force on the robot with the ROBOT's model and
             // parameters, the group sums them, the leader integrates the robot and republishes it; the humans then see the
             // moved robot (gym:264).
+            // a.robot_every >= 1 -- SocialNavSim.update / control_robot (sim:476-529) instead: the humans see the robot's state from
+            // BEFORE its update (sim:484-491), so that state is what goes into entity slot N; with robot_every > 1 the pose advances
+            // every sub-step with the last velocity (update_robot_pose, mmm:655-657, yaw unwrapped) and only every robot_every-th
+            // sub-step refreshes the velocities (update_robot just_velocities with dt = ROBOT_SAMPLING_TIME, sim:523-524).
+            const bool sched = a.robot_every >= 1, jv = a.robot_every > 1;
+            const bool upd = !jv || ((a.robot_phase + s) % a.robot_every) == 0;  // uniform
+            if (sched) {
+                if (leader) {
+                    if (a.consider_robot) ents.put(N, rb[SNP_ROBOT_PX], rb[SNP_ROBOT_PY], rb[SNP_ROBOT_VX], rb[SNP_ROBOT_VY]);
+                    if (jv) {
+                        rb[SNP_ROBOT_PX] = fma_<T>(rb[SNP_ROBOT_VX], dt, rb[SNP_ROBOT_PX]);
+                        rb[SNP_ROBOT_PY] = fma_<T>(rb[SNP_ROBOT_VY], dt, rb[SNP_ROBOT_PY]);
+                        rb[SNP_ROBOT_TH] = fma_<T>(rb[SNP_ROBOT_OM], dt, rb[SNP_ROBOT_TH]);
+                        if (upd && a.robot_type >= 3) {  // compute_robot_forces refreshes v = R(yaw) bv before any force (mmm:605)
+                            T sn_, cs_;
+                            R::sincos_(rb[SNP_ROBOT_TH], &sn_, &cs_);
+                            const T bx = rb[SNP_ROBOT_BVX], by = rb[SNP_ROBOT_BVY];
+                            rb[SNP_ROBOT_VX] = np_mv(cs_, -sn_, bx, by);
+                            rb[SNP_ROBOT_VY] = np_mv(sn_, cs_, bx, by);
+                        }
+                    }
+                }
+                if constexpr (CTA) __syncthreads(); else __syncwarp(wmask);
+            }
             T rfx = T(0), rfy = T(0);
-            if (live) robot_pair<T>(a.robot_type % 3, RPs, exp_tbl_s, wmask, rb, me.px, me.py, me.vx, me.vy, me.rs, &rfx, &rfy);
+            if (live && upd) robot_pair<T>(a.robot_type % 3, RPs, exp_tbl_s, wmask, rb, me.px, me.py, me.vx, me.vy, me.rs, &rfx, &rfy);
             if constexpr (CTA) {
                 if (live) { red[i] = (double)rfx; }
                 __syncthreads();
@@ -448,8 +481,8 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
                 rfx = seg_sum<T>(rfx, i, N, wmask); rfy = seg_sum<T>(rfy, i, N, wmask);
             }
             if (leader) {
-                robot_update<T>(a.robot_type, RPs, exp_tbl_s, segs, seg_cnt, a.W, a.S, rb, rfx, rfy, dt);
-                if (a.consider_robot) ents.put(N, rb[SNP_ROBOT_PX], rb[SNP_ROBOT_PY], rb[SNP_ROBOT_VX], rb[SNP_ROBOT_VY]);
+                if (upd) robot_update<T>(a.robot_type, RPs, exp_tbl_s, segs, seg_cnt, a.W, a.S, rb, rfx, rfy, jv ? a.robot_dt : dt, jv);
+                if (a.consider_robot && !sched) ents.put(N, rb[SNP_ROBOT_PX], rb[SNP_ROBOT_PY], rb[SNP_ROBOT_VX], rb[SNP_ROBOT_VY]);
             }
             if constexpr (CTA) __syncthreads(); else __syncwarp(wmask);
             rpx = rb[SNP_ROBOT_PX]; rpy = rb[SNP_ROBOT_PY]; rvx = rb[SNP_ROBOT_VX]; rvy = rb[SNP_ROBOT_VY];

@@ -235,6 +235,26 @@ class CrowdEngine:
         o = self._opts(dt, n_substeps, robot_mode=2, post_checks=2, advance_time=True)
         L.check(self.lib.snp_step(ctypes.byref(self._crowd()), ctypes.byref(o), _stream()))
 
+    def sim_update(self, dt=0.0125, n_updates=1, robot_every=1, robot_time_step=None, phase=0):
+        """`n_updates` x SocialNavSim.update (social_nav_sim.py:476-492) with the robot driven by its motion model through
+        control_robot (:500-529), the loop behind run_k_steps -- one launch.  The humans see the robot's state from before its
+        update.  robot_every = ROBOT_SAMPLING_TIME / SAMPLING_TIME: 1 -> update_robot(dt) every update (:521); k > 1 -> the pose
+        advances every update with the last velocity (update_robot_pose, motion_model_manager.py:655) and every k-th update
+        (update index `phase` + i a multiple of k) update_robot(robot_time_step, just_velocities=True) refreshes the velocities
+        (:523-524).  `track_touch` reports run_k_steps' collision test (:702-703) in decode_flags()["touched"]."""
+        if self.robot_type is None:
+            raise ValueError("set_robot_motion_model(title) first")
+        if int(robot_every) < 1:
+            raise ValueError("robot_every must be >= 1 (robot sampling time as a multiple of the environment's)")
+        keep = self.consts[5]
+        self.consts[5] = float(robot_time_step if robot_time_step is not None else dt * int(robot_every))
+        try:
+            o = self._opts(dt, n_updates, robot_mode=2, track_touch=True, advance_time=True)
+            o.robot_every, o.robot_phase = int(robot_every), int(phase) % int(robot_every)
+            L.check(self.lib.snp_step(ctypes.byref(self._crowd()), ctypes.byref(o), _stream()))
+        finally:
+            self.consts[5] = keep
+
     def robot_rows(self):
         """Robot state as reference rows [E,13] + carried desired force [E,2]."""
         r = self.robot.double().cpu().numpy()
