@@ -30,6 +30,14 @@ out.append("Scaling (`r01_scale_lines.jsonl`; env-sharded, no data-path collecti
            "(`scenarios.spatial_order`), fp64: 7.7e7 (1 GPU), 1.28e8 (2), 1.72e8 (8) agent-steps/s = 0.85 / 0.51 / 0.38 ms per sub-step; every ordered pair evaluated: "
            "8.5 / 4.3 / 1.16 ms\n(row-by-row numbering, earlier in the round: 3.3e7, 5.8e7, 1.04e8 on 1, 2, 4 GPUs) -- "
            "`tools/multi_gpu_check.py` (sharded == single GPU, bit for bit) OK on 2 and 4 ranks.\n")
+try:
+    su = eval(open(P + f"{R}_sim_update_errors.txt").read())
+    out.append("SocialNavSim.update with a model-driven robot (`snp_step_opts.robot_every`), worst relative error against 4 runs recorded from the live "
+               "reference's `sim.update()` (`" + R + "_sim_update_errors.txt`): " +
+               "; ".join(f"{k}: {v['stable'][0]:.1e}" + (f" (unstable tail of the reference's own run: {v['unstable'][0]:.1e}, reported)" if v['unstable'][1] >= 0 else "")
+                         for k, v in su.items()) + ".\n")
+except OSError:
+    pass
 out += ["## Issue-port model (`issue_model.json`, `r01_pipe_microbench.txt`)\n",
         "An FP64 instruction holds its SMSP's issue port for 2 cycles and nothing issues in its shadow (8 DFMA + 8 FFMA take the sum of their\n"
         "issue times), so `cycles >= 2 N_fp64 + N_other` per SMSP.  Per launch, from the per-SASS-instruction execution counts:\n",
