@@ -48,3 +48,58 @@ def test_serial_update_matches_the_live_reference(mg, model, seed, n, visible):
         got = np.concatenate([S[0, :n, :8], S[0, :n, 10:12], D[0]], 1)
         worst = max(worst, rel_err(got, ref).max())
     assert worst < 1e-9, worst
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_laser_matches_the_live_reference(mg, seed):
+    """LaserSensor.get_laser_measurements (sensors.py:53-69) on a walled scene after a random number of updates, from random sensor
+    poses: ranges bit-identical, hit indices equal to the replayed first-strict-minimum of the reference loop."""
+    rng = np.random.RandomState(seed)
+    sim = mg.custom_sim(mg.dense_example_data(), "hsfm_farina", True)
+    mm = sim.motion_model_manager
+    for _ in range(int(rng.randint(10, 200))):
+        mm.update_humans(0.0, mg.DT)
+    humans = np.array([[h.position[0], h.position[1], h.radius] for h in sim.humans])
+    walls = mg.pack_walls(mm.walls)
+    for rep in range(4):
+        pos, yaw = rng.uniform(-5.0, 5.0, 2), float(rng.uniform(-np.pi, np.pi))
+        samples, span, maxd = int(rng.choice([61, 180, 360])), float(rng.choice([np.pi, 2 * np.pi])), float(rng.choice([6.0, 10.0]))
+        sensor = mg.LaserSensor(pos, yaw, span, samples, maxd, uncertainty=None)
+        sensor.uncertainty = None
+        meas = sensor.get_laser_measurements(sim.humans, mm.walls)
+        ranges, hits = oracle.laser(humans[None], walls, np.array([[pos[0], pos[1], yaw]]), span, samples, maxd)
+        assert np.array_equal(ranges[0], np.array(list(meas.values())))
+        assert np.array_equal(hits[0], mg.laser_hits(sensor, sim.humans, mm.walls))
+
+
+def test_checks_match_the_live_reference(mg):
+    """collision_detection_and_reaching_goal + compute_reward_and_infos (sim:949-1029) and check_actual_collisions_and_goal
+    (gym:107-118) on 150 fresh random robot placements / actions / times: every flag, dmin and reward bit-identical."""
+    rng = np.random.RandomState(77)
+    sim = mg.cc_sim("sfm_guo", 4201, 7, robot_visible=False)
+    sim.time_limit, sim.collision_penalty, sim.success_reward, sim.discomfort_dist, sim.discomfort_penalty_factor = 50, -0.25, 1.0, 0.2, 0.5
+    consts = np.array([50, -0.25, 1.0, 0.2, 0.5, 0.25])
+    mm = sim.motion_model_manager
+    code = {"Timeout": 1, "Collision": 2, "Reaching goal": 3, "Too close": 4, "": 0}
+    seen = set()
+    for k in range(150):
+        for _ in range(3):
+            mm.update_humans(0.0, mg.DT)
+        h0 = sim.humans[rng.randint(7)]
+        if k % 3 == 0:
+            sim.robot.position = h0.position + rng.uniform(-1.2, 1.2, 2)
+        elif k % 3 == 1:
+            sim.robot.position = np.array(sim.robot.goals[0], np.float64) + rng.uniform(-0.5, 0.5, 2)
+        else:
+            sim.robot.position = rng.uniform(-7, 7, 2)
+        a = rng.uniform(-1.0, 1.0, 2)
+        t_now = 49.5 if k % 29 == 0 else float(rng.uniform(0, 40))
+        col, dmin, goal = sim.collision_detection_and_reaching_goal(a, 0.25)
+        reward, term, trunc, info = sim.compute_reward_and_infos(col, dmin, goal, t_now, 0.25)
+        acol, admin, agoal = mg.gym_mod.SocialNavGym.check_actual_collisions_and_goal(sim)
+        H = np.array([h.get_safe_state() for h in sim.humans])[None]
+        out = oracle.checks(H, 7, sim.robot.get_safe_state()[None], a[None], np.array([t_now]), consts)[0]
+        ref = [float(col), dmin, float(goal), reward, float(term), float(trunc), code[str(info)], float(acol), admin, float(agoal)]
+        assert np.array_equal(out[:10], np.array(ref, np.float64)), (k, out[:10], ref)
+        seen.add(code[str(info)])
+    assert seen == {0, 1, 2, 3, 4}
