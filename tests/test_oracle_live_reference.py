@@ -103,3 +103,39 @@ def test_checks_match_the_live_reference(mg):
         assert np.array_equal(out[:10], np.array(ref, np.float64)), (k, out[:10], ref)
         seen.add(code[str(info)])
     assert seen == {0, 1, 2, 3, 4}
+
+
+@pytest.mark.parametrize("model,robot_model,seed,n,visible,robot_dt", [("hsfm_new_guo", "hsfm_farina", 4301, 6, True, 0.1),
+                                                                      ("sfm_guo", "sfm_helbing", 4302, 8, True, 0.25),
+                                                                      ("hsfm_farina", "hsfm_new", 4303, 5, False, 0.0125),
+                                                                      ("sfm_helbing", "hsfm_guo", 4304, 7, True, 0.05)])
+def test_sim_update_matches_the_live_reference(mg, model, robot_model, seed, n, visible, robot_dt):
+    """SocialNavSim.update (sim:476-529) x 120 with a model-driven robot at its own sampling time, on crowds / model pairs /
+    sampling ratios (8, 20, 1, 4) that tests/golden/sim_update.npz does not hold."""
+    sim = mg.cc_sim(model, seed, n, robot_visible=visible)
+    mm, humans, robot = sim.motion_model_manager, sim.humans, sim.robot
+    if len(robot.goals) == 1:
+        robot.goals = [list(robot.goals[0]), [float(robot.position[0]), float(robot.position[1])]]
+    sim.set_time_step(mg.DT)
+    sim.set_robot_time_step(robot_dt)
+    sim.set_robot_policy(policy_name=robot_model, runge_kutta=False)
+    every = int(round(robot_dt / mg.DT))
+    S = np.array([h.get_safe_state() for h in humans])
+    rb = robot.get_safe_state()[None].copy()
+    if visible:
+        S = np.concatenate([S, rb], 0)
+    S, G = S[None], mg.pack_goals(humans)[None]
+    params = np.array([h.get_parameters(model) for h in humans])[None]
+    cfg = OracleConfig(mg.SFMS.index(model), visible, bool(mm.all_equal_humans), False)
+    D, rD, rG = np.zeros((1, n, 2)), np.zeros((1, 2)), np.array(robot.goals, np.float64)[None]
+    rp, rtype = robot.get_parameters(robot_model), mg.SFMS.index(robot_model)
+    worst = 0.0
+    for step in range(120):
+        sim.update()
+        S, G, D, rb, rG, rD = oracle.sim_update_steps(cfg, S, G, None, params, np.zeros((1, S.shape[1])), D, mg.DT, 1, rb, rG, rD, rp, rtype,
+                                                      every, robot_dt, phase=step)
+        ref_h, ref_r = np.array([mg.human_row(h) for h in humans]), mg.human_row(robot)
+        got_h = np.concatenate([S[0, :n, :8], S[0, :n, 10:12], D[0]], 1)
+        got_r = np.concatenate([rb[0, :8], rb[0, 10:12], rD[0]])
+        worst = max(worst, rel_err(got_h, ref_h).max(), rel_err(got_r, ref_r).max())
+    assert worst < 1e-9, worst
