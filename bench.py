@@ -47,8 +47,9 @@ WORKLOADS = {
 def build_inputs(workload, seed0):
     from social_navigation_pyenvs_b200 import scenarios
     model, E, N, with_walls, robot_visible = WORKLOADS[workload]
+    E = int(os.environ.get("SNP_BENCH_ENVS", E))  # tuning experiments only (wave quantisation); the reported workloads use the table
     # per-box scratch (several ranks / several bench runs on one box share it); NOT under gpurun_out/, whose size is capped
-    cache = os.path.join(tempfile.gettempdir(), "snp_b200_scenarios", f"scenario_{workload}_{seed0}.npz")
+    cache = os.path.join(tempfile.gettempdir(), "snp_b200_scenarios", f"scenario_{workload}_{E}_{seed0}.npz")
     if os.path.exists(cache):
         z = np.load(cache)
         sc = dict(states=z["states"], goals=z["goals"], robot=z["robot"])
@@ -533,7 +534,7 @@ def main():
         one_step()
     torch.cuda.synchronize()
     t_ramp = time.perf_counter()  # extra untimed load so the SM clock has ramped before the timed region starts
-    while time.perf_counter() - t_ramp < 0.25:
+    while time.perf_counter() - t_ramp < float(os.environ.get("SNP_BENCH_RAMP_S", "0.25")):
         for _ in range(20):
             one_step()
         torch.cuda.synchronize()
@@ -558,6 +559,9 @@ def main():
         dist.barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(step_ms)
+    if os.environ.get("SNP_BENCH_DUMP_STEPS"):  # tuning: per-step times (the crowd's state, hence the branch mix, evolves over the run)
+        with open(os.environ["SNP_BENCH_DUMP_STEPS"], "w") as f:
+            f.write("\n".join(f"{x:.5f}" for x in step_ms))
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -271,6 +271,10 @@ int snp_laser_host(int32_t E, int32_t N, const double *humans, const double *wal
 int snp_measure_pipe_peak(int32_t kind, double *out);
 /* Test hook: y[i] = the kernels' table-based fp64 exp (csrc/snp_math.cuh exp_tbl) of x[i]; device pointers. */
 int snp_debug_exp(const double *x_dev, double *y_dev, int32_t n, void *cuda_stream);
+/* Test hook for the kernels' own fp64 elementary functions (csrc/snp_math.cuh); device pointers, n elements each.
+ * kind 0: out[i] = exp2_scaled(x[i]) = 2^(x[i] / 2048);  1: out[i] = atan2_poly(y[i], x[i]);
+ * 2: out[i] = sin, out[n + i] = cos of x[i] by sincos_bounded (|x| <= pi + 1);  3: out[i] = rsqrt_(x[i]);  4: out[i] = clamp01_(x[i]). */
+int snp_debug_math(int32_t kind, const double *x_dev, const double *y_dev, double *out_dev, int32_t n, void *cuda_stream);
 /* Launch statistics since the last reset: number of kernels this library launched. */
 int64_t snp_launch_count(int32_t reset);
 

@@ -91,6 +91,7 @@ _SIGNATURES = {
                                       c_double, c_int32, c_void_p, c_void_p]),
     "snp_measure_pipe_peak": (ctypes.c_int, [c_int32, ctypes.POINTER(c_double)]),
     "snp_debug_exp": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_void_p]),
+    "snp_debug_math": (ctypes.c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "snp_launch_count": (c_int64, [c_int32]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -73,6 +73,8 @@ def build_variant(tag: str, defines) -> str:
         objs = [o for o, _ in ex.map(lambda s: _compile(s, False, extra, out_dir), _sources())]
     lib = os.path.join(out_dir, "libsnp_b200.so")
     subprocess.run(["nvcc", "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"], check=True)
+    for o in objs:  # only the library travels to the GPU box
+        os.remove(o)
     return lib
 
 

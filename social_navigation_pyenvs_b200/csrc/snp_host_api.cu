@@ -262,6 +262,19 @@ __global__ void k_debug_exp(const double *x, double *y, int n) {
     if (i < n) y[i] = exp_tbl(x[i], tbl);
 }
 
+__global__ void k_debug_math(int kind, const double *x, const double *y, double *out, int n) {
+    __shared__ __align__(16) double tbl[kExpN];
+    exp_table_init(tbl);
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (kind == 0) out[i] = exp2_scaled(x[i], tbl);
+    else if (kind == 1) out[i] = atan2_poly(y[i], x[i]);
+    else if (kind == 2) sincos_bounded(x[i], &out[i], &out[n + i]);
+    else if (kind == 3) out[i] = Real<double>::rsqrt_(x[i]);
+    else out[i] = Real<double>::clamp01_(x[i]);
+}
+
 }  // namespace
 }  // namespace snp
 
@@ -273,6 +286,15 @@ int snp_debug_exp(const double *x_dev, double *y_dev, int32_t n, void *stream) {
     if (!x_dev || !y_dev || n <= 0) { set_error("snp_debug_exp: bad argument"); return SNP_ERR_INVALID; }
     SNP_CUDA_OK(ensure_exp_table());
     k_debug_exp<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x_dev, y_dev, n);
+    count_launch();
+    SNP_CUDA_OK(cudaGetLastError());
+    return SNP_OK;
+}
+
+int snp_debug_math(int32_t kind, const double *x_dev, const double *y_dev, double *out_dev, int32_t n, void *stream) {
+    if (!x_dev || !out_dev || n <= 0 || kind < 0 || kind > 4 || (kind == 1 && !y_dev)) { set_error("snp_debug_math: bad argument"); return SNP_ERR_INVALID; }
+    SNP_CUDA_OK(ensure_exp_table());
+    k_debug_math<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kind, x_dev, y_dev, out_dev, n);
     count_launch();
     SNP_CUDA_OK(cudaGetLastError());
     return SNP_OK;

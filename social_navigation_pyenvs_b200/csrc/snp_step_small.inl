@@ -39,21 +39,26 @@ constexpr int kPairUnroll = SNP_PAIR_UNROLL;
 #endif
 constexpr int kWarpsPerBlock = SNP_WPB;  // warp-packed mapping: warps (= independent env groups) per CTA
 constexpr int kRobotParamWords = 24;  // Params<T> of the robot staged in shared memory (21 values, padded)
-constexpr int kSlotsPerWarp = 64;  // >= epw * (N + 1) for every N <= 32
+// Entity slots of one env group in shared memory.  Warp-packed mapping: [-N, 0) a second copy of the humans, [0, N) the humans,
+// [N] the robot -- so that the partner (i + k) mod N of the halved pair loop is simply slot i - N + k (a pointer that only ever
+// increments; no wrap test, no index arithmetic per pair).  Block-packed mapping: [0, N] only.
+__host__ __device__ inline int group_stride(int N, bool cta) { return cta ? N + 1 : 2 * N + 1; }
+__host__ __device__ inline int slots_per_warp(int N, int epw) { return (epw * (2 * N + 1) + 3) & ~3; }
+constexpr int kGoalCache = 4;  // goal lists up to this length are staged in shared memory (goal switches then cost no global load)
 
 // Byte offsets of the dynamic shared-memory regions (same arithmetic on host and device).
 template <typename T> struct SmemLayout {
-    size_t segs, seg_cnt, ents, rs, red, xchg, tflag, rb, total;
+    size_t segs, seg_cnt, ents, rs, red, xchg, tflag, rb, goals, total;
     int slots;
     __host__ __device__ SmemLayout(int nseg, int seg_groups, int W, int slots_, int red_doubles, int xchg_vec2 = 0, int groups = 0,
-                                   int robot_groups = 0) : slots(slots_) {
+                                   int robot_groups = 0, int goal_vec2 = 0) : slots(slots_) {
         size_t off = sizeof(T) == 8 ? kExpN * sizeof(double) : 0;  // exp table (fp64 only)
         segs = off; off += sizeof(Seg<T>) * (size_t)nseg * seg_groups;
         off = (off + 15) & ~size_t(15);
         seg_cnt = off; off += sizeof(int) * (size_t)(W > 0 ? W : 1) * seg_groups;
         off = (off + 31) & ~size_t(31);
         ents = off; off += sizeof(Ent<T>) * (size_t)slots * 2;
-        rs = off; off += sizeof(T) * (size_t)slots;
+        rs = off; off += sizeof(Vec2<T>) * (size_t)slots;   // r + safety at the stride of the entity planes (.a; .b unused)
         off = (off + 15) & ~size_t(15);
         red = off; off += sizeof(double) * (size_t)red_doubles;
         off = (off + 15) & ~size_t(15);
@@ -61,6 +66,8 @@ template <typename T> struct SmemLayout {
         tflag = off; off += sizeof(int) * (size_t)groups;
         off = (off + 15) & ~size_t(15);
         rb = off; off += sizeof(T) * (size_t)(robot_groups ? kRobotParamWords + robot_groups * SNP_ROBOT_FIELDS : 0);  // robot_mode 2
+        off = (off + 15) & ~size_t(15);
+        goals = off; off += sizeof(Vec2<T>) * (size_t)goal_vec2;  // [G][threads] goal lists (G <= kGoalCache)
         total = off + 16;
     }
 };
@@ -86,11 +93,6 @@ __device__ __forceinline__ double seg_min(double v, int i, int n, unsigned mask)
     return v;
 }
 
-// Social force of one human with every pair of humans evaluated ONCE per warp (newton's third law): in round k lane i
-// evaluates the pair {i, (i+k) mod N}, keeps +f and hands -f to the partner's lane through a warp shuffle, so a crowd of N
-// needs (N-1)/2 evaluations per lane instead of N-1 (for even N the antipodal pair is evaluated by both ends).  Valid when the
-// law is antisymmetric: uniform parameters, and for Moussaid the reference's symmetric path (lower index is agent 1,
-// forces.py:145-151).  Accumulation order differs from the reference's j-ascending order (rounding-level effect only).
 // Segmented max over the lanes [gbase, gbase + n) of a warp, broadcast to every lane of the group.
 template <typename T> __device__ __forceinline__ T seg_max_bcast(T v, int i, int n, int gbase, unsigned mask) {
     for (int off = 1; off < n; off <<= 1) {
@@ -100,77 +102,88 @@ template <typename T> __device__ __forceinline__ T seg_max_bcast(T v, int i, int
     return __shfl_sync(mask, v, gbase);
 }
 
-// One evaluation of the halved loop: lane i against partner p; for Moussaid the lower index is agent 1 (forces.py:145-151).
+// One evaluation of the halved loop: lane i against its partner; for Moussaid the lower index is agent 1 (forces.py:145-151).
 template <typename T, int SOC, bool CONTACT>
-__device__ __forceinline__ T halved_eval(const Params<T> &P, const double *tbl, const Agent<T> &me, const Ent<T> &o, T rsj, bool sw, T &fx, T &fy) {
+__device__ __forceinline__ T halved_eval(const Params<T> &P, const double *tbl, const Agent<T> &me, const Vec2<T> op, const Vec2<T> ov, T rsj, bool sw,
+                                         T &fx, T &fy) {
     if (SOC == 2) {
-        const T rd = pair_eval<T, SOC, CONTACT>(P, tbl, sw ? o.x : me.px, sw ? o.y : me.py, sw ? o.vx : me.vx, sw ? o.vy : me.vy, sw ? rsj : me.rs,
-                                                sw ? me.px : o.x, sw ? me.py : o.y, sw ? me.vx : o.vx, sw ? me.vy : o.vy, sw ? me.rs : rsj, fx, fy);
+        const T rd = pair_eval<T, SOC, CONTACT>(P, tbl, sw ? op.a : me.px, sw ? op.b : me.py, sw ? ov.a : me.vx, sw ? ov.b : me.vy, sw ? rsj : me.rs,
+                                                sw ? me.px : op.a, sw ? me.py : op.b, sw ? me.vx : ov.a, sw ? me.vy : ov.b, sw ? me.rs : rsj, fx, fy);
         fx = sw ? -fx : fx; fy = sw ? -fy : fy;
         return rd;
     }
-    return pair_eval<T, SOC, CONTACT>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rsj, fx, fy);
+    return pair_eval<T, SOC, CONTACT>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, op.a, op.b, ov.a, ov.b, rsj, fx, fy);
 }
 
-// U rounds of the halved loop starting after partner index p / source lane q: the U evaluations are independent and branch-free,
-// so their dependency chains interleave; ONE vote covers the rare contact re-evaluation of all of them.
+// U rounds of the halved loop: partners at pp[0 .. U) (see group_stride: consecutive slots, no wrap), the lanes whose partner is
+// me walk downwards from `src` and wrap at the group's first lane.  The U evaluations are independent and branch-free, so their
+// dependency chains interleave; ONE vote covers the rare contact re-evaluation of all of them (the partners' velocities are only
+// loaded there, except for Moussaid whose law needs them).
 template <typename T, int SOC, int U>
-__device__ __forceinline__ void halved_rounds(const Params<T> &P, const double *tbl, const EntView<T> &ents, const T *rs_g, const Agent<T> &me,
-                                              int i, int N, unsigned wmask, int gbase, int &p, int &q, T &fsx, T &fsy) {
-    Ent<T> o[U];
+__device__ __forceinline__ void halved_rounds(const Params<T> &P, const double *tbl, const Vec2<T> *pp, const Vec2<T> *pv, const Vec2<T> *pr,
+                                              const Agent<T> &me, int k0, int wrap_at, int N, unsigned wmask, int gbase, int &src, T &fsx, T &fsy) {
+    Vec2<T> op[U], ov[U];
     T rsj[U], fx[U], fy[U];
-    int src[U];
-    bool sw[U];
+    int from[U];
     bool contact = false;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        p = (p + 1 == N) ? 0 : p + 1;  // partner (i + k) mod N
-        q = (q == 0) ? N - 1 : q - 1;  // the lane whose partner in this round is me: (i - k) mod N
-        o[u] = ents.get(p);
-        rsj[u] = rs_g[p];
-        src[u] = gbase + q;
-        sw[u] = p < i;
+        op[u] = pp[u];
+        rsj[u] = pr[u].a;
+        ov[u] = SOC == 2 ? pv[u] : Vec2<T>{T(0), T(0)};
+        src = (src == gbase) ? gbase + N - 1 : src - 1;  // the lane whose partner in this round is me: (i - k) mod N
+        from[u] = src;
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) contact |= halved_eval<T, SOC, false>(P, tbl, me, o[u], rsj[u], sw[u], fx[u], fy[u]) > T(0);
+    for (int u = 0; u < U; ++u)
+        contact |= Real<T>::positive_(halved_eval<T, SOC, false>(P, tbl, me, op[u], ov[u], rsj[u], k0 + u >= wrap_at, fx[u], fy[u]));
     if (__any_sync(wmask, contact)) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) halved_eval<T, SOC, true>(P, tbl, me, o[u], rsj[u], sw[u], fx[u], fy[u]);
+        for (int u = 0; u < U; ++u) halved_eval<T, SOC, true>(P, tbl, me, op[u], pv[u], rsj[u], k0 + u >= wrap_at, fx[u], fy[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const T rx = __shfl_sync(wmask, fx[u], src[u]), ry = __shfl_sync(wmask, fy[u], src[u]);
+        const T rx = __shfl_sync(wmask, fx[u], from[u]), ry = __shfl_sync(wmask, fy[u], from[u]);
         fsx += fx[u] - rx; fsy += fy[u] - ry;
     }
 }
 
+// Social force of one human with every pair of humans evaluated ONCE per warp (newton's third law): in round k lane i
+// evaluates the pair {i, (i+k) mod N}, keeps +f and hands -f to the partner's lane through a warp shuffle, so a crowd of N
+// needs (N-1)/2 evaluations per lane instead of N-1 (for even N the antipodal pair is evaluated by both ends).  Valid when the
+// law is antisymmetric: uniform parameters, and for Moussaid the reference's symmetric path (lower index is agent 1,
+// forces.py:145-151).  Accumulation order differs from the reference's j-ascending order (rounding-level effect only).
+// pos / vel / rs16: the env group's planes, index 0 = human 0 (copies at [-N, 0), robot at [N]).
 template <typename T, int SOC>
-__device__ __forceinline__ void social_force_halved(const Params<T> &P, const double *tbl, const EntView<T> ents, const T *rs_g, const Agent<T> &me,
-                                                    int i, int N, bool with_robot, unsigned wmask, int gbase, T &fsx, T &fsy) {
-    int p = i, q = i;
+__device__ __forceinline__ void social_force_halved(const Params<T> &P, const double *tbl, const Vec2<T> *pos, const Vec2<T> *vel, const Vec2<T> *rs16,
+                                                    const Agent<T> &me, int i, int N, bool with_robot, unsigned wmask, int gbase, T &fsx, T &fsy) {
+    const Vec2<T> *pp = pos + (i - N), *pv = vel + (i - N), *pr = rs16 + (i - N);  // slot of (i + k) mod N = pp + k
+    const int wrap_at = N - i;  // rounds k >= wrap_at pair me with a LOWER index
     const int rounds = (N - 1) >> 1;
-    int k = 0;
-    for (; k + kPairUnroll <= rounds; k += kPairUnroll) halved_rounds<T, SOC, kPairUnroll>(P, tbl, ents, rs_g, me, i, N, wmask, gbase, p, q, fsx, fsy);
-    for (; k < rounds; ++k) halved_rounds<T, SOC, 1>(P, tbl, ents, rs_g, me, i, N, wmask, gbase, p, q, fsx, fsy);
+    int src = gbase + i;
+    int k = 1;
+    for (; k + kPairUnroll - 1 <= rounds; k += kPairUnroll)
+        halved_rounds<T, SOC, kPairUnroll>(P, tbl, pp + k, pv + k, pr + k, me, k, wrap_at, N, wmask, gbase, src, fsx, fsy);
+    for (; k <= rounds; ++k) halved_rounds<T, SOC, 1>(P, tbl, pp + k, pv + k, pr + k, me, k, wrap_at, N, wmask, gbase, src, fsx, fsy);
     // tail: the antipodal pair of an even crowd (both ends evaluate it) and the robot, which exerts force but feels none
     // (forces.py:146,151) -- independent evaluations again, one vote
     const bool anti = !(N & 1);
     T fax = T(0), fay = T(0), frx = T(0), fry = T(0);
-    Ent<T> oa{}, orb{};
+    Vec2<T> oa{}, ova{}, orb{}, ovr{};
     T rsa = T(0), rsr = T(0);
-    bool sw = false, contact = false;
+    const bool sw = k >= wrap_at;
+    bool contact = false;
     if (anti) {
-        p = (p + 1 == N) ? 0 : p + 1;
-        oa = ents.get(p); rsa = rs_g[p]; sw = p < i;
-        contact |= halved_eval<T, SOC, false>(P, tbl, me, oa, rsa, sw, fax, fay) > T(0);
+        oa = pp[k]; ova = pv[k]; rsa = pr[k].a;
+        contact |= Real<T>::positive_(halved_eval<T, SOC, false>(P, tbl, me, oa, ova, rsa, sw, fax, fay));
     }
     if (with_robot) {
-        orb = ents.get(N); rsr = rs_g[N];
-        contact |= pair_eval<T, SOC, false>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, orb.x, orb.y, orb.vx, orb.vy, rsr, frx, fry) > T(0);
+        orb = pos[N]; ovr = vel[N]; rsr = rs16[N].a;
+        contact |= Real<T>::positive_(pair_eval<T, SOC, false>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, orb.a, orb.b, ovr.a, ovr.b, rsr, frx, fry));
     }
     if (__any_sync(wmask, contact)) {
-        if (anti) halved_eval<T, SOC, true>(P, tbl, me, oa, rsa, sw, fax, fay);
-        if (with_robot) pair_eval<T, SOC, true>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, orb.x, orb.y, orb.vx, orb.vy, rsr, frx, fry);
+        if (anti) halved_eval<T, SOC, true>(P, tbl, me, oa, ova, rsa, sw, fax, fay);
+        if (with_robot) pair_eval<T, SOC, true>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, orb.a, orb.b, ovr.a, ovr.b, rsr, frx, fry);
     }
     fsx += fax; fsy += fay;
     fsx += frx; fsy += fry;
@@ -278,14 +291,17 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
     // ---- shared memory carve-up: [exp table][segments][segment counts][entities x2][r+safety][reduction scratch] ----
     const int nseg = a.W * a.S;
     const int seg_groups = a.walls_per_env ? groups : 1;
-    const SmemLayout<T> lay(nseg, seg_groups, a.W, CTA ? a.gpb * (N + 1) : kWarpsPerBlock * kSlotsPerWarp, CTA ? a.gpb * N : 0,
-                            (CTA && HALF) ? rounds * a.gpb * N : 0, CTA ? a.gpb : 0, ROBOT2 ? groups : 0);
+    const int spw = slots_per_warp(N, a.epw);  // warp-packed: entity slots per warp
+    const bool gcache = a.G <= kGoalCache;     // goal lists staged in shared memory
+    const SmemLayout<T> lay(nseg, seg_groups, a.W, CTA ? a.gpb * (N + 1) : kWarpsPerBlock * spw, CTA ? a.gpb * N : 0,
+                            (CTA && HALF) ? rounds * a.gpb * N : 0, CTA ? a.gpb : 0, ROBOT2 ? groups : 0, gcache ? a.G * (int)blockDim.x : 0);
     double *exp_tbl_s = reinterpret_cast<double *>(smem_raw);
     Seg<T> *segs_all = reinterpret_cast<Seg<T> *>(smem_raw + lay.segs);
     int *seg_cnt_all = reinterpret_cast<int *>(smem_raw + lay.seg_cnt);
     const int slots = lay.slots;
     Vec2<T> *ents0 = reinterpret_cast<Vec2<T> *>(smem_raw + lay.ents);  // [2 buffers][pos | vel][slots]
-    T *rs_all = reinterpret_cast<T *>(smem_raw + lay.rs);
+    Vec2<T> *rs_all = reinterpret_cast<Vec2<T> *>(smem_raw + lay.rs);
+    Vec2<T> *goal_s = reinterpret_cast<Vec2<T> *>(smem_raw + lay.goals) + threadIdx.x;  // this thread's goal k at goal_s[k * blockDim.x]
     double *red = reinterpret_cast<double *>(smem_raw + lay.red) + (CTA ? g * N : 0);  // block-packed only: this group's [N] doubles
     Vec2<T> *xchg = reinterpret_cast<Vec2<T> *>(smem_raw + lay.xchg) + (CTA ? g * N : 0);
     int *tflag = reinterpret_cast<int *>(smem_raw + lay.tflag);
@@ -318,10 +334,11 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
     __syncthreads();
     if constexpr (!CTA) { if (!live) return; }
 
-    const int gslot = CTA ? g * (N + 1) : ((threadIdx.x >> 5) * kSlotsPerWarp + (g - (threadIdx.x >> 5) * a.epw) * (N + 1));
+    // slot of this group's human 0 (see group_stride)
+    const int gslot = CTA ? g * (N + 1) : ((threadIdx.x >> 5) * spw + (g - (threadIdx.x >> 5) * a.epw) * (2 * N + 1) + N);
     const Seg<T> *segs = segs_all + (a.walls_per_env ? (size_t)g * nseg : 0);
     const int *seg_cnt = seg_cnt_all + (a.walls_per_env ? g * a.W : 0);
-    T *rs_g = rs_all + gslot;
+    Vec2<T> *rs_g = rs_all + gslot;
     const bool leader = live && i == 0;
     const bool has_robot = a.robot != nullptr;
     const long long EN = a.EN;
@@ -352,7 +369,12 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             P = make_params<T>(p);
         }
         agent_static<T>(P, me);
-        rs_g[i] = me.rs;
+        rs_g[i].a = me.rs;
+        if constexpr (!CTA) rs_g[i - N].a = me.rs;
+        if (gcache) {
+            for (int k = 0; k < a.G; ++k)
+                goal_s[(size_t)k * blockDim.x] = Vec2<T>{a.goals[((size_t)k * 2 + 0) * EN + aidx], a.goals[((size_t)k * 2 + 1) * EN + aidx]};
+        }
     } else {
         me = Agent<T>{};
     }
@@ -366,7 +388,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
         rr = a.robot[SNP_ROBOT_R * E + env]; rrs = rr + a.robot[SNP_ROBOT_SAFETY * E + env];
         rgx = a.robot[SNP_ROBOT_GX * E + env]; rgy = a.robot[SNP_ROBOT_GY * E + env];
         if (a.action) { ax = a.action[env]; ay = a.action[E + env]; }
-        if (leader) rs_g[N] = rrs;
+        if (leader) rs_g[N].a = rrs;
         if constexpr (ROBOT2) if (leader) {  // the robot's full state lives in shared memory (one lane updates it)
 #pragma unroll
             for (int f = 0; f < SNP_ROBOT_FIELDS; ++f) rb[f] = a.robot[(size_t)f * E + env];
@@ -425,8 +447,12 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
     // ---- fused sub-steps ----
     bool touched = false;
     const T dt = a.dt;
+    // every squared distance that can round to a touching distance lies below (r + r_robot)^2 (1 + 2^-48)
+    const double touch_thr = __dadd_rn((double)me.r, (double)rr);
+    const double touch_hi = touch_thr * touch_thr * (1.0 + 3.5527136788005009e-15);
     for (int s = 0; s < a.n_substeps; ++s) {
         const EntView<T> ents{ents0 + (size_t)(s & 1) * 2 * slots + gslot, ents0 + (size_t)(s & 1) * 2 * slots + slots + gslot};
+        if constexpr (!CTA) { if (live) ents.put(i - N, me.px, me.py, me.vx, me.vy); }  // second copy: the halved loop's wrap-free run
         if (a.robot_mode == 1 && has_robot) {  // robot_agent.py:126-131 (holonomic): p = p + a*dt ; v = a
             if (sizeof(T) == 8) { rpx = (T)__dadd_rn((double)rpx, __dmul_rn((double)ax, (double)dt)); rpy = (T)__dadd_rn((double)rpy, __dmul_rn((double)ay, (double)dt)); }
             else { rpx = rpx + ax * dt; rpy = rpy + ay * dt; }
@@ -491,18 +517,23 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
 
         T fox = T(0), foy = T(0), fsx = T(0), fsy = T(0);
         if (live) {
-            // goal switching (mmm:66-70 '<', fp:226 '<=')
+            // goal switching (mmm:66-70 '<', fp:226 '<=') and the desired force (forces.py:9-16) share the goal vector: both are
+            // evaluated at the position the sub-step starts from
             {
-                const T dg = np_norm(me.gx - me.px, me.gy - me.py);
-                if (a.numba ? (dg <= me.r) : (dg < me.r)) {
+                GoalVec<T> gv = goal_vec<T>(me);
+                if (a.numba ? (gv.dist <= me.r) : (gv.dist < me.r)) {
                     gidx = (gidx + 1 >= gcnt) ? 0 : gidx + 1;
-                    me.gx = a.goals[((size_t)gidx * 2 + 0) * EN + aidx]; me.gy = a.goals[((size_t)gidx * 2 + 1) * EN + aidx];
+                    T ngx, ngy;
+                    if (gcache) { const Vec2<T> ng = goal_s[(size_t)gidx * blockDim.x]; ngx = ng.a; ngy = ng.b; }
+                    else { ngx = a.goals[((size_t)gidx * 2 + 0) * EN + aidx]; ngy = a.goals[((size_t)gidx * 2 + 1) * EN + aidx]; }
+                    if (ngx != me.gx || ngy != me.gy) { me.gx = ngx; me.gy = ngy; gv = goal_vec<T>(me); }
                 }
+                desired_force<T>(P, me, gv, a.numba != 0);
             }
             // wall force
             if (a.W > 0) obstacle_force<T, OBS>(P, exp_tbl_s, wmask, segs, seg_cnt, a.W, a.S, a.numba != 0, me.px, me.py, me.vx, me.vy, me.rs, fox, foy);
             if constexpr (HALF && !CTA) {
-                social_force_halved<T, SOC>(P, exp_tbl_s, ents, rs_g, me, i, N, a.consider_robot != 0, wmask, lane - i, fsx, fsy);
+                social_force_halved<T, SOC>(P, exp_tbl_s, ents.pos, ents.vel, rs_g, me, i, N, a.consider_robot != 0, wmask, lane - i, fsx, fsy);
             } else if constexpr (HALF && CTA) {
                 // Block-packed halved loop, phase 1: lane i evaluates the pairs {i, (i+k) mod N}, k = 1..rounds, keeps +f and
                 // leaves -f for the partner in plane k of the exchange buffer (written at the PARTNER's slot: conflict-free).
@@ -512,7 +543,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
                 for (int k = 0; k < rounds; ++k) {
                     pidx = (pidx + 1 == N) ? 0 : pidx + 1;
                     const Ent<T> o = ents.get(pidx);
-                    const T rsj = rs_g[pidx];
+                    const T rsj = rs_g[pidx].a;
                     T fx, fy;
                     if (SOC == 2) {
                         const bool sw = pidx < i;  // the lower index is agent 1 (forces.py:145-151)
@@ -528,7 +559,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
                 if (!(N & 1)) {  // antipodal pair: both ends evaluate it
                     pidx = (pidx + 1 == N) ? 0 : pidx + 1;
                     const Ent<T> o = ents.get(pidx);
-                    const T rsj = rs_g[pidx];
+                    const T rsj = rs_g[pidx].a;
                     T fx, fy;
                     if (SOC == 2) {
                         const bool sw = pidx < i;
@@ -543,7 +574,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
                 if (a.consider_robot) {
                     const Ent<T> o = ents.get(N);
                     T fx, fy;
-                    pair_force<T, SOC>(P, exp_tbl_s, wmask, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rs_g[N], fx, fy);
+                    pair_force<T, SOC>(P, exp_tbl_s, wmask, me.px, me.py, me.vx, me.vy, me.rs, o.x, o.y, o.vx, o.vy, rs_g[N].a, fx, fy);
                     fsx += fx; fsy += fy;
                 }
             } else {
@@ -553,7 +584,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
 #pragma unroll 2
                 for (int j = 0; j < M; ++j) {
                     const Ent<T> o = ents.get(j);
-                    const T rsj = rs_g[j];
+                    const T rsj = rs_g[j].a;
                     T fx, fy;
                     if (SOC == 2) {
                         // symmetric path: the pair is evaluated once with the LOWER index as agent 1 and applied with a minus
@@ -582,7 +613,6 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             }
         }
         if (live) {
-            desired_force<T>(P, me, a.numba != 0);
             integrate<T, HEADED>(P, me, fox, foy, fsx, fsy, dt);
         }
         if constexpr (!CTA) {
@@ -611,6 +641,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
                             const_cast<T *>(a.goals)[(size_t)0 * EN + aidx] = me.gx;
                             const_cast<T *>(a.goals)[(size_t)1 * EN + aidx] = me.gy;
                             const_cast<int *>(a.goal_cnt)[aidx] = 1;
+                            if (gcache) goal_s[0] = Vec2<T>{me.gx, me.gy};
                         }
                         unsigned clear = 0;  // every group retires its lowest pending index
                         for (unsigned rest = pending; rest;) {
@@ -625,8 +656,13 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             }
         }
         if (live) {
-            if (a.track_touch && has_robot)
-                touched |= xnorm_np((double)me.px - (double)rpx, (double)me.py - (double)rpy) < __dadd_rn((double)me.r, (double)rr);
+            if (a.track_touch && has_robot) {
+                // ||p - p_robot|| < r + r_robot (robot_agent.py:37), decided on the square whenever that is safe: the IEEE square
+                // root only runs for lanes within 2^-48 (relative) of touching or beyond, which is rare
+                const double tx = (double)me.px - (double)rpx, ty = (double)me.py - (double)rpy;
+                const double t2 = __fma_rn(ty, ty, __dmul_rn(tx, tx));
+                if (t2 < touch_hi) touched |= sqrt(t2) < __dadd_rn((double)me.r, (double)rr);
+            }
         }
         if (a.time_now) tnow = __dadd_rn(tnow, a.dt_d);
     }
@@ -732,7 +768,8 @@ int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
         const int epb = a.epw * kWarpsPerBlock;
         grid = dim3((unsigned)((a.E + epb - 1) / epb));
         block = dim3(kWarpsPerBlock * 32);
-        smem = SmemLayout<T>(nseg, a.walls_per_env ? epb : 1, a.W, kWarpsPerBlock * kSlotsPerWarp, 0, 0, 0, a.robot_mode == 2 ? epb : 0).total;
+        smem = SmemLayout<T>(nseg, a.walls_per_env ? epb : 1, a.W, kWarpsPerBlock * slots_per_warp(a.N, a.epw), 0, 0, 0, a.robot_mode == 2 ? epb : 0,
+                             a.G <= kGoalCache ? a.G * kWarpsPerBlock * 32 : 0).total;
     } else {
         a.epw = 1;
         a.gpb = gpb;
@@ -741,7 +778,7 @@ int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
         const int rounds = (a.N - 1) >> 1;
         if (half && sizeof(Vec2<T>) * (size_t)rounds * gpb * a.N > 64 * 1024) half = false;  // exchange planes would not fit: ordered loop
         smem = SmemLayout<T>(nseg, a.walls_per_env ? gpb : 1, a.W, gpb * (a.N + 1), gpb * a.N, half ? rounds * gpb * a.N : 0, gpb,
-                             a.robot_mode == 2 ? gpb : 0).total;
+                             a.robot_mode == 2 ? gpb : 0, a.G <= kGoalCache ? a.G * block_threads : 0).total;
     }
     if (smem > 200 * 1024) { set_error("wall/segment tables need %zu bytes of shared memory (limit 200 KiB)", smem); return SNP_ERR_UNSUPPORTED; }
 #define SNP_LAUNCH2(CTA_, PA_, HALF_, R2_)                                                                             \
