@@ -54,9 +54,9 @@ __device__ __forceinline__ T pair_eval(const Params<T> &P, const double *tbl, T 
     const T inv = R::rsqrt_(d2);
     const T rd = fma_<T>(-d2, inv, rs1 + rs2);
     if (SOC < 2) {
-        const T cn = R::exp2s_(fma_<T>(rd, P.kBi, P.lAi), tbl) * inv;
+        const T cn = R::exp2s_times_(fma_<T>(rd, P.kBi, P.lAi), inv, tbl);
         if (SOC == 1) {
-            const T ct = R::exp2s_(fma_<T>(rd, P.kDi, P.lCi), tbl) * inv;
+            const T ct = R::exp2s_times_(fma_<T>(rd, P.kDi, P.lCi), inv, tbl);
             fx = fma_<T>(cn, dx, -(ct * dy));
             fy = fma_<T>(cn, dy, ct * dx);
         } else {
@@ -165,14 +165,14 @@ __device__ __forceinline__ void obstacle_force(const Params<T> &P, const double 
         const T inv = R::rsqrt_(d2);
         const T rd = fma_<T>(-d2, inv, rs);
         const bool contact = __any_sync(vote_mask, R::positive_(rd));  // compression / friction terms only when some lane touches the wall
-        const T cn = R::exp2s_(fma_<T>(rd, P.kBw, P.lAw), tbl) * inv;
+        const T cn = R::exp2s_times_(fma_<T>(rd, P.kBw, P.lAw), inv, tbl);
         if (OBS == 0 && !contact) {
             fx = fma_<T>(cn, dx, fx); fy = fma_<T>(cn, dy, fy);
         } else {
             const T prd = contact ? max0(rd) * inv : T(0);
-            const T dvi = (vx * dy - vy * dx) * inv * inv;  // (delta_v / d),  delta_v = -(v . t),  t = (-dy, dx) / d
+            // delta_v = -(v . t) = (vx dy - vy dx) / d,  t = (-dy, dx) / d
             T ct = -(P.k2 * prd) * (vx * dy - vy * dx) * inv;
-            if (OBS == 1) ct = fma_<T>(-R::exp2s_(fma_<T>(rd, P.kDw, P.lCw), tbl), dvi, ct);
+            if (OBS == 1) ct = fma_<T>(-R::exp2s_times_(fma_<T>(rd, P.kDw, P.lCw), inv * inv, tbl), vx * dy - vy * dx, ct);
             const T en = fma_<T>(P.k1, prd, cn);
             fx += fma_<T>(en, dx, -(ct * dy));
             fy += fma_<T>(en, dy, ct * dx);

@@ -22,7 +22,7 @@ namespace {
 // Resident CTAs per SM the compiler must allow for (register cap = 65536 / (128 threads * min blocks)); tuned on B200, see
 // profiles/.  Overridable at build time for experiments.
 #ifndef SNP_MINB_F32
-#define SNP_MINB_F32 5
+#define SNP_MINB_F32 7  // 72 registers: 28 warps per SM, i.e. the 4096 warps of the 4096 x 25 workload are resident in ONE wave
 #endif
 #ifndef SNP_MINB_F64
 #define SNP_MINB_F64 4
@@ -30,7 +30,7 @@ namespace {
 
 // Pair evaluations of the halved loop issued together (independent, branch-free dependency chains per warp; see halved_rounds).
 #ifndef SNP_PAIR_UNROLL
-#define SNP_PAIR_UNROLL 2
+#define SNP_PAIR_UNROLL 3  // measured on B200 (4096 x 25): fp64 2 / 3 / 4 -> 0.229 / 0.2215 / 0.2216 ms, fp32 at 72 registers 0.129 / 0.126 / -
 #endif
 
 constexpr int kPairUnroll = SNP_PAIR_UNROLL;
