@@ -20,15 +20,18 @@ void set_error(const char *fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-int device_sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+int device_sm_count() {  // SM count of the CURRENT device (cached per device: one process may drive several)
+    static std::atomic<int> sms[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool cacheable = dev >= 0 && dev < 64;
+    int n = cacheable ? sms[dev].load(std::memory_order_relaxed) : 0;
+    if (n <= 0) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+        if (cacheable) sms[dev].store(n, std::memory_order_relaxed);
     }
-    return sms;
+    return n;
 }
 
 template <typename T> static int build_args(const snp_crowd *c, const snp_step_opts *o, KArgs<T> &a) {
@@ -73,6 +76,24 @@ template <typename T> static int build_args(const snp_crowd *c, const snp_step_o
     if (a.robot_every < 0 || (a.robot_every > 1 && o->robot_phase < 0)) { set_error("robot_every / robot_phase must be >= 0"); return SNP_ERR_INVALID; }
     if (o->dyn_out && (o->respawn || o->robot_mode == 2)) { set_error("dyn_out (peek) cannot be combined with respawn or robot_mode 2"); return SNP_ERR_INVALID; }
     return SNP_OK;
+}
+
+// Device-side alias of a pinned host buffer (cudaHostAlloc / cudaHostRegister memory is mapped under unified addressing), or
+// nullptr for pageable memory.
+static void *device_alias(const void *host_ptr) {
+    if (!host_ptr) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+template <typename T>
+static int gym_step_zero_copy(const snp_crowd *crowd, const snp_step_opts *opts, void *obs_dev, int32_t *flags_dev, double *checks_dev, cudaStream_t st) {
+    KArgs<T> a;
+    const int rc = build_args<T>(crowd, opts, a);
+    if (rc) return rc;
+    a.obs_out = (T *)obs_dev; a.flags2 = flags_dev; a.checks2 = checks_dev;
+    return launch_step_small<T>(a, opts->type, st);
 }
 
 }  // namespace snp
@@ -127,6 +148,21 @@ int snp_gym_step_host(const snp_crowd *crowd, const snp_step_opts *opts, const v
     const size_t w = crowd->dtype == SNP_F64 ? 8 : 4;
     const size_t E = (size_t)crowd->E, EN = E * (size_t)crowd->N;
     if (action_host) SNP_CUDA_OK(cudaMemcpyAsync(const_cast<void *>(opts->action), action_host, 2 * E * w, cudaMemcpyHostToDevice, st));
+    // Pinned result buffers: the kernel's store phase writes observation / flags / checks straight into them (posted PCIe writes,
+    // overlapped with the CTAs still computing), so the only host-side cost after the launch is the synchronisation.  Pageable
+    // buffers take the staged path below (D2H copies after the kernel).
+    void *obs_dev = device_alias(obs_host);
+    int32_t *flags_dev = (int32_t *)device_alias(flags_host);
+    double *checks_dev = (double *)device_alias(checks_host);
+    const bool zero_copy = opts->n_substeps > 0 && !opts->dyn_out && (!obs_host || obs_dev) && (!flags_host || flags_dev) && (!checks_host || checks_dev) &&
+                           (obs_host || flags_host || checks_host) && (crowd->dtype == SNP_F64 || crowd->dtype == SNP_F32) && !(opts->reserved & 16);
+    if (zero_copy) {
+        const int rc = crowd->dtype == SNP_F64 ? gym_step_zero_copy<double>(crowd, opts, obs_dev, flags_dev, checks_dev, st)
+                                               : gym_step_zero_copy<float>(crowd, opts, obs_dev, flags_dev, checks_dev, st);
+        if (rc) return rc;
+        SNP_CUDA_OK(cudaStreamSynchronize(st));
+        return SNP_OK;
+    }
     const int rc = snp_step(crowd, opts, stream);
     if (rc) return rc;
     // px, py, vx, vy are the first four fields of dyn: one contiguous block

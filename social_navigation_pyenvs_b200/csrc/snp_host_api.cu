@@ -152,8 +152,10 @@ int update_host(int type, int E, int N, int G, double *agents_state, double *goa
         count_launch();
         SNP_CUDA_OK(cudaMemcpyAsync(desired_force, ws.aos.p, (size_t)EN * 2 * 8, cudaMemcpyDeviceToHost, st));
     }
+    SNP_CUDA_OK(cudaStreamSynchronize(st));
     // in-place side effects of the reference on its INPUT array (fp:254-256): linear velocity of headed agents
-    // becomes R(theta) bv (old theta, old bv); done on the host while the GPU works.
+    // becomes R(theta) bv (old theta, old bv).  After the synchronisation: with pinned host memory the upload of agents_state is
+    // asynchronous, so the rows must not change while it may still be in flight.  (out_state == agents_state is rejected above.)
     if (type >= 3) {
         for (int e = 0; e < E; ++e)
             for (int i = 0; i < N; ++i) {
@@ -163,7 +165,6 @@ int update_host(int type, int E, int N, int G, double *agents_state, double *goa
                 r[4] = sn * r[5] + cs * r[6];
             }
     }
-    SNP_CUDA_OK(cudaStreamSynchronize(st));
     if (G > 16) {  // long goal lists: rotate on the host
         std::vector<double> tmp(2 * (size_t)G);
         for (long long a = 0; a < EN; ++a) {
@@ -308,6 +309,7 @@ int snp_update_humans_parallel_host(int32_t type, int32_t E, int32_t N, int32_t 
     if (E <= 0 || N <= 0 || G <= 0) { set_error("E, N, G must be positive"); return SNP_ERR_INVALID; }
     if (!agents_state || !goals || !agents_params || !safety_space || !out_state) { set_error("null array"); return SNP_ERR_INVALID; }
     if (n_substeps < 1) { set_error("n_substeps must be >= 1"); return SNP_ERR_INVALID; }
+    if (out_state == agents_state) { set_error("out_state must not alias agents_state (the reference returns a new array, forces_parallel.py:214)"); return SNP_ERR_INVALID; }
     if (dtype == SNP_F64)
         return update_host<double>(type, E, N, G, agents_state, goals, obstacles, W, S, agents_params, dt, safety_space, all_params_equal,
                                    last_is_robot, numba_compat, n_substeps, desired_force, out_state);

@@ -53,6 +53,11 @@ template <typename T> struct KArgs {
     T *dyn_out;  // peek: updated pose / velocities are written here instead of in place (goal index untouched)
     int robot_every, robot_phase;  // robot_mode 2: SocialNavSim.update schedule (0 = imitation-learning order), see snp_step_opts
     T robot_dt;  // consts[5] in the crowd's dtype
+    // snp_gym_step_host with pinned (device-mapped) host buffers: the store phase writes the observation (px, py, vx, vy planes),
+    // flags and checks STRAIGHT into host memory -- posted PCIe writes that overlap the rest of the launch; no D2H copy follows
+    T *obs_out = nullptr;
+    int *flags2 = nullptr;
+    double *checks2 = nullptr;
 };
 
 // Host-side launchers implemented per translation unit.

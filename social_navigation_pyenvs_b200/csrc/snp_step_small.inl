@@ -720,6 +720,10 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
         }
         if (!a.dyn_out) a.goal_idx[aidx] = gidx;
         else if (a.goal_idx_out) a.goal_idx_out[aidx] = gidx;
+        if (a.obs_out) {  // the caller's pinned observation buffer [4][E*N]
+            a.obs_out[0 * EN + aidx] = me.px; a.obs_out[1 * EN + aidx] = me.py;
+            a.obs_out[2 * EN + aidx] = me.vx; a.obs_out[3 * EN + aidx] = me.vy;
+        }
     }
     if (leader) {
         if (has_robot && a.robot_mode == 1) {
@@ -736,9 +740,14 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
         }
         if (a.time_now) a.time_now[env] = tnow;
         if (a.flags) a.flags[env] = flags;
+        if (a.flags2) a.flags2[env] = flags;
         if (a.checks) {
             a.checks[env * 4 + 0] = out_dmin; a.checks[env * 4 + 1] = out_reward;
             a.checks[env * 4 + 2] = out_admin; a.checks[env * 4 + 3] = 0.0;
+        }
+        if (a.checks2) {
+            a.checks2[env * 4 + 0] = out_dmin; a.checks2[env * 4 + 1] = out_reward;
+            a.checks2[env * 4 + 2] = out_admin; a.checks2[env * 4 + 3] = 0.0;
         }
     }
 }
@@ -761,6 +770,10 @@ int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
     bool cta = a.N > 32;
     if (a.mapping == 1 && a.N <= 32) cta = false;
     if (a.mapping == 2) cta = true;
+    if (a.respawn && cta) {  // the parallel-traffic respawn (mmm:407-422) lives in the warp-packed mapping only
+        if (a.N <= 32) cta = false;
+        else { set_error("parallel-traffic respawn supports at most 32 humans per env (got %d)", a.N); return SNP_ERR_UNSUPPORTED; }
+    }
     dim3 grid, block;
     size_t smem;
     if (!cta) {

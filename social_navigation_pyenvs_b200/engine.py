@@ -69,6 +69,7 @@ class CrowdEngine:
         # j-ascending order, the reference's own accumulation order (forces.py:145-151).  Same result up to rounding.
         self.full_pair_loop = bool(full_pair_loop)
         self.robot_type, self.robot_params = None, None  # set_robot_motion_model
+        self.safety_space = None                         # set_safety_space
         self.respawn_envs = None    # optional int32 [E]: which envs respawn (hybrid scenario); None = all
         self.respawn_bounds = None  # (traffic_length/2, traffic_height/2): parallel-traffic respawn after every update (mmm:407-422)
         self.mapping = 0  # 0 auto, 1 force warp-packed, 2 force block-packed thread mapping (tests / tuning)
@@ -213,6 +214,8 @@ class CrowdEngine:
         self.robot_type, self.robot_params = SFMS.index(title), model_parameters(title)
         if goals is not None:
             self.set_robot_goals(goals)
+        if getattr(self, "safety_space", None) is not None:  # a safety space set earlier now covers the robot too (mmm:159-162)
+            self.set_safety_space(self.safety_space)
 
     def set_robot_goals(self, goals):
         g = np.asarray(goals, np.float64).reshape(self.E, -1, 2)
@@ -298,11 +301,14 @@ class CrowdEngine:
         L.check(self.lib.snp_step(ctypes.byref(self._crowd()), ctypes.byref(o), _stream()))
 
     def step_host(self, action_host, obs_host, flags_host, checks_host, dt=0.0125, n_substeps=20, pre_checks=True, post_checks=False,
-                  track_touch=False):
+                  track_touch=False, staged=False):
         """The same gym step through ONE C-ABI call with host buffers (snp_gym_step_host): `action_host` [2,E] is copied in, the
-        fused step runs, observation [4,E,N] (px,py,vx,vy), flags [E] int32 and checks [E,4] float64 are copied back and the stream
-        is synchronised.  The buffers are CPU tensors (pinned for asynchronous copies) or NumPy arrays of the engine's dtype."""
+        fused step runs, observation [4,E,N] (px,py,vx,vy), flags [E] int32 and checks [E,4] float64 land in the host buffers and the
+        stream is synchronised.  The buffers are CPU tensors or NumPy arrays of the engine's dtype.  PINNED result buffers are written
+        by the kernel itself (zero-copy: no D2H transfer after the launch); pageable ones -- or staged=True -- get D2H copies."""
         o = self._opts(dt, n_substeps, robot_mode=1, pre_checks=pre_checks, post_checks=post_checks, track_touch=track_touch, advance_time=True)
+        if staged:
+            o.reserved |= 16
         hp = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr() if torch.is_tensor(t) else t.ctypes.data)
         L.check(self.lib.snp_gym_step_host(ctypes.byref(self._crowd()), ctypes.byref(o), hp(action_host), hp(obs_host), hp(flags_host),
                                            hp(checks_host), _stream()))
@@ -493,7 +499,11 @@ class CrowdEngine:
         return self._rotated, self._rewards
 
     def set_safety_space(self, safety_space):
-        """motion_model_manager.py:147-164: humans (and a visible robot) get 0.01 + safety_space."""
-        self.stat[L.STAT_SAFETY].fill_(0.01 + safety_space)
-        if self.robot is not None and self.consider_robot:
-            self.robot[L.ROBOT_SAFETY].fill_(0.01 + safety_space)
+        """motion_model_manager.py:147-164: every human gets 0.01 + safety_space; the robot gets it only when it is driven by an
+        SFM / HSFM model (robot_motion_model_title, set_robot_motion_model) -- visible or not -- and keeps 0 otherwise.
+        None clears both (what a fresh MotionModelManager has)."""
+        self.safety_space = safety_space
+        value = 0.0 if safety_space is None else 0.01 + safety_space
+        self.stat[L.STAT_SAFETY].fill_(value)
+        if self.robot is not None:
+            self.robot[L.ROBOT_SAFETY].fill_(value if self.robot_type is not None else 0.0)

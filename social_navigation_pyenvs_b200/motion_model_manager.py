@@ -60,7 +60,7 @@ class MotionModelManager:
         # (model parameters are identical for every human, agent.py:79-243)
         n = len(self.humans)
         self.all_equal_humans = True if n < 2 else (self.humans[-2].radius == self.humans[-1].radius and self.humans[-2].mass == self.humans[-1].mass)
-        self._engine = None
+        self._engine, self._engine_key = None, None
 
     def _goal_rows(self):
         g = max(len(h.goals) for h in self.humans)
@@ -83,10 +83,15 @@ class MotionModelManager:
         goals = self._goal_rows()
         dt = torch.float64 if self._dtype == "float64" else torch.float32
         eng = self._engine
-        if eng is None or eng.N != len(self.humans) or eng.G != goals.shape[2]:
-            eng = CrowdEngine.from_reference_arrays(self.motion_model_title, rows, goals, walls=_walls_array(self.walls), safety=safety,
+        walls = _walls_array(self.walls)
+        # everything the engine was built from is part of the reuse key: changing consider_robot, all_equal_humans or the walls after
+        # construction rebuilds it instead of being silently ignored
+        key = (len(self.humans), goals.shape[2], self.motion_model_title, bool(self.consider_robot), bool(self.all_equal_humans), dt,
+               None if walls is None else walls.tobytes())
+        if eng is None or key != self._engine_key:
+            eng = CrowdEngine.from_reference_arrays(self.motion_model_title, rows, goals, walls=walls, safety=safety,
                                                     consider_robot=self.consider_robot, all_params_equal=self.all_equal_humans, dtype=dt)
-            self._engine = eng
+            self._engine, self._engine_key = eng, key
         else:
             eng.load_rows(rows, safety)
             eng.load_goals(goals)

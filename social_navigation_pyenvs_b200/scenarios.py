@@ -77,6 +77,11 @@ def _cc_sample(rs, humans_pos, static_upto, i, radius, des_speed, r_i, radii, ro
         return pos, angle
 
 
+def _env_seed(seed0, e):
+    """Seed of env e: seed0 + e, or seed0[e] when the caller passes one seed per env (a case counter that wraps inside the batch)."""
+    return int(seed0[e]) if np.ndim(seed0) else int(seed0) + e
+
+
 def _map_envs(fn, E, args):
     """Run fn(e, *args) for every env, on all host cores when the batch is large (scenario generation is host-side setup)."""
     if E < 256:
@@ -99,7 +104,7 @@ def _attributes(rs, N, randomize):
 
 
 def _cc_env(e, N, seed0, circle_radius, robot_radius, mass, randomize_attributes=False):
-    rs = np.random.RandomState(seed0 + e)
+    rs = np.random.RandomState(_env_seed(seed0, e))
     st, gl = np.zeros((N, 13)), np.zeros((N, 2, 2))
     vd, radii = _attributes(rs, N, randomize_attributes)
     pos_list = []
@@ -132,7 +137,7 @@ def robot_rows(E, circle_radius=7.0, robot_radius=0.3, velocity=(0.0, 1.0)):
 
 
 def _ccso_env(e, N, seed0, circle_radius, robot_radius, mass):
-    rs = np.random.RandomState(seed0 + e)
+    rs = np.random.RandomState(_env_seed(seed0, e))
     st, gl = np.zeros((N, 13)), np.zeros((N, 2, 2))
     inner = circle_radius - 3.0
     radii = [1 + (rs.random_sample() - 1) * 0.4 for _ in range(3)] + [0.3] * (N - 3)
@@ -168,7 +173,7 @@ def ccso_synthetic(E, N=25, seed0=2000, circle_radius=7.0, robot_radius=0.3, mas
 def _ccso_ref_env(e, N, seed0, circle_radius, robot_radius, mass):
     """generate_circular_crossing_with_static_obstacles (social_nav_sim.py:364-431), insert_robot=True: humans 0-2 static on the
     inner circle R-3, the others in angular slots (pi / int(N/2)) (0.5 + 2i + noise) of the circle R."""
-    rs = np.random.RandomState(seed0 + e)
+    rs = np.random.RandomState(_env_seed(seed0, e))
     st, gl = np.zeros((N, 13)), np.zeros((N, 2, 2))
     inner = circle_radius - 3.0
     radii = [(1 + (rs.random_sample() - 1) * 0.4) if i < 3 else 0.3 for i in range(N)]
@@ -216,7 +221,7 @@ def circular_crossing_with_static_obstacles(E, N, seed0=2000, circle_radius=7.0,
 
 
 def _pt_env(e, N, seed0, traffic_length, traffic_height, robot_radius, mass, randomize_attributes=False):
-    rs = np.random.RandomState(seed0 + e)
+    rs = np.random.RandomState(_env_seed(seed0, e))
     st, gl = np.zeros((N, 13)), np.zeros((N, 1, 2))
     robot_pos = np.array([-(traffic_length / 2) + 1, 0.0])
     vd, radii = _attributes(rs, N, randomize_attributes)

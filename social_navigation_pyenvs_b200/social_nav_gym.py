@@ -24,6 +24,8 @@ class BatchedSocialNavGym:
         self.engine = None
         self.safety_space = 0
         self.case_counter = {"train": 0, "test": 0, "val": 0}
+        # social_nav_gym.py:74-76: the counter wraps at case_size (val_size / test_size of env.config; train never wraps in practice)
+        self.case_size = {"train": int(np.iinfo(np.uint32).max) - 2000, "val": 100, "test": 500}
         # crowd_nav/configs/env.config defaults
         self.time_limit, self.time_step, self.robot_time_step = 50, 0.0125, 0.25
         self.success_reward, self.collision_penalty, self.discomfort_dist, self.discomfort_penalty_factor = 1.0, -0.25, 0.2, 0.5
@@ -40,6 +42,7 @@ class BatchedSocialNavGym:
         """config: a configparser object with the reference's sections (social_nav_gym.py:59-84) or a flat dict."""
         if hasattr(config, "getfloat"):
             self.time_limit = config.getint("env", "time_limit")
+            self.case_size["val"], self.case_size["test"] = config.getint("env", "val_size"), config.getint("env", "test_size")
             self.time_step, self.robot_time_step = config.getfloat("env", "time_step"), config.getfloat("env", "robot_time_step")
             self.success_reward, self.collision_penalty = config.getfloat("reward", "success_reward"), config.getfloat("reward", "collision_penalty")
             self.discomfort_dist = config.getfloat("reward", "discomfort_dist")
@@ -72,11 +75,15 @@ class BatchedSocialNavGym:
             self.case_counter[phase] = test_case
         offset = {"train": 2000, "val": 0, "test": 1000}[phase]                  # social_nav_gym.py:135
         sim = self.test_sim if phase == "test" else self.train_val_sim
-        seed0 = offset + self.case_counter[phase]
+        # env e plays case (counter + e) mod case_size: the reference's counter, advanced once per env (social_nav_gym.py:197)
+        cases = (self.case_counter[phase] + np.arange(self.E, dtype=np.int64)) % self.case_size[phase]
+        seed0 = offset + cases
         if on_device:
-            return self._reset_on_device(sim, seed0, phase)
+            return self._reset_on_device(sim, 0, phase, seeds=seed0)
         if sim == "hybrid_scenario":
             raise NotImplementedError("the hybrid scenario is generated on the device only (reset(on_device=True))")
+        if self.randomize_attributes and sim != "circle_crossing":
+            raise NotImplementedError("randomize_attributes on the host path covers circle_crossing only (use reset(on_device=True))")
         if sim == "circle_crossing":
             sc = scenarios.circular_crossing(self.E, self.human_num, seed0, self.circle_radius, self.robot_radius,
                                              randomize_attributes=self.randomize_attributes)
@@ -89,7 +96,7 @@ class BatchedSocialNavGym:
             sc = scenarios.parallel_traffic(self.E, self.human_num, seed0, self.traffic_length, self.traffic_height, self.robot_radius)
         else:
             raise NotImplementedError(f"scenario {sim}: the hybrid scenario mixes generators per env (social_nav_gym.py:155-167)")
-        self.case_counter[phase] += self.E
+        self.case_counter[phase] = (self.case_counter[phase] + self.E) % self.case_size[phase]
         robot = sc["robot"].copy()
         # robot goal list of the reference scenarios: [goal, start] (social_nav_sim.py:237,309)
         self._robot_goals = np.stack([robot[:, 10:12], robot[:, 0:2]], 1)
@@ -118,11 +125,11 @@ class BatchedSocialNavGym:
                          circle_radius=self.circle_radius, robot_radius=self.robot_radius, traffic_length=self.traffic_length,
                          traffic_height=self.traffic_height)
         if mask is None:
-            self.case_counter[phase] += self.E
-        if self.safety_space > 0:
-            e.set_safety_space(self.safety_space)
-        elif fresh:
-            e.stat[L.STAT_SAFETY].zero_()
+            self.case_counter[phase] = (self.case_counter[phase] + self.E) % self.case_size[phase]
+        # always rewritten: snp_reset keeps the safety columns, so a safety space from an earlier episode must not survive (gym:215)
+        if self.robot_motion_model_title is not None and e.robot_type is None:
+            e.set_robot_motion_model(self.robot_motion_model_title)
+        e.set_safety_space(self.safety_space if self.safety_space > 0 else None)
         # robot goal list of the reference scenarios: [goal, start] (social_nav_sim.py:237,309)
         r = e.robot
         self._robot_goals = torch.stack([torch.stack([r[L.ROBOT_GX], r[L.ROBOT_GY]], -1), torch.stack([r[L.ROBOT_GX2], r[L.ROBOT_GY2]], -1)], 1).double().cpu().numpy()
@@ -136,11 +143,11 @@ class BatchedSocialNavGym:
         fin = torch.as_tensor(finished, device=self.device).bool()
         offset = {"train": 2000, "val": 0, "test": 1000}[phase]
         order = torch.cumsum(fin.int(), 0) - 1
-        seeds = (offset + self.case_counter[phase] + order).to(torch.int32)
+        seeds = (offset + (self.case_counter[phase] + order.long()) % self.case_size[phase]).to(torch.int32)
         n = int(fin.sum().item())
         sim = self.test_sim if phase == "test" else self.train_val_sim
         self._reset_on_device(sim, 0, phase, mask=fin, seeds=seeds)
-        self.case_counter[phase] += n
+        self.case_counter[phase] = (self.case_counter[phase] + n) % self.case_size[phase]
         return self.observation()
 
     def observation(self, theta_and_omega_visible=False):

@@ -1,5 +1,5 @@
-"""The oracle against the LIVE reference, on seeds no committed fixture holds (build container only: /root/reference does not
-exist on the GPU box, where this module is skipped).  tests/golden/*.npz pin the oracle on recorded runs; this re-derives the pin
+"""The oracle against the LIVE reference, on seeds no committed fixture holds (the reference is imported from /root/reference in the
+build container and from the copy staged under oracle/_ref -- oracle/build.py::stage_reference -- on the GPU box).  tests/golden/*.npz pin the oracle on recorded runs; this re-derives the pin
 from the reference itself every time the CPU suite runs here, on fresh circular-crossing crowds of every model family."""
 import os
 import sys
@@ -11,9 +11,10 @@ import oracle
 from oracle import OracleConfig
 from helpers import rel_err
 
-REF = "/root/reference"
+from oracle import reference
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "social_gym")), reason="the live reference exists in the build container only")
+pytestmark = pytest.mark.skipif(not reference.available(), reason="the live reference is neither at /root/reference nor staged under oracle/_ref")
 
 
 @pytest.fixture(scope="module")
