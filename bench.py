@@ -312,6 +312,7 @@ def run_large_crowd(args, rank, world, local_rank):
     steps = min(args.steps, 50)
     for _ in range(args.warmup):
         crowd.step(DT, 1)
+    crowd.check_peers()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -380,6 +381,56 @@ def run_large_crowd(args, rank, world, local_rank):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def large_crowd_probe(tdtype, rank, world, substeps_per_call=10, calls=3):
+    """BASELINE configs[4] beside the default line, at every N: ONE crowd of 65536 HSFM humans sharded by agent over the N GPUs,
+    the sub-step loop inside one C call (snp_large_run_p2p: peer stores of entries + tile boxes fused into the producer, a
+    single-warp barrier kernel between sub-steps).  Returns ms per sub-step (device time, max over ranks), the exchange in use
+    and whether this rank's slice equals the single-GPU result bit for bit."""
+    import torch
+    from social_navigation_pyenvs_b200 import scenarios
+    from social_navigation_pyenvs_b200.large import LargeCrowd
+    from social_navigation_pyenvs_b200.parallel import max_over_ranks
+    sc = scenarios.jittered_grid_crowd(256, pitch=2.0, jitter=0.5, seed=0)
+    perm = scenarios.spatial_order(sc["states"][0, :, 0:2])
+    S, G = np.ascontiguousarray(sc["states"][0, perm]), np.ascontiguousarray(sc["goals"][0, perm])
+    n = S.shape[0]
+    crowd = LargeCrowd("hsfm_farina", S, G, dtype=tdtype, rank=rank, world=world, exchange=os.environ.get("SNP_EXCHANGE", "auto"))
+    stream = torch.cuda.current_stream()
+
+    def timed(k, reps):
+        crowd.step(DT, k)  # warm-up call
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a_, b_ in ev:
+            a_.record(stream)
+            crowd.step(DT, k)
+            b_.record(stream)
+        torch.cuda.synchronize()
+        return max_over_ranks(sum(a_.elapsed_time(b_) for a_, b_ in ev), "cuda", world) / (reps * k)
+
+    # bit-equality first (from the initial state): 4 sub-steps sharded vs the whole crowd on this GPU alone
+    crowd.step(DT, 4)
+    mine = crowd.local_rows(S[crowd.offset:crowd.offset + crowd.n_local])
+    equal = True
+    if world > 1:
+        single = LargeCrowd("hsfm_farina", S, G, dtype=tdtype, rank=0, world=1)
+        single.step(DT, 4)
+        equal = bool(np.array_equal(mine, single.local_rows(S)[crowd.offset:crowd.offset + crowd.n_local]))
+        del single
+        equal = max_over_ranks(0.0 if equal else 1.0, "cuda", world) == 0.0
+    culled = timed(substeps_per_call, calls)
+    crowd.culling = False
+    allpairs = timed(2, 1)
+    crowd.culling = True
+    crowd.check_peers()
+    return {"workload": "65536_hsfm_single_crowd", "humans": n, "n_gpus": world, "scaling": "strong", "dtype": "f64" if tdtype == torch.float64 else "f32",
+            "ms_per_substep": culled, "agent_steps_per_s": n / (culled * 1e-3), "ms_per_substep_all_pairs": allpairs,
+            "exchange": {"p2p": "peer (NVLink) stores of entries + tile boxes fused into the finish kernel, device-side barrier kernel, "
+                                "sub-step loop in one C call (snp_large_run_p2p)",
+                         "fused": "single GPU: sub-step loop in one C call (snp_large_run_p2p), no exchange",
+                         "nccl": "NCCL all-gather of the [5, N] view per sub-step"}[crowd.exchange],
+            "substeps_per_call": substeps_per_call, "bit_equal_to_single_gpu": equal, "timing": "CUDA events around each call, max over ranks"}
 
 
 def run_laser(args, rank, world, local_rank):
@@ -699,6 +750,14 @@ def main():
     h2d = action_host.numel() * action_host.element_size()
     d2h = sum(x.numel() * x.element_size() for x in (obs_host, flags_host, checks_host))
 
+    # ---- BASELINE configs[4] at this N (all ranks take part): one 65536-human crowd sharded by agent ----
+    large = None
+    if not os.environ.get("SNP_BENCH_NO_LARGE"):
+        del flush
+        try:
+            large = large_crowd_probe(tdtype, rank, world)
+        except Exception as exc:  # keep the headline line even if the side measurement cannot run on this box
+            large = {"workload": "65536_hsfm_single_crowd", "error": repr(exc)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -743,7 +802,7 @@ def main():
                     "steps": e2e_steps, "statistic": "median step (host clock around each call), max over ranks",
                     "ms_per_step_median": e2e_med * 1e3, "ms_per_step_mean": e2e_mean * 1e3,
                     "staged_copies_ms_per_step_median": e2e_staged_med * 1e3, "cpu_affinity": affinity_note},
-            "roofline": roofline, "wall_s_timed_region": wall}
+            "roofline": roofline, "wall_s_timed_region": wall, "large_crowd": large}
 
     if not args.no_cpu_baseline and world == 1:
         if full_affinity:

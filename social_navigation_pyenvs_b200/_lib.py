@@ -84,6 +84,8 @@ _SIGNATURES = {
     "snp_large_step_p2p": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpStepOpts), c_void_p, c_int64, c_int64,
                                           ctypes.POINTER(c_void_p), c_int32, c_void_p, c_int64, c_void_p]),
     "snp_large_publish": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), c_int32, c_void_p, c_int64, c_int64, c_void_p]),
+    "snp_large_run_p2p": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpStepOpts), c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int32,
+                                         c_int32, c_void_p, ctypes.c_uint64, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
     "snp_update_humans_parallel_host": (ctypes.c_int, [c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                                        c_void_p, c_double, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                                        c_void_p, c_void_p]),

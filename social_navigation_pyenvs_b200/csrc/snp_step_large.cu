@@ -38,9 +38,11 @@ template <typename T> struct LargeArgs {
     int n_peers;
     T *partial;   // [J][2][N_local]
     T *boxes;     // [n_tiles][5] xmin, xmax, ymin, ymax, max(r+s)
+    T *peer_boxes[8];  // snp_large_run_p2p: the NEXT view's tile boxes on every rank; the finish kernel writes its own tiles' boxes there
     unsigned char *live;  // [i-blocks][J]: 1 when the (i-block, chunk) CTA evaluated at least one tile and wrote its partial sums
     int J, n_tiles;
     T cull_margin;  // distance beyond r+s sums at which the pair law is exactly zero; < 0 disables culling
+    int boxes_ready;  // the tile boxes of `others` are already in `boxes` (written by the previous sub-step's producer)
 };
 
 template <typename T> __device__ __forceinline__ T warp_min(T v) {
@@ -243,7 +245,8 @@ __global__ void __launch_bounds__(kTile) k_large_finish(const LargeArgs<T> la) {
     __syncthreads();
     const long long N = a.EN, M = la.M;
     const long long i = (long long)blockIdx.x * kTile + threadIdx.x;
-    if (i >= N) return;
+    const bool fold_boxes = la.peer_boxes[0] != nullptr;  // uniform; only offered when N is a whole number of tiles, so that every
+    if (i >= N) return;                                    // thread of every block reaches the box reduction at the end
     const unsigned vote_mask = __activemask();  // the lanes that own an agent (the tail warp is partial)
     const Params<T> &P = a.P;
     Agent<T> m;
@@ -298,6 +301,48 @@ __global__ void __launch_bounds__(kTile) k_large_finish(const LargeArgs<T> la) {
         la.next_view[o] = m.px; la.next_view[M + o] = m.py; la.next_view[2 * M + o] = m.vx; la.next_view[3 * M + o] = m.vy;
         la.next_view[4 * M + o] = m.rs;
     }
+    if (fold_boxes) {
+        // k_tile_boxes folded into the producer: this block's agents ARE one tile of the next view (self_offset is a multiple of
+        // the tile size), so its bounding box goes to every rank's next-box table with the entries themselves
+        __shared__ T sbox2[20];
+        T out[5];
+        block_box<T>(m.px, m.px, m.py, m.py, m.rs, sbox2, out);
+        if (threadIdx.x < 5) {
+            const long long tile = la.self_offset / kTile + blockIdx.x;
+            for (int p = 0; p < la.n_peers; ++p) la.peer_boxes[p][tile * 5 + threadIdx.x] = out[threadIdx.x];
+        }
+    }
+}
+
+// Cross-rank barrier of our own between sub-steps (one tiny kernel instead of a host-driven collective): slot [r] of every rank's
+// flag array receives rank r's epoch through a peer store; a rank passes once all its slots have reached the epoch.  Epochs only
+// grow, so nothing is ever reset and a fast rank that is already signalling the next barrier cannot release a slow one early.
+// The kernel boundary orders the finish kernel's peer stores before the signal (fence.sc.sys + release store); the acquire loads
+// order the next sub-step's reads after it.  A rank that never arrives trips the time-out instead of hanging the GPU.
+struct BarrierArgs {
+    unsigned long long *flags[8];  // every rank's flag array [world] (peer-mapped), index = rank
+    int world, rank;
+    unsigned long long epoch;
+    int *error;
+};
+
+__global__ void k_rank_barrier(const BarrierArgs b) {
+    const int t = threadIdx.x;
+    if (t < b.world) {
+        __threadfence_system();
+        unsigned long long *dst = b.flags[t] + b.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(b.epoch) : "memory");
+        const unsigned long long *src = b.flags[b.rank] + t;
+        const long long t0 = clock64();
+        unsigned long long seen = 0;
+        while (true) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
+            if (seen >= b.epoch) break;
+            if (clock64() - t0 > 40000000000LL) { *b.error = 1; break; }  // ~20 s: a peer died; report instead of spinning forever
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
 }
 
 // x, y, vx, vy, r+safety of every agent into a [5][stride] view (v = R(yaw) bv for headed models, mmm:448).
@@ -321,7 +366,7 @@ template <typename T, int SOC, int OBS, int HEADED> int launch_large(const Large
     const long long N = la.k.EN;
     const int nseg = la.k.W * la.k.S;
     if (sizeof(T) == 8) SNP_CUDA_OK(ensure_exp_table());
-    k_tile_boxes<T><<<(unsigned)la.n_tiles, kTile, 0, st>>>(la.others, la.M, la.boxes);
+    if (!la.boxes_ready) k_tile_boxes<T><<<(unsigned)la.n_tiles, kTile, 0, st>>>(la.others, la.M, la.boxes);
     const long long per_block = (long long)kTile * kAgentsPerThread;
     dim3 grid((unsigned)((N + per_block - 1) / per_block), (unsigned)la.J);
     k_large_pairs<T, SOC><<<grid, kTile, 0, st>>>(la);
@@ -329,7 +374,7 @@ template <typename T, int SOC, int OBS, int HEADED> int launch_large(const Large
     auto fin = k_large_finish<T, OBS, HEADED>;
     if (smem > 48 * 1024) SNP_CUDA_OK(cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fin<<<(unsigned)((N + kTile - 1) / kTile), kTile, smem, st>>>(la);
-    count_launch(3);
+    count_launch(la.boxes_ready ? 2 : 3);
     SNP_CUDA_OK(cudaGetLastError());
     return SNP_OK;
 }
@@ -340,10 +385,12 @@ inline long long large_iblocks(long long N) { return (N + (long long)kTile * kAg
 
 template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, const void *others, long long M, long long self_offset,
                                     void *next_view, const void *const *peer_views, int n_peers, void *scratch, long long scratch_bytes,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, const void *cur_boxes = nullptr, bool boxes_ready = false, const void *const *peer_next_boxes = nullptr) {
     LargeArgs<T> la;
     la.n_peers = n_peers;
     for (int p = 0; p < 8; ++p) la.peers[p] = (p < n_peers) ? (T *)peer_views[p] : nullptr;
+    for (int p = 0; p < 8; ++p) la.peer_boxes[p] = (peer_next_boxes && p < n_peers) ? (T *)peer_next_boxes[p] : nullptr;
+    la.boxes_ready = boxes_ready ? 1 : 0;
     KArgs<T> &a = la.k;
     a.E = 1; a.N = 0; a.G = c->G; a.EN = (long long)c->E * c->N;
     a.dyn = (T *)c->dyn; a.stat = (const T *)c->stat; a.goals = (const T *)c->goals; a.goal_idx = c->goal_idx; a.goal_cnt = c->goal_cnt;
@@ -359,6 +406,7 @@ template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, 
     la.partial = (T *)scratch;
     la.boxes = la.partial + (size_t)la.J * 2 * a.EN;
     la.live = reinterpret_cast<unsigned char *>(la.boxes + (size_t)la.n_tiles * 5);
+    if (cur_boxes) la.boxes = (T *)cur_boxes;  // the view's own box table (snp_large_run_p2p)
     // exact culling distance beyond the r+s sums: where exp(rd/B) is identically zero in the arithmetic in use
     const int soc = o->type % 3;
     const double under = sizeof(T) == 8 ? 700.0 : 88.0;
@@ -421,6 +469,45 @@ int snp_large_step_p2p(const snp_crowd *c, const snp_step_opts *o, const void *o
     if (c->dtype == SNP_F32) return run_large<float>(c, o, others, M, self_offset, nullptr, peer_next_views, n_peers, scratch, scratch_bytes, (cudaStream_t)stream);
     set_error("bad dtype %d", c->dtype);
     return SNP_ERR_INVALID;
+}
+
+int snp_large_run_p2p(const snp_crowd *c, const snp_step_opts *o, const void *const *peer_views_a, const void *const *peer_views_b,
+                      int32_t first_is_b, int64_t M, int64_t self_offset, int32_t world, int32_t rank, const void *const *peer_flags,
+                      uint64_t epoch_base, int32_t n_substeps, int32_t *error_flag, void *scratch, int64_t scratch_bytes, void *stream) {
+    if (!c || !o || !peer_views_a || !peer_views_b || !peer_flags || !error_flag) { set_error("snp_large_run_p2p: null argument"); return SNP_ERR_INVALID; }
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) { set_error("snp_large_run_p2p: 1..8 ranks (got world %d rank %d)", world, rank); return SNP_ERR_INVALID; }
+    if (!c->dyn || !c->stat || !c->goals || !c->goal_idx || !c->goal_cnt) { set_error("snp_large_run_p2p: crowd arrays missing"); return SNP_ERR_INVALID; }
+    if (c->agent_params || c->walls_per_env) { set_error("snp_large_run_p2p: uniform parameters and one wall set only"); return SNP_ERR_UNSUPPORTED; }
+    const long long N = (long long)c->E * c->N;
+    if (M < N || self_offset < 0 || self_offset + N > M) { set_error("snp_large_run_p2p: M=%lld offset=%lld N=%lld", (long long)M, (long long)self_offset, N); return SNP_ERR_INVALID; }
+    if (self_offset % kTile || N % kTile) { set_error("snp_large_run_p2p: every rank's slice must be a whole number of %d-entity tiles", kTile); return SNP_ERR_UNSUPPORTED; }
+    if (c->dtype != SNP_F64 && c->dtype != SNP_F32) { set_error("bad dtype %d", c->dtype); return SNP_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t w = c->dtype == SNP_F64 ? 8 : 4;
+    // a view buffer = [5][M] entity view followed by its [n_tiles][5] box table
+    auto boxes_of = [&](const void *view) { return (const void *)((const char *)view + (size_t)5 * M * w); };
+    BarrierArgs b;
+    for (int p = 0; p < 8; ++p) b.flags[p] = p < world ? (unsigned long long *)peer_flags[p] : nullptr;
+    b.world = world; b.rank = rank; b.error = error_flag;
+    int cur_is_b = first_is_b ? 1 : 0;
+    for (int s = 0; s < n_substeps; ++s) {
+        const void *const *cur = cur_is_b ? peer_views_b : peer_views_a, *const *nxt = cur_is_b ? peer_views_a : peer_views_b;
+        const void *nxt_boxes[8];
+        for (int p = 0; p < world; ++p) nxt_boxes[p] = boxes_of(nxt[p]);
+        int rc;
+        // sub-step 0 computes the tile boxes of the view it was handed; from then on the producer has written them
+        if (c->dtype == SNP_F64) rc = run_large<double>(c, o, cur[rank], M, self_offset, nullptr, nxt, world, scratch, scratch_bytes, st, boxes_of(cur[rank]), s > 0, nxt_boxes);
+        else rc = run_large<float>(c, o, cur[rank], M, self_offset, nullptr, nxt, world, scratch, scratch_bytes, st, boxes_of(cur[rank]), s > 0, nxt_boxes);
+        if (rc) return rc;
+        if (world > 1) {
+            b.epoch = epoch_base + (unsigned long long)s + 1;
+            k_rank_barrier<<<1, 32, 0, st>>>(b);
+            count_launch();
+            SNP_CUDA_OK(cudaGetLastError());
+        }
+        cur_is_b ^= 1;
+    }
+    return SNP_OK;
 }
 
 int snp_large_publish(const snp_crowd *c, int32_t type, void *view, int64_t stride, int64_t offset, void *stream) {

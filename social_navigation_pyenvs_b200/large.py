@@ -33,23 +33,43 @@ class LargeCrowd:
         # peer-mapped (torch symmetric memory, NVLink) pointers and only a barrier separates sub-steps; "nccl" = all-gather
         # after every sub-step.  "auto" tries p2p on multi-GPU runs and falls back to nccl.
         self.exchange, self._symm = "nccl", None
-        if world > 1 and exchange in ("auto", "p2p"):
+        # a view buffer = the [5, N] entity view followed by the [N/128, 5] bounding boxes of its 128-entity tiles (written by the
+        # producer together with the entries, see snp_large_run_p2p)
+        self._n_tiles = (self.n_total + 127) // 128
+        vlen = 5 * self.n_total + 5 * self._n_tiles
+        fused_ok = self.n_local % 128 == 0
+        if world > 1 and exchange in ("auto", "p2p") and fused_ok:
             try:
                 import torch.distributed as dist
                 import torch.distributed._symmetric_memory as symm_mem
                 grp = group if group is not None else dist.group.WORLD
-                self.view = [symm_mem.empty((5, self.n_total), dtype=dtype, device=self.eng.device) for _ in range(2)]
-                for v in self.view:
+                self._vbuf = [symm_mem.empty((vlen,), dtype=dtype, device=self.eng.device) for _ in range(2)]
+                self._flags = symm_mem.empty((16,), dtype=torch.int64, device=self.eng.device)
+                for v in self._vbuf + [self._flags]:
                     v.zero_()
-                self._symm = [symm_mem.rendezvous(v, grp) for v in self.view]
+                self._symm = [symm_mem.rendezvous(v, grp) for v in self._vbuf]
+                self._symm_flags = symm_mem.rendezvous(self._flags, grp)
                 self._peer_ptrs = [(ctypes.c_void_p * world)(*[int(p) for p in h.buffer_ptrs]) for h in self._symm]
+                self._peer_flags = (ctypes.c_void_p * world)(*[int(p) for p in self._symm_flags.buffer_ptrs])
+                torch.cuda.synchronize()
+                self._symm[0].barrier()
                 self.exchange = "p2p"
             except Exception as exc:  # no peer access / symmetric memory unavailable
                 if exchange == "p2p":
                     raise
                 self._p2p_error = repr(exc)
+        elif world == 1 and fused_ok and exchange != "nccl":
+            # one GPU: the same fused run (sub-step loop inside one C call, tile boxes written by the producer), no barrier
+            self._vbuf = [torch.zeros((vlen,), dtype=dtype, device=self.eng.device) for _ in range(2)]
+            self._flags = torch.zeros((16,), dtype=torch.int64, device=self.eng.device)
+            self._peer_ptrs = [(ctypes.c_void_p * 1)(v.data_ptr()) for v in self._vbuf]
+            self._peer_flags = (ctypes.c_void_p * 1)(self._flags.data_ptr())
+            self.exchange = "fused"
         if self.exchange == "nccl":
-            self.view = [torch.zeros((5, self.n_total), dtype=dtype, device=self.eng.device) for _ in range(2)]
+            self._vbuf = [torch.zeros((vlen,), dtype=dtype, device=self.eng.device) for _ in range(2)]
+        self.view = [v[:5 * self.n_total].view(5, self.n_total) for v in self._vbuf]
+        self._epoch = 0
+        self._err = torch.zeros((1,), dtype=torch.int32, device=self.eng.device)
         nbytes = int(self.eng.lib.snp_large_scratch_bytes(self.n_local, self.n_total, L.SNP_F64 if dtype == torch.float64 else L.SNP_F32))
         self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.eng.device)
         self.culling = True
@@ -64,6 +84,11 @@ class LargeCrowd:
         if self.exchange == "p2p":
             self._symm[0].barrier()
 
+    def check_peers(self):
+        """Raises if a rank never reached a sub-step barrier (the barrier kernel timed out instead of hanging the GPU)."""
+        if int(self._err.item()):
+            raise RuntimeError("LargeCrowd: a peer rank did not reach the sub-step barrier")
+
     def _publish(self):
         v = self.view[self.cur]
         L.check(self.eng.lib.snp_large_publish(ctypes.byref(self.eng._crowd()), self.type, ctypes.c_void_p(v.data_ptr()), self.n_total,
@@ -74,6 +99,16 @@ class LargeCrowd:
         c = self.eng._crowd()
         o = self.eng._opts(dt, 1)
         o.reserved = 0 if self.culling else 2  # SNP_OPT_NO_CULLING
+        if self.exchange in ("p2p", "fused") and not getattr(self, "legacy_loop", False):
+            # the whole sub-step loop in ONE C call: per sub-step two launches + a single-warp cross-rank barrier kernel, nothing
+            # returns to Python in between
+            L.check(self.eng.lib.snp_large_run_p2p(ctypes.byref(c), ctypes.byref(o), self._peer_ptrs[0], self._peer_ptrs[1], self.cur, self.n_total,
+                                                   self.offset, self.world, self.rank, self._peer_flags, self._epoch, int(n_substeps),
+                                                   ctypes.c_void_p(self._err.data_ptr()), ctypes.c_void_p(self.scratch.data_ptr()),
+                                                   self.scratch.numel(), self._stream()))
+            self._epoch += int(n_substeps)
+            self.cur ^= int(n_substeps) & 1
+            return
         for _ in range(n_substeps):
             cur, nxt = self.view[self.cur], self.view[self.cur ^ 1]
             if self.exchange == "p2p":

@@ -97,6 +97,34 @@ def test_fused_post_checks_and_touch_match_oracle_4096_envs():
     assert np.all(r["touched"][post[:, 10] != 0])
 
 
+def _grazing(humans, walls, origin, angle, hit_pair, range_pair, maxd, eps=2e-3):
+    """A single-precision scan may disagree with the reference about WHICH entity a ray hits only where the geometry is marginal:
+    the ray passes within `eps` metres of the rim of a circle / the end of a segment it hits in one result and misses in the other,
+    or the two results name different entities at (nearly) the same range."""
+    if abs(range_pair[0] - range_pair[1]) <= eps:
+        return True
+    o, d = np.asarray(origin, np.float64), np.array([np.cos(angle), np.sin(angle)])
+    n = humans.shape[0]
+    segs = walls.reshape(-1, 2, 2)
+    for h in set(hit_pair):
+        if h < 0:
+            continue
+        if h < n:  # circle: distance of the centre from the ray's line vs the radius, or a hit next to the range limit
+            c = humans[h, :2] - o
+            if abs(abs(c[0] * d[1] - c[1] * d[0]) - humans[h, 2]) < eps or abs(np.hypot(*c) - humans[h, 2] - maxd) < eps:
+                return True
+        else:      # segment: the crossing point sits within eps of one of its ends, or the ray is nearly parallel to it
+            a, b = segs[h - n]
+            e = b - a
+            den = d[0] * e[1] - d[1] * e[0]
+            if abs(den) < 1e-6:
+                return True
+            u = ((a[0] - o[0]) * d[1] - (a[1] - o[1]) * d[0]) / den
+            if min(abs(u), abs(u - 1)) * np.hypot(*e) < eps:
+                return True
+    return False
+
+
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 def test_laser_vs_reference_golden(dtype):
     from social_navigation_pyenvs_b200 import sensors
@@ -108,10 +136,14 @@ def test_laser_vs_reference_golden(dtype):
         if dtype == "float64":
             assert np.array_equal(hits[0], z[key + "_hits"]), key
             assert np.abs(ranges[0] - z[key + "_ranges"]).max() <= 1e-12, key
-        else:  # fp32: ranges to 1e-4 relative wherever both agree on hit/miss; grazing rays may flip
+        else:  # fp32: ranges to 1e-4 relative wherever both agree on the hit entity; a ray may only name another entity when it GRAZES
             same = hits[0] == z[key + "_hits"]
-            assert same.mean() > 0.97, (key, same.mean())
             assert (np.abs(ranges[0] - z[key + "_ranges"])[same] <= 1e-4 * np.maximum(z[key + "_ranges"][same], 1)).all(), key
+            ang = yaw - rng / 2 + np.arange(int(samples)) * (rng / (int(samples) - 1)) if int(samples) > 1 else np.array([yaw])
+            for r in np.nonzero(~same)[0]:
+                assert _grazing(z[key + "_humans"], z[key + "_walls"], (x, y), z[key + "_angles"][r] if key + "_angles" in z.files else ang[r],
+                                (int(hits[0][r]), int(z[key + "_hits"][r])), (float(ranges[0][r]), float(z[key + "_ranges"][r])), maxd), (key, int(r))
+            assert same.mean() > 0.9, (key, same.mean())
 
 
 def test_laser_class_matches_reference_dict():

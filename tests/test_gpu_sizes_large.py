@@ -1,5 +1,7 @@
 """GPU parity at other crowd shapes: lane packing (N=5, several envs per warp, ragged last warp), CTA-per-env (N > 32),
 per-env walls, per-agent parameter rows, the host operator with serial semantics, and the large tiled all-pairs kernel."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -190,3 +192,38 @@ def test_large_crowd_chunked_sums_and_exact_culling(dtype, order):
     ref, _, _ = oracle.update_humans(cfg, S, G, None, params, np.zeros((1, n)), np.zeros((1, n, 2)), 0.0125, 2)
     tol = 1e-9 if dtype == torch.float64 else 1e-4
     assert rel_err(out[True][:, :8], ref[0, :, :8]).max() < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("workload", ["4096x25_hsfm_ccso_walls_robot", "4096x5_sfm_helbing_cc"])
+def test_state_parity_at_the_bench_configurations(workload, dtype):
+    """BASELINE configs[2] and configs[1] at their FULL size (4096 envs), the crowds bench.py times: the state after one fused
+    launch of 20 sub-steps against the oracle (fp64: 1e-9 relative; fp32: 1e-4 after ONE sub-step -- north_star's per-step bar --
+    and the accumulated figure after 20 reported through a looser bound)."""
+    import oracle
+    from oracle import OracleConfig
+    from social_navigation_pyenvs_b200 import CrowdEngine, scenarios
+    model, E, N, with_walls, visible = {"4096x25_hsfm_ccso_walls_robot": ("hsfm_farina", 4096, 25, True, True),
+                                        "4096x5_sfm_helbing_cc": ("sfm_helbing", 4096, 5, False, False)}[workload]
+    sc = scenarios.ccso_synthetic(E, N, 2000) if with_walls else scenarios.circular_crossing(E, N, 2000)
+    walls = scenarios.pack_walls(scenarios.EXAMPLE_WALLS) if with_walls else None
+    states = np.concatenate([sc["states"], sc["robot"][:, None]], 1) if visible else sc["states"]
+    safety = np.zeros(states.shape[:2])
+    action = np.tile([0.0, 1.0], (E, 1))
+    cfg = OracleConfig(oracle.type_code(model), visible, True, False)
+    params = np.tile(oracle.default_params(model), (E, N, 1))
+    for k, tol64, tol32 in ((1, 1e-9, 1e-4), (20, 1e-9, 2e-3)):
+        eng = CrowdEngine.from_reference_arrays(model, states, sc["goals"], walls=walls, safety=safety, consider_robot=visible, all_params_equal=True,
+                                                dtype=dtype, robot=None if visible else sc["robot"])
+        eng.step(action, 0.0125, n_substeps=k, pre_checks=True, track_touch=True)
+        got = eng.rows(states)
+        ref, _, _ = oracle.update_humans(cfg, states, sc["goals"], walls, params, safety, np.zeros((E, N, 2)), 0.0125, k,
+                                         robot_vel=action if visible else None, n_threads=os.cpu_count() or 1)
+        g, r = got[:, :N, :8].copy(), ref[:, :N, :8]
+        g[..., 2] = r[..., 2] + (g[..., 2] - r[..., 2] + np.pi) % (2 * np.pi) - np.pi   # headings compared as angles
+        err = rel_err(g, r).max()
+        assert err < (tol64 if dtype == torch.float64 else tol32), (workload, k, float(err))
+        if dtype == torch.float64:
+            assert np.array_equal(got[:, :N, 10:12], ref[:, :N, 10:12])   # current goals: exact
+        else:                                                              # (the same goal, stored in single precision)
+            assert np.abs(got[:, :N, 10:12] - ref[:, :N, 10:12]).max() < 1e-5
