@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SNP_ABI_VERSION 2
+#define SNP_ABI_VERSION 3
 
 typedef enum snp_status {
     SNP_OK = 0,
@@ -108,9 +108,12 @@ typedef struct snp_step_opts {
     int32_t robot_mode;       /* 0: robot row fixed during the launch; 1: holonomic action: before every sub-step
                                  p += a*dt, v = a (robot_agent.py:126-131); 2: the robot is moved by its own SFM / HSFM model
                                  before every human update (motion_model_manager.py:593-653 update_robot, as in
-                                 SocialNavGym.imitation_learning_step, social_nav_gym.py:260-265) */
+                                 SocialNavGym.imitation_learning_step, social_nav_gym.py:260-265); 3: unicycle action (v, r):
+                                 before every sub-step p += v (cos, sin)(yaw + r) dt, yaw = (yaw + r) % 2 pi, velocity along the
+                                 new yaw (robot_agent.py:116-136); the swept check uses v (cos, sin)(yaw + r) (social_nav_sim.py:973,
+                                 with the robot's yaw where the reference reads its never-assigned `theta`) */
     double dt;
-    const void *action;       /* [2][E] (dtype of the crowd) when robot_mode == 1 or pre_checks */
+    const void *action;       /* [2][E] (dtype of the crowd) when robot_mode == 1 / 3 or pre_checks: (vx, vy), or (v, r) in mode 3 */
     int32_t pre_checks;       /* swept collision / goal / reward on the PRE-step state (social_nav_gym.py:232-234) */
     int32_t post_checks;      /* 1: actual collision / goal on the POST-step state (social_nav_gym.py:107-118); 2: also reward, terminated,
                                  truncated and info code from them at the end time (imitation_learning_step, social_nav_gym.py:269-271) */
@@ -155,6 +158,14 @@ typedef struct snp_laser_args {
     double range, max_distance, robot_radius; /* robot_radius is subtracted from the ranges (robot_agent.py:81); 0 for raw */
     void *ranges;             /* [E][samples] out */
     int32_t *hits;            /* [E][samples] out (optional): human index, N + segment ordinal, or -1 */
+    /* ABI 3 (appended): LaserSensor.add_uncertainty (sensors.py:71-74) on the device -- every range becomes
+     * clip(N(range, uncertainty), 0, max_distance) before the robot radius is subtracted.  The reference draws from the caller's global
+     * np.random stream, one normal per ray in ray order; here ray (env, k) of scan `noise_scan` takes its normal from the counter-based
+     * Philox4x32-10 stream keyed by `noise_seed` (counter = k, env, scan): same distribution, reproducible, independent of the launch
+     * geometry.  uncertainty <= 0 (or NaN): no noise, as with uncertainty=None. */
+    double uncertainty;
+    uint64_t noise_seed;
+    uint64_t noise_scan;
 } snp_laser_args;
 
 /* One-step lookahead of the value-network policies (crowd_nav/policy/cadrl.py:42-83 compute_rotated_states_and_reward,
@@ -211,6 +222,10 @@ int snp_robot_push_out(const snp_crowd *crowd, void *cuda_stream);
 int snp_reset(const snp_crowd *crowd, const snp_reset_args *args, void *cuda_stream);
 /* Uses crowd->dyn (current px,py,vx,vy,theta,omega), crowd->stat (radius) and crowd->robot (px,py,r,gx,gy,vd). */
 int snp_lookahead(const snp_crowd *crowd, const snp_lookahead_args *args, void *cuda_stream);
+/* The policies' query_env = False branch (crowd_nav/policy/cadrl.py:92-105 propagate_humans_state_with_constant_velocity_model):
+ * `next` [SNP_DYN_FIELDS][E*N] (crowd dtype) = the humans one step of length dt ahead under constant velocity (x + vx dt, y + vy dt,
+ * theta + omega dt, velocities carried over) -- the `next` input of snp_lookahead when the env is not queried. */
+int snp_constant_velocity(const snp_crowd *crowd, double dt, void *next, void *cuda_stream);
 /* AoS <-> SoA: rows are the reference's 13-wide float64 state rows [E][rows][13] with the robot (if any) as row N. */
 int snp_unpack_states(const snp_crowd *crowd, const double *rows_dev, int32_t rows_per_env, const double *safety_dev,
                       void *cuda_stream);

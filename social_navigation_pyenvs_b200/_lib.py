@@ -43,7 +43,7 @@ class SnpLaserArgs(ctypes.Structure):
                 ("px", c_void_p), ("py", c_void_p), ("radius", c_void_p), ("walls", c_void_p),
                 ("W", c_int32), ("S", c_int32), ("walls_per_env", c_int32), ("reserved", c_int32),
                 ("pose", c_void_p), ("range", c_double), ("max_distance", c_double), ("robot_radius", c_double),
-                ("ranges", c_void_p), ("hits", c_void_p)]
+                ("ranges", c_void_p), ("hits", c_void_p), ("uncertainty", c_double), ("noise_seed", ctypes.c_uint64), ("noise_scan", ctypes.c_uint64)]
 
 
 class SnpLookaheadArgs(ctypes.Structure):
@@ -72,6 +72,7 @@ _SIGNATURES = {
     "snp_checks": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpStepOpts), c_void_p]),
     "snp_laser": (ctypes.c_int, [ctypes.POINTER(SnpLaserArgs), c_void_p]),
     "snp_lookahead": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpLookaheadArgs), c_void_p]),
+    "snp_constant_velocity": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), c_double, c_void_p, c_void_p]),
     "snp_reset": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), ctypes.POINTER(SnpResetArgs), c_void_p]),
     "snp_robot_push_out": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), c_void_p]),
     "snp_unpack_states": (ctypes.c_int, [ctypes.POINTER(SnpCrowd), c_void_p, c_int32, c_void_p, c_void_p]),

@@ -42,8 +42,8 @@ template <typename T> static int build_args(const snp_crowd *c, const snp_step_o
     if (o->n_substeps < 0) { set_error("n_substeps must be >= 0"); return SNP_ERR_INVALID; }
     const bool need_robot = o->consider_robot || o->pre_checks || o->post_checks || o->track_touch || o->robot_mode;
     if (need_robot && !c->robot) { set_error("a robot array is required when consider_robot, robot_mode or any check is on"); return SNP_ERR_INVALID; }
-    if (o->robot_mode < 0 || o->robot_mode > 2) { set_error("robot_mode must be 0, 1 or 2"); return SNP_ERR_INVALID; }
-    if ((o->robot_mode == 1 || o->pre_checks) && !o->action) { set_error("an action array is required for robot_mode=1 / pre_checks"); return SNP_ERR_INVALID; }
+    if (o->robot_mode < 0 || o->robot_mode > 3) { set_error("robot_mode must be 0, 1, 2 or 3"); return SNP_ERR_INVALID; }
+    if ((o->robot_mode == 1 || o->robot_mode == 3 || o->pre_checks) && !o->action) { set_error("an action array is required for robot_mode 1 / 3 and pre_checks"); return SNP_ERR_INVALID; }
     if ((o->pre_checks || o->post_checks || o->track_touch) && !o->flags) { set_error("flags output required when checks are on"); return SNP_ERR_INVALID; }
     if (c->W < 0 || c->S < 0 || (c->W > 0 && (!c->walls || c->S == 0))) { set_error("walls: W=%d S=%d but no segment array", c->W, c->S); return SNP_ERR_INVALID; }
     if (c->agent_params && o->symmetric && !o->numba_compat) {

@@ -106,7 +106,34 @@ template <typename T> struct LArgs {
     T range, maxd, robot_radius;
     T *ranges;
     int *hits;
+    double sigma;                        // add_uncertainty (sensors.py:71-74); <= 0: off
+    unsigned long long seed, scan;
 };
+
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so ray (env, k) of scan s owns its random numbers whatever thread computes it.
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// clip(N(m, sigma), 0, maxd): one Box-Muller normal from two 32-bit uniforms in (0, 1)
+template <typename T> __device__ __forceinline__ T add_uncertainty(const LArgs<T> &a, T m, int e, int ray) {
+    if (!(a.sigma > 0.0)) return m;
+    unsigned r[4];
+    philox4x32_10((unsigned)ray, (unsigned)e, (unsigned)a.scan, (unsigned)(a.scan >> 32), (unsigned)a.seed, (unsigned)(a.seed >> 32), r);
+    const double u1 = ((double)r[0] + 0.5) * 2.3283064365386963e-10, u2 = ((double)r[1] + 0.5) * 2.3283064365386963e-10;
+    const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    double v = fma(a.sigma, z, (double)m);
+    v = v < (double)a.maxd ? v : (double)a.maxd;
+    return (T)(v > 0.0 ? v : 0.0);
+}
 
 template <typename T> __global__ void __launch_bounds__(128) k_laser_rays(const LArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -141,7 +168,7 @@ template <typename T> __global__ void __launch_bounds__(128) k_laser_rays(const 
         if (rc < best) { best = rc; hit = ord; }
         ++ord;
     }
-    a.ranges[(size_t)e * a.samples + ray] = best - a.robot_radius;
+    a.ranges[(size_t)e * a.samples + ray] = add_uncertainty<T>(a, best, e, ray) - a.robot_radius;
     if (a.hits) a.hits[(size_t)e * a.samples + ray] = hit;
 }
 
@@ -190,7 +217,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_laser_warp(const 
         if (ob < best || (ob == best && oh < hit)) { best = ob; hit = oh; }
     }
     if (lane == 0) {
-        a.ranges[(size_t)e * a.samples + ray] = best - a.robot_radius;
+        a.ranges[(size_t)e * a.samples + ray] = add_uncertainty<T>(a, best, e, ray) - a.robot_radius;
         if (a.hits) a.hits[(size_t)e * a.samples + ray] = (hit == 0x7fffffff) ? -1 : hit;
     }
 }
@@ -201,6 +228,7 @@ template <typename T> int run_laser(const snp_laser_args *g, cudaStream_t st) {
     a.px = (const T *)g->px; a.py = (const T *)g->py; a.radius = (const T *)g->radius; a.walls = (const T *)g->walls; a.pose = (const T *)g->pose;
     a.range = (T)g->range; a.maxd = (T)g->max_distance; a.robot_radius = (T)g->robot_radius;
     a.ranges = (T *)g->ranges; a.hits = g->hits;
+    a.sigma = g->uncertainty; a.seed = g->noise_seed; a.scan = g->noise_scan;
     const int entities = a.N + a.W * a.S;
     const size_t smem_rays = ((sizeof(Circ<T>) * a.N + 15) & ~size_t(15)) + sizeof(RaySeg<T>) * (size_t)(a.W * a.S);
     if (entities <= 512 && smem_rays <= 48 * 1024) {

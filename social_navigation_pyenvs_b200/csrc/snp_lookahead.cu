@@ -254,6 +254,43 @@ template <typename T> int launch_lookahead(LookArgs a, cudaStream_t st) {
 
 using namespace snp;
 
+namespace snp {
+namespace {
+// propagate_humans_state_with_constant_velocity_model (crowd_nav/policy/cadrl.py:92-105), the policies' query_env = False branch:
+// x + vx dt, y + vy dt, theta + omega dt with the velocities carried over -- into a [SNP_DYN_FIELDS][E*N] buffer laid out like dyn,
+// which is what snp_lookahead takes as `next`.  The reference's expression is a product followed by a sum (no contraction).
+template <typename T> __global__ void k_constant_velocity(const T *dyn, T *next, long long EN, T dt) {
+    const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= EN) return;
+    const T vx = dyn[SNP_DYN_VX * EN + a], vy = dyn[SNP_DYN_VY * EN + a], om = dyn[SNP_DYN_OM * EN + a];
+    if (sizeof(T) == 8) {
+        next[SNP_DYN_PX * EN + a] = (T)__dadd_rn((double)dyn[SNP_DYN_PX * EN + a], __dmul_rn((double)vx, (double)dt));
+        next[SNP_DYN_PY * EN + a] = (T)__dadd_rn((double)dyn[SNP_DYN_PY * EN + a], __dmul_rn((double)vy, (double)dt));
+        next[SNP_DYN_TH * EN + a] = (T)__dadd_rn((double)dyn[SNP_DYN_TH * EN + a], __dmul_rn((double)om, (double)dt));
+    } else {
+        next[SNP_DYN_PX * EN + a] = (T)__fadd_rn((float)dyn[SNP_DYN_PX * EN + a], __fmul_rn((float)vx, (float)dt));
+        next[SNP_DYN_PY * EN + a] = (T)__fadd_rn((float)dyn[SNP_DYN_PY * EN + a], __fmul_rn((float)vy, (float)dt));
+        next[SNP_DYN_TH * EN + a] = (T)__fadd_rn((float)dyn[SNP_DYN_TH * EN + a], __fmul_rn((float)om, (float)dt));
+    }
+    next[SNP_DYN_VX * EN + a] = vx; next[SNP_DYN_VY * EN + a] = vy; next[SNP_DYN_OM * EN + a] = om;
+    next[SNP_DYN_BVX * EN + a] = dyn[SNP_DYN_BVX * EN + a]; next[SNP_DYN_BVY * EN + a] = dyn[SNP_DYN_BVY * EN + a];
+}
+}  // namespace
+}  // namespace snp
+
+extern "C" int snp_constant_velocity(const snp_crowd *c, double dt, void *next, void *stream) {
+    if (!c || !c->dyn || !next) { set_error("snp_constant_velocity: null argument"); return SNP_ERR_INVALID; }
+    if (c->E <= 0 || c->N <= 0) { set_error("snp_constant_velocity: E and N must be positive"); return SNP_ERR_INVALID; }
+    const long long EN = (long long)c->E * c->N;
+    const unsigned blocks = (unsigned)((EN + 255) / 256);
+    if (c->dtype == SNP_F64) snp::k_constant_velocity<double><<<blocks, 256, 0, (cudaStream_t)stream>>>((const double *)c->dyn, (double *)next, EN, dt);
+    else if (c->dtype == SNP_F32) snp::k_constant_velocity<float><<<blocks, 256, 0, (cudaStream_t)stream>>>((const float *)c->dyn, (float *)next, EN, (float)dt);
+    else { set_error("dtype %d is neither SNP_F32 nor SNP_F64", c->dtype); return SNP_ERR_INVALID; }
+    count_launch();
+    SNP_CUDA_OK(cudaGetLastError());
+    return SNP_OK;
+}
+
 extern "C" int snp_lookahead(const snp_crowd *c, const snp_lookahead_args *g, void *stream) {
     if (!c || !g) { set_error("snp_lookahead: null descriptor"); return SNP_ERR_INVALID; }
     if (c->E <= 0 || c->N <= 0 || g->A <= 0) { set_error("snp_lookahead: E, N and A must be positive"); return SNP_ERR_INVALID; }

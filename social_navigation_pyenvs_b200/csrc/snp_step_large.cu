@@ -23,9 +23,14 @@ namespace snp {
 namespace {
 
 constexpr int kTile = 128;           // entities per shared-memory tile == threads per block
-constexpr int kAgentsPerThread = 2;  // register tiling: every staged entity is used for two agents
+// Register tiling of the pairs kernel: every staged entity is used for APT agents of the thread.  2 halves the shared-memory
+// loads per pair (best when every ordered pair is evaluated: 7.8 vs 8.4 ms per sub-step at 65536 humans); 1 doubles the number of
+// CTAs, which is what a culled step needs once the crowd is sharded (one rank of an 8-way split keeps only ~300 live CTAs of
+// 256 agents x 512 entities -- a serial loop per CTA that no longer fills 148 SMs: 0.22 ms per rank; 128 agents x 256 entities:
+// 0.15 ms).  The summation order per agent does not depend on it, so results stay bit-identical.
+constexpr int kMaxAgentsPerThread = 2;
 #ifndef SNP_LARGE_CHUNK
-#define SNP_LARGE_CHUNK 512
+#define SNP_LARGE_CHUNK 256
 #endif
 constexpr int kChunk = SNP_LARGE_CHUNK;  // entities per j-chunk (one partial sum each); fixed so results are sharding-independent
 
@@ -43,6 +48,7 @@ template <typename T> struct LargeArgs {
     int J, n_tiles;
     T cull_margin;  // distance beyond r+s sums at which the pair law is exactly zero; < 0 disables culling
     int boxes_ready;  // the tile boxes of `others` are already in `boxes` (written by the previous sub-step's producer)
+    int apt;          // agents per thread of the pairs kernel (1 or 2): fixes the i-block size the `live` map is indexed by
 };
 
 template <typename T> __device__ __forceinline__ T warp_min(T v) {
@@ -79,7 +85,7 @@ template <typename T> __global__ void __launch_bounds__(kTile) k_tile_boxes(cons
     if (threadIdx.x < 5) boxes[(size_t)blockIdx.x * 5 + threadIdx.x] = out[threadIdx.x];
 }
 
-template <typename T, int SOC>
+template <typename T, int SOC, int kAgentsPerThread>
 __global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
     __shared__ __align__(16) unsigned char tile_raw[sizeof(Ent<T>) * kTile];
     __shared__ T tile_rs[kTile];
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(kTile) k_large_finish(const LargeArgs<T> la) {
     const int gcnt = a.goal_cnt[i];
     m.gx = a.goals[((size_t)gidx * 2 + 0) * N + i]; m.gy = a.goals[((size_t)gidx * 2 + 1) * N + i];
     T fsx = T(0), fsy = T(0);
-    const unsigned char *lv = la.live + (size_t)(i / (kTile * kAgentsPerThread)) * la.J;  // the same flags for the whole CTA
+    const unsigned char *lv = la.live + (size_t)(i / (kTile * la.apt)) * la.J;  // the same flags for the whole CTA
     for (int p = 0; p < la.J; ++p)
         if (lv[p]) { fsx += la.partial[((size_t)p * 2 + 0) * N + i]; fsy += la.partial[((size_t)p * 2 + 1) * N + i]; }
 
@@ -367,9 +373,10 @@ template <typename T, int SOC, int OBS, int HEADED> int launch_large(const Large
     const int nseg = la.k.W * la.k.S;
     if (sizeof(T) == 8) SNP_CUDA_OK(ensure_exp_table());
     if (!la.boxes_ready) k_tile_boxes<T><<<(unsigned)la.n_tiles, kTile, 0, st>>>(la.others, la.M, la.boxes);
-    const long long per_block = (long long)kTile * kAgentsPerThread;
+    const long long per_block = (long long)kTile * la.apt;
     dim3 grid((unsigned)((N + per_block - 1) / per_block), (unsigned)la.J);
-    k_large_pairs<T, SOC><<<grid, kTile, 0, st>>>(la);
+    if (la.apt == 1) k_large_pairs<T, SOC, 1><<<grid, kTile, 0, st>>>(la);
+    else k_large_pairs<T, SOC, 2><<<grid, kTile, 0, st>>>(la);
     const size_t smem = sizeof(double) * kExpN + ((sizeof(Seg<T>) * (size_t)nseg + 15) & ~size_t(15)) + sizeof(int) * (la.k.W + 1) + 16;
     auto fin = k_large_finish<T, OBS, HEADED>;
     if (smem > 48 * 1024) SNP_CUDA_OK(cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -381,7 +388,7 @@ template <typename T, int SOC, int OBS, int HEADED> int launch_large(const Large
 
 inline long long large_J(long long M) { return (M + kChunk - 1) / kChunk; }
 inline long long large_tiles(long long M) { return (M + kTile - 1) / kTile; }
-inline long long large_iblocks(long long N) { return (N + (long long)kTile * kAgentsPerThread - 1) / ((long long)kTile * kAgentsPerThread); }
+inline long long large_iblocks(long long N) { return (N + kTile - 1) / kTile; }  // sized for one agent per thread (the finer split)
 
 template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, const void *others, long long M, long long self_offset,
                                     void *next_view, const void *const *peer_views, int n_peers, void *scratch, long long scratch_bytes,
@@ -416,6 +423,7 @@ template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, 
         else if (soc == 1 && c->params[3] > 0 && c->params[7] > 0) margin = under * (c->params[3] > c->params[7] ? c->params[3] : c->params[7]);
     }
     la.cull_margin = (T)margin;
+    la.apt = margin >= 0.0 ? 1 : kMaxAgentsPerThread;
     switch (o->type) {
         case 0: return launch_large<T, 0, 0, 0>(la, st);
         case 1: return launch_large<T, 1, 1, 0>(la, st);

@@ -248,6 +248,23 @@ __device__ __noinline__ void robot_update(int rtype, const Params<T> *RPp, const
     rb[SNP_ROBOT_GX] = m.gx; rb[SNP_ROBOT_GY] = m.gy;
 }
 
+// RobotAgent.step with unicycle kinematics (robot_agent.py:116-136), action = ActionRot(v, r): the position advances along
+// yaw + r, the yaw becomes (yaw + r) % 2 pi -- r is added at EVERY call, whatever delta_t -- and the velocity points along the new
+// yaw.  Double arithmetic (what the reference computes in); by the group's leader lane, out of line.
+template <typename T> __device__ __noinline__ void robot_unicycle_step(T *rb, double v, double r, double dt) {
+    const double two_pi = 6.283185307179586;
+    const double yaw = (double)rb[SNP_ROBOT_TH] + r;
+    double sn, cs;
+    sincos(yaw, &sn, &cs);
+    rb[SNP_ROBOT_PX] = (T)__dadd_rn((double)rb[SNP_ROBOT_PX], __dmul_rn(__dmul_rn(cs, v), dt));
+    rb[SNP_ROBOT_PY] = (T)__dadd_rn((double)rb[SNP_ROBOT_PY], __dmul_rn(__dmul_rn(sn, v), dt));
+    double w = fmod(yaw, two_pi);   // Python's float %: the result takes the divisor's sign
+    if (w < 0.0) w += two_pi;
+    sincos(w, &sn, &cs);
+    rb[SNP_ROBOT_TH] = (T)w;
+    rb[SNP_ROBOT_VX] = (T)__dmul_rn(cs, v); rb[SNP_ROBOT_VY] = (T)__dmul_rn(sn, v);
+}
+
 template <typename T> __device__ __forceinline__ T seg_sum(T v, int i, int n, unsigned mask) {  // valid in the group's lane 0
     for (int off = 1; off < n; off <<= 1) {
         const T o = __shfl_down_sync(mask, v, off);
@@ -392,7 +409,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
         if constexpr (ROBOT2) if (leader) {  // the robot's full state lives in shared memory (one lane updates it)
 #pragma unroll
             for (int f = 0; f < SNP_ROBOT_FIELDS; ++f) rb[f] = a.robot[(size_t)f * E + env];
-            if (a.robot_type >= 3 && a.robot_every <= 1) {  // headed robot: linear velocity = R(yaw) bv (mmm:605); with robot_every > 1
+            if (a.robot_mode == 2 && a.robot_type >= 3 && a.robot_every <= 1) {  // headed robot: linear velocity = R(yaw) bv (mmm:605); with robot_every > 1
                 T sn, cs;                                   // the velocity of the last refresh is what moves the pose (mmm:655-657)
                 R::sincos_(rb[SNP_ROBOT_TH], &sn, &cs);
                 rb[SNP_ROBOT_VX] = np_mv(cs, -sn, rb[SNP_ROBOT_BVX], rb[SNP_ROBOT_BVY]);
@@ -406,6 +423,14 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
     double out_dmin = 0.0, out_reward = 0.0, out_admin = 0.0;
 
     // ---- pre-step checks: swept collision + goal + reward (gym:232-234) ----
+    // unicycle action (v, r): the swept test and the goal test use the velocity v (cos, sin)(yaw + r) (sim:973, robot_agent.py:122)
+    // (ROBOT2 instantiations only: they also carry the unicycle robot, so that the common kernel has none of its code)
+    if (ROBOT2 && a.robot_mode == 3 && has_robot && live) {
+        const double uv = (double)ax, ur = (double)ay;
+        double sn_, cs_;
+        sincos((double)a.robot[SNP_ROBOT_TH * a.E + env] + ur, &sn_, &cs_);
+        ax = (T)__dmul_rn(uv, cs_); ay = (T)__dmul_rn(uv, sn_);
+    }
     if (a.pre_checks) {
         double cd = CUDART_INF;
         if (live) cd = swept_distance((double)me.px, (double)me.py, (double)me.vx, (double)me.vy, (double)me.r, (double)rpx, (double)rpy,
@@ -458,11 +483,19 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             else { rpx = rpx + ax * dt; rpy = rpy + ay * dt; }
             rvx = ax; rvy = ay;
         }
+        if constexpr (ROBOT2) {
+            if (a.robot_mode == 3 && has_robot) {  // unicycle robot: uniform branch; the pose lives in the group's shared record
+                if (leader) robot_unicycle_step<T>(rb, (double)a.action[env], (double)a.action[a.E + env], (double)dt);  // (v, r)
+                if constexpr (CTA) __syncthreads(); else __syncwarp(wmask);
+                rpx = rb[SNP_ROBOT_PX]; rpy = rb[SNP_ROBOT_PY]; rvx = rb[SNP_ROBOT_VX]; rvy = rb[SNP_ROBOT_VY];
+                if (leader && a.consider_robot) ents.put(N, rpx, rpy, rvx, rvy);
+            }
+        }
         if (live) ents.put(i, me.px, me.py, me.vx, me.vy);
         if (!ROBOT2 && leader && a.consider_robot) ents.put(N, rpx, rpy, rvx, rvy);
         if constexpr (CTA) __syncthreads(); else __syncwarp(wmask);
 
-        if constexpr (ROBOT2) {
+        if constexpr (ROBOT2) if (a.robot_mode == 2) {
             // update_robot first (gym:262): every human lane evaluates its force on the robot with the ROBOT's model and
             // parameters, the group sums them, the leader integrates the robot and republishes it; the humans then see the
             // moved robot (gym:264).
@@ -781,7 +814,7 @@ int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
         const int epb = a.epw * kWarpsPerBlock;
         grid = dim3((unsigned)((a.E + epb - 1) / epb));
         block = dim3(kWarpsPerBlock * 32);
-        smem = SmemLayout<T>(nseg, a.walls_per_env ? epb : 1, a.W, kWarpsPerBlock * slots_per_warp(a.N, a.epw), 0, 0, 0, a.robot_mode == 2 ? epb : 0,
+        smem = SmemLayout<T>(nseg, a.walls_per_env ? epb : 1, a.W, kWarpsPerBlock * slots_per_warp(a.N, a.epw), 0, 0, 0, a.robot_mode >= 2 ? epb : 0,
                              a.G <= kGoalCache ? a.G * kWarpsPerBlock * 32 : 0).total;
     } else {
         a.epw = 1;
@@ -791,7 +824,7 @@ int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
         const int rounds = (a.N - 1) >> 1;
         if (half && sizeof(Vec2<T>) * (size_t)rounds * gpb * a.N > 64 * 1024) half = false;  // exchange planes would not fit: ordered loop
         smem = SmemLayout<T>(nseg, a.walls_per_env ? gpb : 1, a.W, gpb * (a.N + 1), gpb * a.N, half ? rounds * gpb * a.N : 0, gpb,
-                             a.robot_mode == 2 ? gpb : 0, a.G <= kGoalCache ? a.G * block_threads : 0).total;
+                             a.robot_mode >= 2 ? gpb : 0, a.G <= kGoalCache ? a.G * block_threads : 0).total;
     }
     if (smem > 200 * 1024) { set_error("wall/segment tables need %zu bytes of shared memory (limit 200 KiB)", smem); return SNP_ERR_UNSUPPORTED; }
 #define SNP_LAUNCH2(CTA_, PA_, HALF_, R2_)                                                                             \
@@ -801,7 +834,7 @@ int launch_one(const KArgs<T> &a_in, cudaStream_t st) {
         kern<<<grid, block, smem, st>>>(a);                                                                            \
     } while (0)
 #define SNP_LAUNCH(CTA_, PA_, HALF_) SNP_LAUNCH2(CTA_, PA_, HALF_, false)
-    if (a.robot_mode == 2) {  // robot driven by its own model: separate instantiations so the common path keeps its registers
+    if (a.robot_mode >= 2) {  // robot driven by its own model, or a unicycle robot: separate instantiations so the common path keeps its registers
         if (per_agent) { set_error("robot_mode 2 with per-agent parameter rows is not supported"); return SNP_ERR_UNSUPPORTED; }
         if (!a.robot) { set_error("robot_mode 2 needs a robot array"); return SNP_ERR_INVALID; }
         if (cta) { if (half) SNP_LAUNCH2(true, false, true, true); else SNP_LAUNCH2(true, false, false, true); }

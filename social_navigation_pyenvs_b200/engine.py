@@ -290,14 +290,18 @@ class CrowdEngine:
         """MotionModelManager.update_humans (motion_model_manager.py:354) for every env: `n_substeps` Euler updates in one launch."""
         L.check(self.lib.snp_step(ctypes.byref(self._crowd()), ctypes.byref(self._opts(dt, n_substeps, post_update=post_update)), _stream()))
 
-    def step(self, action=None, dt=0.0125, n_substeps=20, pre_checks=True, post_checks=False, track_touch=False):
+    def step(self, action=None, dt=0.0125, n_substeps=20, pre_checks=True, post_checks=False, track_touch=False, kinematics="holonomic"):
         """SocialNavGym.step for every env (social_nav_gym.py:227-250): swept collision / goal test and reward on the current
-        state, then `n_substeps` x (robot.step(action, dt); update_humans(dt)).  `action` [E,2] holonomic velocities
-        (device tensor or array); None reuses self.action.  Results land in self.flags / self.checks / self.time_now."""
+        state, then `n_substeps` x (robot.step(action, dt); update_humans(dt)).  `action` [E,2]: holonomic velocities (vx, vy)
+        (ActionXY), or (v, r) with kinematics="unicycle" (ActionRot, robot_agent.py:116-136: the rotation r is applied at every
+        sub-step); device tensor or array; None reuses self.action.  Results land in self.flags / self.checks / self.time_now."""
+        if kinematics not in ("holonomic", "unicycle"):
+            raise ValueError("kinematics must be 'holonomic' or 'unicycle'")
         if action is not None:
             a = torch.as_tensor(action, dtype=self.dtype, device=self.device)
             self.action.copy_(a.t() if a.shape == (self.E, 2) else a)
-        o = self._opts(dt, n_substeps, robot_mode=1, pre_checks=pre_checks, post_checks=post_checks, track_touch=track_touch, advance_time=True)
+        o = self._opts(dt, n_substeps, robot_mode=1 if kinematics == "holonomic" else 3, pre_checks=pre_checks, post_checks=post_checks,
+                       track_touch=track_touch, advance_time=True)
         L.check(self.lib.snp_step(ctypes.byref(self._crowd()), ctypes.byref(o), _stream()))
 
     def step_host(self, action_host, obs_host, flags_host, checks_host, dt=0.0125, n_substeps=20, pre_checks=True, post_checks=False,
@@ -475,14 +479,26 @@ class CrowdEngine:
 
     def lookahead(self, time_step=0.25, theta_and_omega_visible=False, query_env=True, bulk_store=True):
         """What CADRL.predict computes before evaluating its value network (crowd_nav/policy/cadrl.py:235-262), for every env:
-        peek the humans `time_step` ahead (query_env; else the constant-velocity model :85-105 is NOT offered -- pass your own
-        `next` through lookahead_from), then compute_rotated_states_and_reward (:42-83) for the whole action space.
+        the humans `time_step` ahead -- query_env=True: a peek of the motion model (:257-258); False: the constant-velocity model
+        (:92-105, snp_constant_velocity) -- then compute_rotated_states_and_reward (:42-83) for the whole action space.
         Returns device tensors (rotated [E,A,N,13|15] in the engine's dtype, rewards [E,A] float64); two launches."""
-        if not query_env:
-            raise NotImplementedError("query_env=False (constant-velocity propagation) is not part of the engine")
-        return self.lookahead_from(self.peek(time_step), time_step, theta_and_omega_visible, bulk_store)
+        if query_env:
+            return self.lookahead_from(self.peek(time_step), time_step, theta_and_omega_visible, bulk_store)
+        return self.lookahead_from(self.constant_velocity_next(time_step), time_step, theta_and_omega_visible, bulk_store, yaw_from_next=True)
 
-    def lookahead_from(self, nxt, time_step=0.25, theta_and_omega_visible=False, bulk_store=True):
+    def constant_velocity_next(self, dt):
+        """propagate_humans_state_with_constant_velocity_model (crowd_nav/policy/cadrl.py:92-105) into the peek buffer: the
+        [DYN_FIELDS,E,N] device tensor of the humans one step ahead if nobody changed velocity; the crowd itself is untouched."""
+        if self._peek_buf is None:
+            self._peek_buf, self._peek_idx = torch.empty_like(self.dyn), torch.empty_like(self.goal_idx)
+        L.check(self.lib.snp_constant_velocity(ctypes.byref(self._crowd()), float(dt), ctypes.c_void_p(self._peek_buf.data_ptr()), _stream()))
+        return self._peek_buf
+
+    def lookahead_from(self, nxt, time_step=0.25, theta_and_omega_visible=False, bulk_store=True, yaw_from_next=False):
+        """compute_rotated_states_and_reward on a given `nxt` [DYN_FIELDS,E,N].  With theta_and_omega_visible the next yaw / omega are
+        read from `nxt` for headed models and from the current state otherwise (what get_next_human_observable_states returns,
+        mmm:691-709); yaw_from_next=True reads them from `nxt` whatever the model (the constant-velocity propagation integrates
+        theta + omega dt for every model, cadrl.py:103)."""
         if getattr(self, "action_space", None) is None:
             raise ValueError("set_action_space(actions) first")
         if self.robot is None:
@@ -492,7 +508,7 @@ class CrowdEngine:
             self._rotated = torch.empty((self.E, A, self.N, ow), dtype=self.dtype, device=self.device)
             self._rewards = torch.empty((self.E, A), dtype=torch.float64, device=self.device)
         g = L.SnpLookaheadArgs()
-        g.type, g.A, g.theta_and_omega_visible, g.reserved = self.type, A, int(theta_and_omega_visible), 0 if bulk_store else 1
+        g.type, g.A, g.theta_and_omega_visible, g.reserved = (max(self.type, 3) if yaw_from_next else self.type), A, int(theta_and_omega_visible), 0 if bulk_store else 1
         g.next, g.actions, g.dt = nxt.data_ptr(), self.action_space.data_ptr(), float(time_step)
         g.rotated, g.rewards = self._rotated.data_ptr(), self._rewards.data_ptr()
         L.check(self.lib.snp_lookahead(ctypes.byref(self._crowd()), ctypes.byref(g), _stream()))

@@ -17,13 +17,15 @@ from .parallel import all_gather_columns, agent_shard
 
 class LargeCrowd:
     def __init__(self, model, states, goals, walls=None, dtype=torch.float64, device="cuda", symmetric=True, numba_compat=False,
-                 rank=0, world=1, group=None, safety=None, exchange="auto"):
-        """states [N_total,13], goals [N_total,G,2] (the WHOLE crowd on every rank; each rank keeps its slice)."""
+                 rank=0, world=1, group=None, safety=None, exchange="auto", shard=None):
+        """states [N_total,13], goals [N_total,G,2] (the WHOLE crowd on every rank; each rank keeps its slice).
+        shard=(offset, n_local) with world=1 steps only that slice against a frozen rest of the crowd (profiling what ONE rank of
+        a sharded run executes, on one GPU)."""
         states = np.asarray(states, np.float64)
         goals = np.asarray(goals, np.float64)
         self.n_total = states.shape[0]
         self.rank, self.world, self.group = rank, world, group
-        self.offset, self.n_local = agent_shard(self.n_total, rank, world)
+        self.offset, self.n_local = agent_shard(self.n_total, rank, world) if shard is None else shard
         sl = slice(self.offset, self.offset + self.n_local)
         saf = None if safety is None else np.asarray(safety, np.float64)[None, sl]
         self.eng = CrowdEngine.from_reference_arrays(model, states[None, sl], goals[None, sl], walls=walls, safety=saf, consider_robot=False,
@@ -74,6 +76,10 @@ class LargeCrowd:
         self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.eng.device)
         self.culling = True
         self.cur = 0
+        if shard is not None:  # the frozen rest of the crowd: both view buffers start from the whole crowd's entries
+            whole = CrowdEngine.from_reference_arrays(model, states[None], goals[None], consider_robot=False, all_params_equal=symmetric, dtype=dtype, device=device)
+            for v in self.view:
+                L.check(whole.lib.snp_large_publish(ctypes.byref(whole._crowd()), self.type, ctypes.c_void_p(v.data_ptr()), self.n_total, 0, self._stream()))
         self._publish()
 
     def _stream(self):

@@ -63,8 +63,9 @@ def scan_batch(humans, walls, pose, range_, samples, max_distance, robot_radius=
 
 
 class LaserSensor:
-    """social_gym/src/sensors.py:6-74 for one sensor.  `uncertainty` must be None or 0: the Gaussian noise of
-    add_uncertainty (sensors.py:71-74) draws from the caller's global np.random stream and is applied on the host."""
+    """social_gym/src/sensors.py:6-74 for one sensor.  The Gaussian noise of add_uncertainty (sensors.py:71-74) is applied on the
+    host from the caller's global np.random stream, one draw per ray in ray order -- exactly the reference's draws.  (Batched scans
+    take their noise on the device: EngineScanner(uncertainty=...).)"""
 
     def __init__(self, init_pos, init_yaw, range, samples, max_distance, uncertainty=None):
         self.range = range
@@ -102,11 +103,17 @@ class EngineScanner:
     scan costs one C call: `ranges, hits = scanner.scan(pose)` with pose a [3,E] device tensor (x, y, yaw) of the engine's dtype.
     The returned tensors are reused by the next scan."""
 
-    def __init__(self, engine, range_, samples, max_distance, robot_radius=0.0, want_hits=True):
+    def __init__(self, engine, range_, samples, max_distance, robot_radius=0.0, want_hits=True, uncertainty=None, seed=0):
+        """uncertainty: LaserSensor's Gaussian range noise (sensors.py:71-74) applied on the device: every range becomes
+        clip(N(range, uncertainty), 0, max_distance); ray k of env e draws from the Philox4x32-10 stream keyed by `seed` at
+        counter (k, e, scan number), so scans are reproducible and successive scans independent.  (The reference draws from the
+        caller's global np.random stream: same distribution, different numbers.)"""
         import torch
         if max_distance > 10:
             raise ValueError("Maxium distance for laser is 10 meters")
         self.engine, self.torch = engine, torch
+        self.n_scans = 0
+        self._pose_dev = None
         self.ranges = torch.empty((engine.E, samples), dtype=engine.dtype, device=engine.device)
         self.hits = torch.empty((engine.E, samples), dtype=torch.int32, device=engine.device) if want_hits else None
         a = L.SnpLaserArgs()
@@ -119,13 +126,38 @@ class EngineScanner:
         a.range, a.max_distance, a.robot_radius = float(range_), float(max_distance), float(robot_radius)
         a.ranges = self.ranges.data_ptr()
         a.hits = None if self.hits is None else self.hits.data_ptr()
+        a.uncertainty = float(uncertainty) if uncertainty else 0.0
+        a.noise_seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.args, self.fn = a, L.lib().snp_laser
+
+    def _launch(self, pose, ranges_ptr, hits_ptr):
+        a = self.args
+        a.pose, a.ranges, a.hits = pose.data_ptr(), ranges_ptr, hits_ptr
+        a.noise_scan = self.n_scans
+        self.n_scans += 1
+        L.check(self.fn(ctypes.byref(a), ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)))
 
     def scan(self, pose):
         assert pose.is_contiguous() and pose.dtype == self.engine.dtype and pose.shape == (3, self.engine.E)
-        self.args.pose = pose.data_ptr()
-        L.check(self.fn(ctypes.byref(self.args), ctypes.c_void_p(self.torch.cuda.current_stream().cuda_stream)))
+        self._launch(pose, self.ranges.data_ptr(), None if self.hits is None else self.hits.data_ptr())
         return self.ranges, self.hits
+
+    def scan_host(self, pose_host, ranges_host, hits_host=None):
+        """The same scan with HOST buffers, end to end: `pose_host` [3,E] (pinned CPU tensor of the engine's dtype) is copied in,
+        and the kernel writes `ranges_host` [E,samples] (and `hits_host` int32) straight into PINNED host memory -- no device-to-host
+        copy follows the launch; returns after the stream is synchronised."""
+        t = self.torch
+        for h in (pose_host, ranges_host) + (() if hits_host is None else (hits_host,)):
+            if not (t.is_tensor(h) and h.is_pinned() and h.is_contiguous()):
+                raise ValueError("scan_host needs contiguous pinned CPU tensors (tensor.pin_memory())")
+        if ranges_host.dtype != self.engine.dtype or tuple(ranges_host.shape) != tuple(self.ranges.shape):
+            raise ValueError("ranges_host must be [E, samples] of the engine's dtype")
+        if self._pose_dev is None:
+            self._pose_dev = t.empty((3, self.engine.E), dtype=self.engine.dtype, device=self.engine.device)
+        self._pose_dev.copy_(pose_host, non_blocking=True)
+        self._launch(self._pose_dev, ranges_host.data_ptr(), None if hits_host is None else hits_host.data_ptr())
+        t.cuda.current_stream().synchronize()
+        return ranges_host, hits_host
 
 
 def scan_engine(engine, pose, range_, samples, max_distance, robot_radius=0.0, want_hits=True):

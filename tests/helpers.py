@@ -93,3 +93,23 @@ def moussaid_rest_ambiguity(states, n, dt, Ei=360.0, gamma=0.35):
         d[i] = np.inf
         bound[i] = (2 * Ei * np.exp(-d / gamma)).sum() * dt / m[i]
     return bound, 0.1 * (np.pi + 1) * m * bound
+
+
+def unicycle_step(pos, yaw, v, r, dt):
+    """RobotAgent.step with unicycle kinematics, action = ActionRot(v, r) (robot_agent.py:116-136), restated with the same NumPy
+    expressions: returns (new position, new yaw, new linear velocity).  Pinned against the live reference in
+    tests/test_oracle_live_reference.py::test_unicycle_robot_step_matches_the_live_reference."""
+    act = np.array([np.cos(yaw + r) * v, np.sin(yaw + r) * v], np.float64)
+    pos = np.asarray(pos, np.float64) + act * dt
+    yaw = (yaw + r) % (2 * np.pi)
+    return pos, yaw, np.array([np.cos(yaw) * v, np.sin(yaw) * v], np.float64)
+
+
+def constant_velocity_next(cur, dt, visible):
+    """propagate_humans_state_with_constant_velocity_model (crowd_nav/policy/cadrl.py:92-105) restated in NumPy: cur [..., N, 5|7] =
+    x, y, vx, vy, radius(, theta, omega) -> [..., N, 4|6] = x, y, (yaw,) Vx, Vy(, Omega).  Pinned against the live function in
+    tests/test_oracle_live_reference.py."""
+    x, y = cur[..., 0] + cur[..., 2] * dt, cur[..., 1] + cur[..., 3] * dt
+    if visible:
+        return np.stack([x, y, cur[..., 5] + cur[..., 6] * dt, cur[..., 2], cur[..., 3], cur[..., 6]], -1)
+    return np.stack([x, y, cur[..., 2], cur[..., 3]], -1)

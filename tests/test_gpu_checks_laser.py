@@ -229,3 +229,57 @@ def test_robot_push_out_vs_reference_golden_and_oracle():
     ref = oracle.robot_push_out(sc["states"][:, :, [0, 1, 8]], walls, robot[:, [0, 1, 8]])
     got = eng.robot_rows()[0][:, 0:2]
     assert np.array_equal(got, ref) and (np.abs(ref - robot[:, 0:2]).sum(1) > 0).sum() > 100
+
+
+def test_batched_laser_noise_has_the_reference_distribution():
+    """LaserSensor.add_uncertainty (sensors.py:71-74) for batched scans: clip(N(range, sigma), 0, max_distance), drawn on the device
+    from a counter-based Philox stream (the reference uses the caller's global np.random stream, so parity is distributional):
+    residuals are standard normal (moments + Kolmogorov-Smirnov), uncorrelated between neighbouring rays and envs, reproducible for
+    a (seed, scan number) and fresh for the next scan; clipping as in the reference."""
+    from scipy import stats
+    from social_navigation_pyenvs_b200 import CrowdEngine, scenarios, sensors, _lib as L
+    E, N, samples, sigma, maxd, rr = 256, 6, 360, 0.05, 10.0, 0.3
+    sc = scenarios.circular_crossing(E, N, seed0=5)
+    states = np.concatenate([sc["states"], sc["robot"][:, None]], 1)
+    eng = CrowdEngine.from_reference_arrays("sfm_helbing", states, sc["goals"], walls=scenarios.pack_walls(scenarios.EXAMPLE_WALLS), consider_robot=True)
+    pose = torch.stack([eng.robot[L.ROBOT_PX], eng.robot[L.ROBOT_PY], torch.full((E,), 1.0, dtype=torch.float64, device="cuda")]).contiguous()
+    clean = sensors.EngineScanner(eng, 2 * np.pi, samples, maxd, robot_radius=rr).scan(pose)[0].cpu().numpy().copy()
+    noisy_scanner = sensors.EngineScanner(eng, 2 * np.pi, samples, maxd, robot_radius=rr, uncertainty=sigma, seed=1234)
+    r0 = noisy_scanner.scan(pose)[0].cpu().numpy().copy()
+    r1 = noisy_scanner.scan(pose)[0].cpu().numpy().copy()
+    again = sensors.EngineScanner(eng, 2 * np.pi, samples, maxd, robot_radius=rr, uncertainty=sigma, seed=1234).scan(pose)[0].cpu().numpy()
+    other = sensors.EngineScanner(eng, 2 * np.pi, samples, maxd, robot_radius=rr, uncertainty=sigma, seed=1235).scan(pose)[0].cpu().numpy()
+    assert np.array_equal(r0, again) and not np.array_equal(r0, r1) and not np.array_equal(r0, other)
+    inner = (clean + rr > 10 * sigma) & (clean + rr < maxd - 10 * sigma)          # rays whose noise cannot reach a clipping bound
+    assert inner.sum() > 20000
+    z = ((r0 - clean) / sigma)[inner]
+    n = z.size
+    assert abs(z.mean()) < 5 / np.sqrt(n) and abs(z.var() - 1) < 0.05 and abs(stats.skew(z)) < 0.08 and abs(stats.kurtosis(z)) < 0.15
+    assert stats.kstest(z, "norm").pvalue > 1e-3
+    both = inner[:, 1:] & inner[:, :-1]
+    za = (r0 - clean) / sigma
+    assert abs(np.corrcoef(za[:, 1:][both], za[:, :-1][both])[0, 1]) < 0.02       # neighbouring rays
+    z2 = ((r1 - clean) / sigma)[inner]
+    assert abs(np.corrcoef(z, z2)[0, 1]) < 0.02                                  # successive scans
+    # clipping (sensors.py:73): a miss reads max_distance and can only come back lower; nothing leaves [0, max_distance]
+    miss = clean + rr == maxd
+    assert miss.any() and (r0[miss] + rr <= maxd).all() and ((r0[miss] + rr == maxd).mean() > 0.4)
+    assert (r0 + rr >= 0).all() and (r0 + rr <= maxd).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_scan_host_writes_pinned_buffers_directly(dtype):
+    from social_navigation_pyenvs_b200 import CrowdEngine, scenarios, sensors, _lib as L
+    E, N, samples = 300, 9, 181
+    sc = scenarios.circular_crossing(E, N, seed0=15)
+    states = np.concatenate([sc["states"], sc["robot"][:, None]], 1)
+    eng = CrowdEngine.from_reference_arrays("sfm_helbing", states, sc["goals"], walls=scenarios.pack_walls(scenarios.EXAMPLE_WALLS), consider_robot=True, dtype=dtype)
+    pose = torch.stack([eng.robot[L.ROBOT_PX], eng.robot[L.ROBOT_PY], torch.full((E,), -0.4, dtype=dtype, device="cuda")]).contiguous()
+    scanner = sensors.EngineScanner(eng, np.pi, samples, 8.0, robot_radius=0.3)
+    ranges, hits = (t.clone() for t in scanner.scan(pose))
+    rh = torch.full((E, samples), -1.0, dtype=dtype).pin_memory()
+    hh = torch.full((E, samples), -7, dtype=torch.int32).pin_memory()
+    scanner.scan_host(pose.cpu().pin_memory(), rh, hh)
+    assert torch.equal(rh, ranges.cpu()) and torch.equal(hh, hits.cpu())
+    with pytest.raises(ValueError):
+        scanner.scan_host(pose.cpu(), rh, hh)   # pageable pose

@@ -152,3 +152,32 @@ def test_lookahead_full_size_properties(dtype):
     rot2 = rot.clone()
     rot3, _ = eng.lookahead(0.25, bulk_store=False)
     assert torch.equal(rot2, rot3)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 1e-4)])
+def test_lookahead_without_querying_the_env(dtype, tol):
+    """query_env = False (crowd_nav/policy/cadrl.py:259): the humans are propagated with the constant-velocity model (:92-105)
+    instead of a peek of the motion model; rewards bit-exact, rotated states within tolerance, for headed and non-headed models
+    (a non-headed crowd with non-zero omega integrates its yaw here, unlike the peek)."""
+    from social_navigation_pyenvs_b200 import CrowdEngine, _lib as L
+    from helpers import constant_velocity_next
+    E, n = 64, 9
+    sc, S, R = _batch(E, n, 515)
+    S[:, :, 7] = np.random.RandomState(1).uniform(-0.8, 0.8, (E, n))   # omega
+    acts = _actions()
+    for model, vis in [("hsfm_farina", True), ("sfm_guo", True), ("sfm_helbing", False)]:
+        eng = CrowdEngine.from_reference_arrays(model, S, sc["goals"], consider_robot=False, all_params_equal=True, robot=R, dtype=dtype)
+        eng.set_action_space(acts)
+        before = eng.dyn.clone()
+        rot, rew = eng.lookahead(0.25, theta_and_omega_visible=vis, query_env=False)
+        assert torch.equal(eng.dyn, before)
+        d, st, rb = eng.dyn.double().cpu().numpy(), eng.stat.double().cpu().numpy(), eng.robot.double().cpu().numpy()
+        cur = np.stack([d[L.DYN_PX], d[L.DYN_PY], d[L.DYN_VX], d[L.DYN_VY], st[L.STAT_R]] + ([d[L.DYN_TH], d[L.DYN_OM]] if vis else []), -1)
+        rob = np.stack([rb[L.ROBOT_PX], rb[L.ROBOT_PY], rb[L.ROBOT_VX], rb[L.ROBOT_VY], rb[L.ROBOT_R], rb[L.ROBOT_GX], rb[L.ROBOT_GY],
+                        rb[L.ROBOT_VD], rb[L.ROBOT_TH]], -1)
+        rot_ref, rew_ref = oracle.lookahead(cur, constant_velocity_next(cur, 0.25, vis), rob, acts, 0.25, visible=vis)
+        if dtype == torch.float64:
+            assert np.array_equal(rew.cpu().numpy(), rew_ref), (model, vis)
+        else:  # the propagated positions are single precision here, the reference's double: decisions may differ at the margin only
+            assert (rew.cpu().numpy() != rew_ref).mean() < 0.01
+        assert rel_err(rot.double().cpu().numpy(), rot_ref).max() < tol, (model, vis)

@@ -29,7 +29,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
         assert hasattr(handle, name), f"{name} declared in include/snp_b200.h but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared, "ctypes signature table and header disagree"
     lib = _lib.lib()
-    assert lib.snp_abi_version() == 2
+    assert lib.snp_abi_version() == 3
 
 
 def test_ctypes_struct_layouts_match_the_header(tmp_path):

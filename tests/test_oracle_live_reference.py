@@ -140,3 +140,34 @@ def test_sim_update_matches_the_live_reference(mg, model, robot_model, seed, n, 
         got_r = np.concatenate([rb[0, :8], rb[0, 10:12], rD[0]])
         worst = max(worst, rel_err(got_h, ref_h).max(), rel_err(got_r, ref_r).max())
     assert worst < 1e-9, worst
+
+
+def test_unicycle_robot_step_matches_the_live_reference(mg):
+    """RobotAgent.step / compute_position with unicycle kinematics (robot_agent.py:116-136) vs tests/helpers.unicycle_step, which the
+    GPU test of robot_mode 3 steps the oracle with: bit-identical over 200 random (v, r, dt) calls.  (The reference's own swept
+    check cannot be run with an ActionRot: social_nav_sim.py:973 reads robot.theta, which is never assigned -- TypeError.)"""
+    from crowd_nav.utils.action import ActionRot
+    from helpers import unicycle_step
+    sim = mg.cc_sim("sfm_helbing", 4401, 5, robot_visible=True)
+    robot = sim.robot
+    robot.kinematics = "unicycle"
+    rng = np.random.RandomState(3)
+    pos, yaw = np.array(robot.position, np.float64), float(robot.yaw)
+    for _ in range(200):
+        v, r, dt = float(rng.uniform(0, 1.2)), float(rng.uniform(-0.6, 0.6)), float(rng.choice([0.0125, 0.25]))
+        want_pos = robot.compute_position(ActionRot(v, r), dt)
+        robot.step(ActionRot(v, r), dt)
+        pos, yaw, vel = unicycle_step(pos, yaw, v, r, dt)
+        assert np.array_equal(want_pos, robot.position) and np.array_equal(pos, robot.position)
+        assert yaw == robot.yaw and np.array_equal(vel, robot.linear_velocity)
+
+
+def test_constant_velocity_propagation_matches_the_live_reference(mg):
+    """propagate_humans_state_with_constant_velocity_model (cadrl.py:92-105, the policies' query_env = False branch) vs the NumPy
+    restatement the GPU test of CrowdEngine.lookahead(query_env=False) feeds the oracle with: bit-identical."""
+    from crowd_nav.policy.cadrl import propagate_humans_state_with_constant_velocity_model as ref_fn
+    from helpers import constant_velocity_next
+    rng = np.random.RandomState(9)
+    for vis in (False, True):
+        cur = rng.uniform(-3, 3, (11, 7 if vis else 5))
+        assert np.array_equal(ref_fn(cur, 0.25, theta_and_omega_visible=vis), constant_velocity_next(cur, 0.25, vis))
