@@ -423,7 +423,7 @@ template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, 
         else if (soc == 1 && c->params[3] > 0 && c->params[7] > 0) margin = under * (c->params[3] > c->params[7] ? c->params[3] : c->params[7]);
     }
     la.cull_margin = (T)margin;
-    la.apt = margin >= 0.0 ? 1 : kMaxAgentsPerThread;
+    la.apt = (margin >= 0.0 && sizeof(T) == 8) ? 1 : kMaxAgentsPerThread;  // fp32 pair evaluations are short: the finer split only adds launch overhead there
     switch (o->type) {
         case 0: return launch_large<T, 0, 0, 0>(la, st);
         case 1: return launch_large<T, 1, 1, 0>(la, st);

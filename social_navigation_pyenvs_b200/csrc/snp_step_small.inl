@@ -164,6 +164,14 @@ __device__ __forceinline__ void social_force_halved(const Params<T> &P, const do
     int k = 1;
     for (; k + kPairUnroll - 1 <= rounds; k += kPairUnroll)
         halved_rounds<T, SOC, kPairUnroll>(P, tbl, pp + k, pv + k, pr + k, me, k, wrap_at, N, wmask, gbase, src, fsx, fsy);
+    // remaining rounds (fewer than kPairUnroll) in flight TOGETHER as well: a crowd of 5 has 2 rounds in all, and a lone warp per
+    // SMSP (4096 envs x 5 humans = 683 warps on 592 schedulers) has nothing else to hide their latency with
+    if constexpr (kPairUnroll > 2) {
+        if (rounds - k + 1 >= 2) {
+            halved_rounds<T, SOC, 2>(P, tbl, pp + k, pv + k, pr + k, me, k, wrap_at, N, wmask, gbase, src, fsx, fsy);
+            k += 2;
+        }
+    }
     for (; k <= rounds; ++k) halved_rounds<T, SOC, 1>(P, tbl, pp + k, pv + k, pr + k, me, k, wrap_at, N, wmask, gbase, src, fsx, fsy);
     // tail: the antipodal pair of an even crowd (both ends evaluate it) and the robot, which exerts force but feels none
     // (forces.py:146,151) -- independent evaluations again, one vote
