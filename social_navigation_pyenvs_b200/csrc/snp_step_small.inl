@@ -174,27 +174,29 @@ __device__ __forceinline__ void social_force_halved(const Params<T> &P, const do
     }
     for (; k <= rounds; ++k) halved_rounds<T, SOC, 1>(P, tbl, pp + k, pv + k, pr + k, me, k, wrap_at, N, wmask, gbase, src, fsx, fsy);
     // tail: the antipodal pair of an even crowd (both ends evaluate it) and the robot, which exerts force but feels none
-    // (forces.py:146,151) -- independent evaluations again, one vote
-    const bool anti = !(N & 1);
-    T fax = T(0), fay = T(0), frx = T(0), fry = T(0);
-    Vec2<T> oa{}, ova{}, orb{}, ovr{};
-    T rsa = T(0), rsr = T(0);
-    const bool sw = k >= wrap_at;
-    bool contact = false;
-    if (anti) {
-        oa = pp[k]; ova = pv[k]; rsa = pr[k].a;
-        contact |= Real<T>::positive_(halved_eval<T, SOC, false>(P, tbl, me, oa, ova, rsa, sw, fax, fay));
+    // (forces.py:146,151).  Two self-contained blocks (each with its own vote): nothing is zero-initialised or carried for the case
+    // that does not occur -- an odd crowd with a robot, the benchmark shape, runs exactly one pair evaluation here.
+    if (!(N & 1)) {
+        const Vec2<T> oa = pp[k], ova = pv[k];
+        const T rsa = pr[k].a;
+        const bool sw = k >= wrap_at;
+        T fax, fay;
+        if (__any_sync(wmask, Real<T>::positive_(halved_eval<T, SOC, false>(P, tbl, me, oa, ova, rsa, sw, fax, fay))))
+            halved_eval<T, SOC, true>(P, tbl, me, oa, ova, rsa, sw, fax, fay);
+        fsx += fax; fsy += fay;
     }
     if (with_robot) {
-        orb = pos[N]; ovr = vel[N]; rsr = rs16[N].a;
-        contact |= Real<T>::positive_(pair_eval<T, SOC, false>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, orb.a, orb.b, ovr.a, ovr.b, rsr, frx, fry));
+        const Vec2<T> orb = pos[N];
+        const T rsr = rs16[N].a;
+        T frx, fry;
+        const bool contact = Real<T>::positive_(pair_eval<T, SOC, false>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, orb.a, orb.b, SOC == 2 ? vel[N].a : T(0),
+                                                                           SOC == 2 ? vel[N].b : T(0), rsr, frx, fry));
+        if (__any_sync(wmask, contact)) {
+            const Vec2<T> ovr = vel[N];
+            pair_eval<T, SOC, true>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, orb.a, orb.b, ovr.a, ovr.b, rsr, frx, fry);
+        }
+        fsx += frx; fsy += fry;
     }
-    if (__any_sync(wmask, contact)) {
-        if (anti) halved_eval<T, SOC, true>(P, tbl, me, oa, ova, rsa, sw, fax, fay);
-        if (with_robot) pair_eval<T, SOC, true>(P, tbl, me.px, me.py, me.vx, me.vy, me.rs, orb.a, orb.b, ovr.a, ovr.b, rsr, frx, fry);
-    }
-    fsx += fax; fsy += fay;
-    fsx += frx; fsy += fry;
 }
 
 // ---- robot driven by its own SFM / HSFM model (robot_mode 2; motion_model_manager.py:593-653) ----
@@ -483,10 +485,14 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
     // every squared distance that can round to a touching distance lies below (r + r_robot)^2 (1 + 2^-48)
     const double touch_thr = __dadd_rn((double)me.r, (double)rr);
     const double touch_hi = touch_thr * touch_thr * (1.0 + 3.5527136788005009e-15);
-    for (int s = 0; s < a.n_substeps; ++s) {
+    // loop-invariant switches as predicates (otherwise every sub-step re-reads them from the constant bank)
+    const bool move_robot = a.robot_mode == 1 && has_robot, robot_seen = a.consider_robot != 0, walls_on = a.W > 0, numba_sem = a.numba != 0;
+    const bool touch_on = a.track_touch && has_robot, clock_on = a.time_now != nullptr;
+    const int n_sub = a.n_substeps;
+    for (int s = 0; s < n_sub; ++s) {
         const EntView<T> ents{ents0 + (size_t)(s & 1) * 2 * slots + gslot, ents0 + (size_t)(s & 1) * 2 * slots + slots + gslot};
         if constexpr (!CTA) { if (live) ents.put(i - N, me.px, me.py, me.vx, me.vy); }  // second copy: the halved loop's wrap-free run
-        if (a.robot_mode == 1 && has_robot) {  // robot_agent.py:126-131 (holonomic): p = p + a*dt ; v = a
+        if (move_robot) {  // robot_agent.py:126-131 (holonomic): p = p + a*dt ; v = a
             if (sizeof(T) == 8) { rpx = (T)__dadd_rn((double)rpx, __dmul_rn((double)ax, (double)dt)); rpy = (T)__dadd_rn((double)rpy, __dmul_rn((double)ay, (double)dt)); }
             else { rpx = rpx + ax * dt; rpy = rpy + ay * dt; }
             rvx = ax; rvy = ay;
@@ -500,7 +506,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             }
         }
         if (live) ents.put(i, me.px, me.py, me.vx, me.vy);
-        if (!ROBOT2 && leader && a.consider_robot) ents.put(N, rpx, rpy, rvx, rvy);
+        if (!ROBOT2 && leader && robot_seen) ents.put(N, rpx, rpy, rvx, rvy);
         if constexpr (CTA) __syncthreads(); else __syncwarp(wmask);
 
         if constexpr (ROBOT2) if (a.robot_mode == 2) {
@@ -562,19 +568,19 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             // evaluated at the position the sub-step starts from
             {
                 GoalVec<T> gv = goal_vec<T>(me);
-                if (a.numba ? (gv.dist <= me.r) : (gv.dist < me.r)) {
+                if (numba_sem ? (gv.dist <= me.r) : (gv.dist < me.r)) {
                     gidx = (gidx + 1 >= gcnt) ? 0 : gidx + 1;
                     T ngx, ngy;
                     if (gcache) { const Vec2<T> ng = goal_s[(size_t)gidx * blockDim.x]; ngx = ng.a; ngy = ng.b; }
                     else { ngx = a.goals[((size_t)gidx * 2 + 0) * EN + aidx]; ngy = a.goals[((size_t)gidx * 2 + 1) * EN + aidx]; }
                     if (ngx != me.gx || ngy != me.gy) { me.gx = ngx; me.gy = ngy; gv = goal_vec<T>(me); }
                 }
-                desired_force<T>(P, me, gv, a.numba != 0);
+                desired_force<T>(P, me, gv, numba_sem);
             }
             // wall force
-            if (a.W > 0) obstacle_force<T, OBS>(P, exp_tbl_s, wmask, segs, seg_cnt, a.W, a.S, a.numba != 0, me.px, me.py, me.vx, me.vy, me.rs, fox, foy);
+            if (walls_on) obstacle_force<T, OBS>(P, exp_tbl_s, wmask, segs, seg_cnt, a.W, a.S, numba_sem, me.px, me.py, me.vx, me.vy, me.rs, fox, foy);
             if constexpr (HALF && !CTA) {
-                social_force_halved<T, SOC>(P, exp_tbl_s, ents.pos, ents.vel, rs_g, me, i, N, a.consider_robot != 0, wmask, lane - i, fsx, fsy);
+                social_force_halved<T, SOC>(P, exp_tbl_s, ents.pos, ents.vel, rs_g, me, i, N, robot_seen, wmask, lane - i, fsx, fsy);
             } else if constexpr (HALF && CTA) {
                 // Block-packed halved loop, phase 1: lane i evaluates the pairs {i, (i+k) mod N}, k = 1..rounds, keeps +f and
                 // leaves -f for the partner in plane k of the exchange buffer (written at the PARTNER's slot: conflict-free).
@@ -697,7 +703,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             }
         }
         if (live) {
-            if (a.track_touch && has_robot) {
+            if (touch_on) {
                 // ||p - p_robot|| < r + r_robot (robot_agent.py:37), decided on the square whenever that is safe: the IEEE square
                 // root only runs for lanes within 2^-48 (relative) of touching or beyond, which is rare
                 const double tx = (double)me.px - (double)rpx, ty = (double)me.py - (double)rpy;
@@ -705,7 +711,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
                 if (t2 < touch_hi) touched |= sqrt(t2) < __dadd_rn((double)me.r, (double)rr);
             }
         }
-        if (a.time_now) tnow = __dadd_rn(tnow, a.dt_d);
+        if (clock_on) tnow = __dadd_rn(tnow, a.dt_d);
     }
 
     // ---- post-step checks (gym:107-118) ----
