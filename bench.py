@@ -136,15 +136,19 @@ def measured_traffic(args):
 
 
 def issue_model(key, clocks, measured_ms):
-    """Issue-port bound of the dominant kernel: warp instructions of ONE launch from the committed ncu capture of this workload
-    (profiles/issue_model.json, written by tools/issue_cost.py), an FP64 instruction costing 2 issue cycles of its SMSP with nothing
-    issuing in its shadow (profiles/r01_pipe_microbench.txt), at the SM clock sampled during the timed region."""
+    """Pipe / issue bound of the dominant kernel: warp instructions of ONE launch from the committed ncu capture of this workload
+    (profiles/issue_model.json, written by tools/issue_cost.py), costed with the pipe figures tools/pipe_microbench.cu measured on
+    B200 (profiles/r02_pipe_microbench.txt): DFMA 3.0 cycles of its SMSP's FP64 pipe, DMUL / DADD / DSETP 2.06, FMA-pipe instructions
+    on the same dispatch port, ALU-pipe instructions overlapping at 2 cycles each; bound = max(port, ALU, issue slots), at the SM
+    clock sampled during the timed region."""
     try:
         m = json.load(open(os.path.join(ROOT, "profiles", "issue_model.json")))[key]
         mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
         bound_ms = m["issue_cycles_per_smsp"] / (mhz * 1e3)
         return {"bound_ms": bound_ms, "frac": bound_ms / measured_ms, "fp64_warp_instructions": m["fp64_warp_instructions"],
-                "other_warp_instructions": m["other_warp_instructions"], "fp64_issue_cycles": m["fp64_issue_cycles"], "sm_mhz": mhz,
+                "other_warp_instructions": m["other_warp_instructions"], "fp64_issue_cycles": m["fp64_issue_cycles"],
+                "port_cycles_per_smsp": m.get("port_cycles_per_smsp"), "alu_cycles_per_smsp": m.get("alu_cycles_per_smsp"),
+                "issue_slots_per_smsp": m.get("issue_slots_per_smsp"), "sm_mhz": mhz,
                 "source": "profiles/issue_model.json (" + m["source"] + ")"}
     except (OSError, KeyError, ValueError, TypeError):
         return None
