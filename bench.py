@@ -398,6 +398,12 @@ def large_crowd_probe(tdtype, rank, world, substeps_per_call=10, calls=3):
     from social_navigation_pyenvs_b200.parallel import max_over_ranks
     sc = scenarios.jittered_grid_crowd(256, pitch=2.0, jitter=0.5, seed=0)
     perm = scenarios.spatial_order(sc["states"][0, :, 0:2])
+    if world > 1 and os.environ.get("SNP_LARGE_DEAL", "1") == "1":
+        # load balance: the 128-human tiles (compact patches) are dealt to the ranks round-robin, so every rank owns patches from
+        # all over the crowd instead of one block of strips (an interior block has ~25 % more near neighbours than a corner one).
+        # The numbering is the caller's; no force depends on it.
+        tiles = perm.reshape(-1, 128)
+        perm = np.concatenate([tiles[r::world] for r in range(world)]).reshape(-1)
     S, G = np.ascontiguousarray(sc["states"][0, perm]), np.ascontiguousarray(sc["goals"][0, perm])
     n = S.shape[0]
     crowd = LargeCrowd("hsfm_farina", S, G, dtype=tdtype, rank=rank, world=world, exchange=os.environ.get("SNP_EXCHANGE", "auto"))
@@ -434,7 +440,8 @@ def large_crowd_probe(tdtype, rank, world, substeps_per_call=10, calls=3):
                                 "sub-step loop in one C call (snp_large_run_p2p)",
                          "fused": "single GPU: sub-step loop in one C call (snp_large_run_p2p), no exchange",
                          "nccl": "NCCL all-gather of the [5, N] view per sub-step"}[crowd.exchange],
-            "substeps_per_call": substeps_per_call, "bit_equal_to_single_gpu": equal, "timing": "CUDA events around each call, max over ranks"}
+            "substeps_per_call": substeps_per_call, "bit_equal_to_single_gpu": equal, "timing": "CUDA events around each call, max over ranks",
+            "agent_order": "patch by patch (scenarios.spatial_order)" + (", 128-human tiles dealt round-robin to the ranks" if world > 1 and os.environ.get("SNP_LARGE_DEAL", "1") == "1" else "")}
 
 
 def run_laser(args, rank, world, local_rank):
@@ -800,9 +807,15 @@ def main():
     ach_tflops = launch_flops / per_launch_s / 1e12
     ach_gbs = launch_bytes / per_launch_s / 1e9
     ach_sfu = E * N * SUBSTEPS * cost["sfu"] / per_launch_s / 1e9
+    info4 = (ctypes.c_int32 * 4)()
+    _lib.check(lib.snp_device_info(info4))
+    mhz = clocks.summary().get("sm_mhz") or clocks.summary().get("sm_max_mhz") or 1965.0
+    nominal = info4[0] * (64 if args.dtype == "f64" else 128) * 2 * mhz * 1e6 / 1e12   # SMs x FMA lanes x 2 flop x sampled clock
     roofline = {"bound": "fp64" if args.dtype == "f64" else "fp32", "achieved": ach_tflops, "peak": pipe.value, "unit": "TFLOP/s",
                 "frac": ach_tflops / pipe.value, "traffic": measured_traffic(args),
                 "peak_source": "measured in this run: register-resident FMA loop on all SMs (snp_measure_pipe_peak)",
+                "peak_nominal": nominal, "frac_of_nominal": ach_tflops / nominal,
+                "peak_nominal_source": f"{info4[0]} SMs x {64 if args.dtype == 'f64' else 128} FMA lanes x 2 x {mhz:.0f} MHz sampled during the timed region",
                 "kernel": "snp::k_step (fused 20 sub-steps)", "flops_per_agent_substep": cost["flops"],
                 "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": hbm_peak, "frac": ach_gbs / hbm_peak, "peak_source": hbm_src,
                         "bytes_per_agent_step": cost["words"] * wbytes / SUBSTEPS},

@@ -310,11 +310,23 @@ class CrowdEngine:
         fused step runs, observation [4,E,N] (px,py,vx,vy), flags [E] int32 and checks [E,4] float64 land in the host buffers and the
         stream is synchronised.  The buffers are CPU tensors or NumPy arrays of the engine's dtype.  PINNED result buffers are written
         by the kernel itself (zero-copy: no D2H transfer after the launch); pageable ones -- or staged=True -- get D2H copies."""
-        o = self._opts(dt, n_substeps, robot_mode=1, pre_checks=pre_checks, post_checks=post_checks, track_touch=track_touch, advance_time=True)
-        if staged:
-            o.reserved |= 16
+        # the two descriptor blocks are rebuilt only when something they describe changed (a gym loop calls this every 0.25 s of
+        # simulated time with the same arguments; building them costs more host time than the launch)
+        key = (float(dt), int(n_substeps), bool(pre_checks), int(post_checks), bool(track_touch), bool(staged), self.full_pair_loop, self.mapping,
+               self.consider_robot, self.symmetric, self.numba_compat, tuple(self.consts), self.respawn_bounds,
+               None if self.respawn_envs is None else self.respawn_envs.data_ptr(), self.params.tobytes(),
+               self.dyn.data_ptr(), self.stat.data_ptr(), self.goals.data_ptr(), self.goal_idx.data_ptr(), self.goal_cnt.data_ptr(),
+               None if self.agent_params is None else self.agent_params.data_ptr(), None if self.robot is None else self.robot.data_ptr(),
+               None if self.walls is None else self.walls.data_ptr(), self.W, self.S, self.walls_per_env, self.action.data_ptr(),
+               self.time_now.data_ptr(), self.flags.data_ptr(), self.checks.data_ptr())
+        cached = getattr(self, "_host_call", None)
+        if cached is None or cached[0] != key:
+            o = self._opts(dt, n_substeps, robot_mode=1, pre_checks=pre_checks, post_checks=post_checks, track_touch=track_touch, advance_time=True)
+            if staged:
+                o.reserved |= 16
+            cached = self._host_call = (key, self._crowd(), o)
         hp = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr() if torch.is_tensor(t) else t.ctypes.data)
-        L.check(self.lib.snp_gym_step_host(ctypes.byref(self._crowd()), ctypes.byref(o), hp(action_host), hp(obs_host), hp(flags_host),
+        L.check(self.lib.snp_gym_step_host(ctypes.byref(cached[1]), ctypes.byref(cached[2]), hp(action_host), hp(obs_host), hp(flags_host),
                                            hp(checks_host), _stream()))
 
     def run_checks(self, action=None, pre=True, post=True):

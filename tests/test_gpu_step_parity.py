@@ -114,7 +114,11 @@ def test_halved_and_full_pair_loops_agree(name):
 @pytest.mark.parametrize("name", ["pt5_robot_hsfm_farina", "pt7_sfm_helbing", "pt5_robot_hsfm_new_guo", "pt10_robot_sfm_guo"])
 def test_parallel_traffic_with_respawn_full_trajectory(name):
     """1600 fused sub-steps of the parallel-traffic scenario with 5-11 respawns (mmm:407-422) against the recorded reference:
-    positions jump to the right end, the goal list collapses to (gx, new y) -- all inside the kernel."""
+    positions jump to the right end, the goal list collapses to (gx, new y) -- all inside the kernel.
+    The engine runs FREE for the whole episode (it is never re-synchronised with the recording), so the bound below is a multi-step
+    divergence allowance, not the parity bar: single steps from identical states meet 1e-9 (test_single_step_vs_reference_golden,
+    tests/test_gpu_live_reference.py); over 1600 steps of an N-body system the 1e-16 rounding differences of a different summation
+    order grow to at most ~1e-8 here."""
     d = load_traj(name)
     n = d["n"]
     S, G, D, rv = inputs_at(d, 0)
