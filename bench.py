@@ -436,8 +436,8 @@ def large_crowd_probe(tdtype, rank, world, substeps_per_call=10, calls=3):
     crowd.check_peers()
     return {"workload": "65536_hsfm_single_crowd", "humans": n, "n_gpus": world, "scaling": "strong", "dtype": "f64" if tdtype == torch.float64 else "f32",
             "ms_per_substep": culled, "agent_steps_per_s": n / (culled * 1e-3), "ms_per_substep_all_pairs": allpairs,
-            "exchange": {"p2p": "peer (NVLink) stores of entries + tile boxes fused into the finish kernel, cross-rank epoch flags signalled by its last "
-                                "block and awaited by the next pairs kernel (no barrier launch), sub-step loop in one C call (snp_large_run_p2p)",
+            "exchange": {"p2p": "peer (NVLink) stores of entries + tile boxes fused into the finish kernel, device-side barrier kernel, "
+                                "sub-step loop in one C call (snp_large_run_p2p)",
                          "fused": "single GPU: sub-step loop in one C call (snp_large_run_p2p), no exchange",
                          "nccl": "NCCL all-gather of the [5, N] view per sub-step"}[crowd.exchange],
             "substeps_per_call": substeps_per_call, "bit_equal_to_single_gpu": equal, "timing": "CUDA events around each call, max over ranks",

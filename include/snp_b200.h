@@ -252,14 +252,12 @@ int snp_large_step(const snp_crowd *crowd, const snp_step_opts *opts, const void
 int snp_large_step_p2p(const snp_crowd *crowd, const snp_step_opts *opts, const void *others, int64_t M, int64_t self_offset,
                        const void *const *peer_next_views, int32_t n_peers, void *scratch, int64_t scratch_bytes, void *cuda_stream);
 /* `n_substeps` of the agent-sharded step in ONE call (the loop SocialNavGym.step runs, social_nav_gym.py:240-245, for one crowd spread
- * over `world` GPUs of a node): per sub-step two launches (tiled pairs, finish), the cross-rank synchronisation folded into them (the
- * last finish block signals this rank's epoch to every rank, the next pairs kernel waits for all of them), all enqueued on
+ * over `world` GPUs of a node): per sub-step two launches (tiled pairs, finish) + one single-warp barrier kernel, all enqueued on
  * `cuda_stream` without returning to the host.  Buffers, all peer-mapped (e.g. torch symmetric memory), as host arrays of `world`
  * device pointers indexed by rank: `peer_views_a` / `peer_views_b` = the two view buffers, each [5][M] entities followed by the
  * view's [ceil(M/128)][5] tile-box table (the producer writes entries AND boxes into every rank's next buffer); `peer_flags` =
  * uint64[world] barrier slots per rank, zero-initialised once.  `first_is_b` selects the buffer that holds the current view;
- * `epoch_base` must grow by `n_substeps` from call to call.  `error_flag` = device int32[2], zero-initialised once: [0] is set if a
- * peer never signalled an epoch (time-out instead of a hang), [1] is the kernels' own counter of retired finish blocks. */
+ * `epoch_base` must grow by `n_substeps` from call to call.  `error_flag` (device int32) is set if a peer never reached a barrier. */
 int snp_large_run_p2p(const snp_crowd *crowd, const snp_step_opts *opts, const void *const *peer_views_a, const void *const *peer_views_b,
                       int32_t first_is_b, int64_t M, int64_t self_offset, int32_t world, int32_t rank, const void *const *peer_flags,
                       uint64_t epoch_base, int32_t n_substeps, int32_t *error_flag, void *scratch, int64_t scratch_bytes, void *cuda_stream);

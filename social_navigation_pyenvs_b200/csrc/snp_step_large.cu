@@ -49,13 +49,6 @@ template <typename T> struct LargeArgs {
     T cull_margin;  // distance beyond r+s sums at which the pair law is exactly zero; < 0 disables culling
     int boxes_ready;  // the tile boxes of `others` are already in `boxes` (written by the previous sub-step's producer)
     int apt;          // agents per thread of the pairs kernel (1 or 2): fixes the i-block size the `live` map is indexed by
-    // cross-rank synchronisation folded into the two kernels (snp_large_run_p2p, world > 1): the pairs kernel WAITS until every
-    // rank has signalled `wait_epoch` (the producers of the view it is about to read have finished), the last finish block to
-    // retire SIGNALS `signal_epoch` to every rank.  flags[p] = rank p's slot array [world], peer-mapped; sync_words = {error, done}.
-    unsigned long long *flags[8];
-    unsigned long long wait_epoch, signal_epoch;
-    int sync_world, sync_rank;
-    int *sync_words;
 };
 
 template <typename T> __device__ __forceinline__ T warp_min(T v) {
@@ -102,20 +95,6 @@ __global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
     const KArgs<T> &a = la.k;
     bool have_tbl = false;  // the 16 kB exp table is staged only by CTAs that evaluate at least one tile (most are culled)
 
-    if (la.sync_world > 1 && la.wait_epoch > 0) {
-        // nothing of the view (not even its tile boxes) may be read before every rank's producer of it has retired
-        if (threadIdx.x < la.sync_world) {
-            const unsigned long long *src = la.flags[la.sync_rank] + threadIdx.x;
-            const long long t0 = clock64();
-            unsigned long long seen = 0;
-            while (true) {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
-                if (seen >= la.wait_epoch) break;
-                if (clock64() - t0 > 40000000000LL) { la.sync_words[0] = 1; break; }  // ~20 s: a peer died; report instead of hanging
-            }
-        }
-        __syncthreads();
-    }
     const long long N = a.EN, M = la.M;
     const Params<T> &P = a.P;
     const long long j_begin = (long long)blockIdx.y * kChunk;
@@ -339,36 +318,38 @@ __global__ void __launch_bounds__(kTile) k_large_finish(const LargeArgs<T> la) {
             for (int p = 0; p < la.n_peers; ++p) la.peer_boxes[p][tile * 5 + threadIdx.x] = out[threadIdx.x];
         }
     }
-    if (la.sync_world > 1 && la.signal_epoch > 0) {
-        // every thread's peer stores are fenced at system scope before its block counts itself done; the block that observes all the
-        // others done publishes this rank's epoch to every rank (release), so a reader that acquires the epoch sees all entries + boxes
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int prev = atomicAdd(&la.sync_words[1], 1);
-            if (prev == (int)gridDim.x - 1) {
-                la.sync_words[1] = 0;
-                __threadfence_system();
-                for (int p = 0; p < la.sync_world; ++p) {
-                    unsigned long long *dst = la.flags[p] + la.sync_rank;
-                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(la.signal_epoch) : "memory");
-                }
-            }
-        }
-    }
 }
 
-// Cross-rank synchronisation of our own between sub-steps, folded into the two kernels (no host-driven collective, no extra
-// launch): slot [r] of every rank's flag array receives rank r's epoch through a release store over NVLink from the LAST finish block
-// of rank r to retire; a rank's pairs kernel starts reading the next view only once its own slots have all reached that epoch.
-// Epochs only grow, so nothing is ever reset and a fast rank that already signals the next epoch cannot release a slow one early.
-// A rank that never arrives trips a time-out (sync_words[0] = 1) instead of hanging the GPU.
+// Cross-rank barrier of our own between sub-steps (one tiny kernel instead of a host-driven collective): slot [r] of every rank's
+// flag array receives rank r's epoch through a peer store; a rank passes once all its slots have reached the epoch.  Epochs only
+// grow, so nothing is ever reset and a fast rank that is already signalling the next barrier cannot release a slow one early.
+// The kernel boundary orders the finish kernel's peer stores before the signal (fence.sc.sys + release store); the acquire loads
+// order the next sub-step's reads after it.  A rank that never arrives trips the time-out instead of hanging the GPU.
 struct BarrierArgs {
     unsigned long long *flags[8];  // every rank's flag array [world] (peer-mapped), index = rank
     int world, rank;
     unsigned long long epoch;
-    int *error;                    // int32[2]: {error flag, count of finish blocks retired in the current sub-step}
+    int *error;
 };
+
+__global__ void k_rank_barrier(const BarrierArgs b) {
+    const int t = threadIdx.x;
+    if (t < b.world) {
+        __threadfence_system();
+        unsigned long long *dst = b.flags[t] + b.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(b.epoch) : "memory");
+        const unsigned long long *src = b.flags[b.rank] + t;
+        const long long t0 = clock64();
+        unsigned long long seen = 0;
+        while (true) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
+            if (seen >= b.epoch) break;
+            if (clock64() - t0 > 40000000000LL) { *b.error = 1; break; }  // ~20 s: a peer died; report instead of spinning forever
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+}
 
 // x, y, vx, vy, r+safety of every agent into a [5][stride] view (v = R(yaw) bv for headed models, mmm:448).
 template <typename T> __global__ void k_large_publish(const T *dyn, const T *stat, long long N, int headed, T *view, long long stride, long long offset) {
@@ -411,12 +392,8 @@ inline long long large_iblocks(long long N) { return (N + kTile - 1) / kTile; } 
 
 template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, const void *others, long long M, long long self_offset,
                                     void *next_view, const void *const *peer_views, int n_peers, void *scratch, long long scratch_bytes,
-                                    cudaStream_t st, const void *cur_boxes = nullptr, bool boxes_ready = false, const void *const *peer_next_boxes = nullptr,
-                                    const BarrierArgs *sync = nullptr, unsigned long long wait_epoch = 0, unsigned long long signal_epoch = 0) {
+                                    cudaStream_t st, const void *cur_boxes = nullptr, bool boxes_ready = false, const void *const *peer_next_boxes = nullptr) {
     LargeArgs<T> la;
-    for (int p = 0; p < 8; ++p) la.flags[p] = sync ? sync->flags[p] : nullptr;
-    la.sync_world = sync ? sync->world : 1; la.sync_rank = sync ? sync->rank : 0; la.sync_words = sync ? sync->error : nullptr;
-    la.wait_epoch = wait_epoch; la.signal_epoch = signal_epoch;
     la.n_peers = n_peers;
     for (int p = 0; p < 8; ++p) la.peers[p] = (p < n_peers) ? (T *)peer_views[p] : nullptr;
     for (int p = 0; p < 8; ++p) la.peer_boxes[p] = (peer_next_boxes && p < n_peers) ? (T *)peer_next_boxes[p] : nullptr;
@@ -527,12 +504,15 @@ int snp_large_run_p2p(const snp_crowd *c, const snp_step_opts *o, const void *co
         for (int p = 0; p < world; ++p) nxt_boxes[p] = boxes_of(nxt[p]);
         int rc;
         // sub-step 0 computes the tile boxes of the view it was handed; from then on the producer has written them
-        // the pairs kernel waits for the epoch the previous sub-step's producers signalled (epoch_base itself for the first sub-step
-        // of a call: the last epoch of the previous call, 0 = nothing to wait for); the last finish block signals epoch_base + s + 1
-        const unsigned long long wait = epoch_base + (unsigned long long)s, signal = wait + 1;
-        if (c->dtype == SNP_F64) rc = run_large<double>(c, o, cur[rank], M, self_offset, nullptr, nxt, world, scratch, scratch_bytes, st, boxes_of(cur[rank]), s > 0, nxt_boxes, &b, wait, signal);
-        else rc = run_large<float>(c, o, cur[rank], M, self_offset, nullptr, nxt, world, scratch, scratch_bytes, st, boxes_of(cur[rank]), s > 0, nxt_boxes, &b, wait, signal);
+        if (c->dtype == SNP_F64) rc = run_large<double>(c, o, cur[rank], M, self_offset, nullptr, nxt, world, scratch, scratch_bytes, st, boxes_of(cur[rank]), s > 0, nxt_boxes);
+        else rc = run_large<float>(c, o, cur[rank], M, self_offset, nullptr, nxt, world, scratch, scratch_bytes, st, boxes_of(cur[rank]), s > 0, nxt_boxes);
         if (rc) return rc;
+        if (world > 1) {
+            b.epoch = epoch_base + (unsigned long long)s + 1;
+            k_rank_barrier<<<1, 32, 0, st>>>(b);
+            count_launch();
+            SNP_CUDA_OK(cudaGetLastError());
+        }
         cur_is_b ^= 1;
     }
     return SNP_OK;

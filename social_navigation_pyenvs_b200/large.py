@@ -71,7 +71,7 @@ class LargeCrowd:
             self._vbuf = [torch.zeros((vlen,), dtype=dtype, device=self.eng.device) for _ in range(2)]
         self.view = [v[:5 * self.n_total].view(5, self.n_total) for v in self._vbuf]
         self._epoch = 0
-        self._err = torch.zeros((2,), dtype=torch.int32, device=self.eng.device)   # {peer time-out flag, retired finish blocks}
+        self._err = torch.zeros((1,), dtype=torch.int32, device=self.eng.device)
         nbytes = int(self.eng.lib.snp_large_scratch_bytes(self.n_local, self.n_total, L.SNP_F64 if dtype == torch.float64 else L.SNP_F32))
         self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.eng.device)
         self.culling = True
@@ -92,7 +92,7 @@ class LargeCrowd:
 
     def check_peers(self):
         """Raises if a rank never reached a sub-step barrier (the barrier kernel timed out instead of hanging the GPU)."""
-        if int(self._err[0].item()):
+        if int(self._err.item()):
             raise RuntimeError("LargeCrowd: a peer rank did not reach the sub-step barrier")
 
     def _publish(self):
@@ -106,8 +106,8 @@ class LargeCrowd:
         o = self.eng._opts(dt, 1)
         o.reserved = 0 if self.culling else 2  # SNP_OPT_NO_CULLING
         if self.exchange in ("p2p", "fused") and not getattr(self, "legacy_loop", False):
-            # the whole sub-step loop in ONE C call: per sub-step two launches with the cross-rank synchronisation folded into them,
-            # nothing returns to Python in between
+            # the whole sub-step loop in ONE C call: per sub-step two launches + a single-warp cross-rank barrier kernel, nothing
+            # returns to Python in between
             L.check(self.eng.lib.snp_large_run_p2p(ctypes.byref(c), ctypes.byref(o), self._peer_ptrs[0], self._peer_ptrs[1], self.cur, self.n_total,
                                                    self.offset, self.world, self.rank, self._peer_flags, self._epoch, int(n_substeps),
                                                    ctypes.c_void_p(self._err.data_ptr()), ctypes.c_void_p(self.scratch.data_ptr()),
