@@ -151,33 +151,64 @@ __device__ __forceinline__ void closest_point(const Seg<T> *segs, int cnt, T px,
     else closest_point_impl<T, false>(segs, cnt, px, py, dxb, dyb, best);             // serial: '<=' keeps the last (obstacle.py:63)
 }
 
+// Wall force of G consecutive polygons on one agent, accumulated into (fx, fy) in polygon order.  The G closest-point searches run
+// first; the G force evaluations that follow (rsqrt -> exponent -> table -> polynomial: ~30 dependent FP64 instructions each) are
+// independent and branch-free, so their chains interleave -- in a kernel that is bound by dependency latency this is worth more than
+// the instructions it saves.  ONE contact vote covers the group.
+template <typename T, int OBS, int G>
+__device__ __forceinline__ void wall_forces(const Params<T> &P, const double *tbl, unsigned vote_mask, const Seg<T> *segs, const int *seg_cnt,
+                                            int S, bool numba, T px, T py, T vx, T vy, T rs, T &fx, T &fy) {
+    using R = Real<T>;
+    T dx[G], dy[G], inv[G], rd[G], cn[G];
+    bool touch = false;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        T d2;
+        closest_point<T>(segs + k * S, seg_cnt[k], px, py, numba, dx[k], dy[k], d2);
+    }
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const T d2 = np_sq(dx[k], dy[k]) + tiny_<T>();
+        inv[k] = R::rsqrt_(d2);
+        rd[k] = fma_<T>(-d2, inv[k], rs);
+        touch |= R::positive_(rd[k]);
+        cn[k] = R::exp2s_times_(fma_<T>(rd[k], P.kBw, P.lAw), inv[k], tbl);
+    }
+    const bool contact = __any_sync(vote_mask, touch);  // compression / friction terms only when some lane touches a wall of the group
+    if (OBS == 0 && !contact) {
+#pragma unroll
+        for (int k = 0; k < G; ++k) { fx = fma_<T>(cn[k], dx[k], fx); fy = fma_<T>(cn[k], dy[k], fy); }
+    } else {
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            const T prd = contact ? max0(rd[k]) * inv[k] : T(0);
+            // delta_v = -(v . t) = (vx dy - vy dx) / d,  t = (-dy, dx) / d
+            const T cr = vx * dy[k] - vy * dx[k];
+            T ct = -(P.k2 * prd) * cr * inv[k];
+            if (OBS == 1) ct = fma_<T>(-R::exp2s_times_(fma_<T>(rd[k], P.kDw, P.lCw), inv[k] * inv[k], tbl), cr, ct);
+            const T en = fma_<T>(P.k1, prd, cn[k]);
+            fx += fma_<T>(en, dx[k], -(ct * dy[k]));
+            fy += fma_<T>(en, dy[k], ct * dx[k]);
+        }
+    }
+}
+
 // Wall force of all W polygons on one agent (forces.py:27-53).  OBS: 0 Helbing (mean over walls), 1 Guo (sum; mean in Numba).
 // Same un-normalised form as pair_eval: f = (cn / d) (dx, dy) + (ct / d) (-dy, dx).
+#ifndef SNP_WALL_GROUP
+#define SNP_WALL_GROUP 3
+#endif
 template <typename T, int OBS>
 __device__ __forceinline__ void obstacle_force(const Params<T> &P, const double *tbl, unsigned vote_mask, const Seg<T> *segs, const int *seg_cnt,
                                                int W, int S, bool numba, T px, T py, T vx, T vy, T rs, T &fx, T &fy) {
     using R = Real<T>;
+    constexpr int G = SNP_WALL_GROUP;
     fx = T(0); fy = T(0);
-    for (int w = 0; w < W; ++w) {
-        T dx, dy, d2;
-        closest_point<T>(segs + w * S, seg_cnt[w], px, py, numba, dx, dy, d2);
-        d2 = np_sq(dx, dy) + tiny_<T>();
-        const T inv = R::rsqrt_(d2);
-        const T rd = fma_<T>(-d2, inv, rs);
-        const bool contact = __any_sync(vote_mask, R::positive_(rd));  // compression / friction terms only when some lane touches the wall
-        const T cn = R::exp2s_times_(fma_<T>(rd, P.kBw, P.lAw), inv, tbl);
-        if (OBS == 0 && !contact) {
-            fx = fma_<T>(cn, dx, fx); fy = fma_<T>(cn, dy, fy);
-        } else {
-            const T prd = contact ? max0(rd) * inv : T(0);
-            // delta_v = -(v . t) = (vx dy - vy dx) / d,  t = (-dy, dx) / d
-            T ct = -(P.k2 * prd) * (vx * dy - vy * dx) * inv;
-            if (OBS == 1) ct = fma_<T>(-R::exp2s_times_(fma_<T>(rd, P.kDw, P.lCw), inv * inv, tbl), vx * dy - vy * dx, ct);
-            const T en = fma_<T>(P.k1, prd, cn);
-            fx += fma_<T>(en, dx, -(ct * dy));
-            fy += fma_<T>(en, dy, ct * dx);
-        }
+    int w = 0;
+    if constexpr (G > 1) {
+        for (; w + G <= W; w += G) wall_forces<T, OBS, G>(P, tbl, vote_mask, segs + w * S, seg_cnt + w, S, numba, px, py, vx, vy, rs, fx, fy);
     }
+    for (; w < W; ++w) wall_forces<T, OBS, 1>(P, tbl, vote_mask, segs + w * S, seg_cnt + w, S, numba, px, py, vx, vy, rs, fx, fy);
     if (W > 0 && (OBS == 0 || numba)) { const T iw = R::rcp_(T(W)); fx *= iw; fy *= iw; }
 }
 
