@@ -43,13 +43,13 @@ for k, v in im.items():
         continue
     out.append(f"| {k} | {v['fp64_warp_instructions'] / 1e6:.1f} M | {v.get('dfma_warp_instructions', 0) / 1e6:.1f} M | {v['other_warp_instructions'] / 1e6:.1f} M | "
                f"{v['issue_cycles_per_smsp'] / 1e3:.1f} K |")
-out += ["\nk_step fp64 runs at 61 % of its bound (fp32 70 %, k_large_pairs 94 %, k_laser 76 %): the remainder is dependency latency -- one full wave of",
+out += ["\nk_step fp64 runs at 63 % of its bound (fp32 69 %, k_large_pairs 95 %, k_laser 76 %): the remainder is dependency latency -- one full wave of",
         "4 / 8 / 12 / 16 warps per SM takes 0.101 / 0.111 / 0.128 / 0.147 ms (`SNP_BENCH_ENVS` = 592 / 1184 / 1776 / 2368, measured mid-round), i.e. 0.09 ms for a lone",
         "warp per scheduler plus 0.0036 ms per additional warp (DESIGN.md 4.1).\n",
         "## k_step fp64, round 1 -> round 2 (ncu, one launch of the default workload)\n",
         "| | round 1 | round 2 |", "|---|---|---|",
-        "| warp instructions | 182.4 M | 149.9 M |", "| FP64 (DFMA + DMUL + DADD + DSETP) | 67.5 M | 57.8 M |", "| other | 115.0 M | 92.1 M |",
-        "| UMOV | 7.7 M | 2.2 M |", "| duration under ncu | 273.9 us | 230.8 us |", "| bench ms per launch | 0.2666 | 0.2212 |",
+        "| warp instructions | 182.4 M | 144.8 M |", "| FP64 (DFMA + DMUL + DADD + DSETP) | 67.5 M | 59.0 M |", "| other | 115.0 M | 85.8 M |",
+        "| UMOV | 7.7 M | 2.2 M |", "| duration under ncu | 273.9 us | 229.0 us |", "| bench ms per launch | 0.2666 | 0.2212 |",
         "| roofline frac (FP64 FMA peak measured in the run) | 0.297 | 0.360 |"]
 open(P + f"{R}_summary.md", "w").write("\n".join(out) + "\n")
 print(f"wrote profiles/{R}_summary.md ({len(out)} lines)")
