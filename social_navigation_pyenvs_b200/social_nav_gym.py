@@ -35,6 +35,7 @@ class BatchedSocialNavGym:
         self.robot_visible = False
         self.randomize_attributes = False
         self.robot_motion_model_title = None
+        self.robot_kinematics = "holonomic"   # or "unicycle" (robot_agent.py:95: the robot policy's kinematics)
         self._robot_goals = None
         self.walls = None
 
@@ -158,7 +159,10 @@ class BatchedSocialNavGym:
         return torch.stack(cols, -1).double().cpu().numpy()
 
     def step(self, action):
-        self.engine.step(action, self.time_step, n_substeps=self.time_step_factor, pre_checks=True)
+        """SocialNavGym.step (social_nav_gym.py:227-250) for every env.  `action` [E,2]: (vx, vy) for a holonomic robot (ActionXY) or
+        (v, r) for a unicycle one (ActionRot; set `robot_kinematics = "unicycle"`, what RobotAgent takes from its policy,
+        robot_agent.py:95)."""
+        self.engine.step(action, self.time_step, n_substeps=self.time_step_factor, pre_checks=True, kinematics=self.robot_kinematics)
         r = self.engine.decode_flags()
         return self.observation(), r["reward"], r["terminated"], r["truncated"], r["info"]
 
