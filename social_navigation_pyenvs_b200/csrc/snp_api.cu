@@ -155,7 +155,7 @@ int snp_gym_step_host(const snp_crowd *crowd, const snp_step_opts *opts, const v
     int32_t *flags_dev = (int32_t *)device_alias(flags_host);
     double *checks_dev = (double *)device_alias(checks_host);
     const bool zero_copy = opts->n_substeps > 0 && !opts->dyn_out && (!obs_host || obs_dev) && (!flags_host || flags_dev) && (!checks_host || checks_dev) &&
-                           (obs_host || flags_host || checks_host) && (crowd->dtype == SNP_F64 || crowd->dtype == SNP_F32) && !(opts->reserved & 16);
+                           (obs_host || flags_host || checks_host) && (crowd->dtype == SNP_F64 || crowd->dtype == SNP_F32) && !(opts->reserved & SNP_OPT_STAGED_COPIES);
     if (zero_copy) {
         const int rc = crowd->dtype == SNP_F64 ? gym_step_zero_copy<double>(crowd, opts, obs_dev, flags_dev, checks_dev, st)
                                                : gym_step_zero_copy<float>(crowd, opts, obs_dev, flags_dev, checks_dev, st);
