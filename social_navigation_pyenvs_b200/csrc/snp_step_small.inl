@@ -375,6 +375,8 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
     Agent<T> me;
     Params<T> P = a.P;
     int gidx = 0, gcnt = 1;
+    bool goals_differ = true;  // false: every entry of the goal list is the same point (the zero-speed "static obstacle" humans of the
+                               // reference's CCSO scenario have goals [p, p]): rotating such a list changes nothing, so the switch is skipped
     if (live) {
         me.px = a.dyn[SNP_DYN_PX * EN + aidx]; me.py = a.dyn[SNP_DYN_PY * EN + aidx];
         me.vx = a.dyn[SNP_DYN_VX * EN + aidx]; me.vy = a.dyn[SNP_DYN_VY * EN + aidx];
@@ -399,8 +401,12 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
         rs_g[i].a = me.rs;
         if constexpr (!CTA) rs_g[i - N].a = me.rs;
         if (gcache) {
-            for (int k = 0; k < a.G; ++k)
-                goal_s[(size_t)k * blockDim.x] = Vec2<T>{a.goals[((size_t)k * 2 + 0) * EN + aidx], a.goals[((size_t)k * 2 + 1) * EN + aidx]};
+            goals_differ = false;
+            for (int k = 0; k < a.G; ++k) {
+                const Vec2<T> gk{a.goals[((size_t)k * 2 + 0) * EN + aidx], a.goals[((size_t)k * 2 + 1) * EN + aidx]};
+                goal_s[(size_t)k * blockDim.x] = gk;
+                if (k < gcnt && (gk.a != me.gx || gk.b != me.gy)) goals_differ = true;
+            }
         }
     } else {
         me = Agent<T>{};
@@ -568,7 +574,7 @@ __global__ void __launch_bounds__(CTA ? 512 : kWarpsPerBlock * 32, CTA ? 1 : (si
             // evaluated at the position the sub-step starts from
             {
                 GoalVec<T> gv = goal_vec<T>(me);
-                if (numba_sem ? (gv.dist <= me.r) : (gv.dist < me.r)) {
+                if (goals_differ && (numba_sem ? (gv.dist <= me.r) : (gv.dist < me.r))) {
                     gidx = (gidx + 1 >= gcnt) ? 0 : gidx + 1;
                     T ngx, ngy;
                     if (gcache) { const Vec2<T> ng = goal_s[(size_t)gidx * blockDim.x]; ngx = ng.a; ngy = ng.b; }
