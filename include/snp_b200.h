@@ -52,7 +52,8 @@ typedef enum snp_status {
 
 enum { SNP_F32 = 0, SNP_F64 = 1 };
 enum { SNP_OPT_FULL_PAIR_LOOP = 1, SNP_OPT_NO_CULLING = 2, SNP_OPT_MAP_WARP = 4, SNP_OPT_MAP_BLOCK = 8,
-       SNP_OPT_STAGED_COPIES = 16 /* snp_gym_step_host: D2H copies after the launch even for pinned result buffers */ };
+       SNP_OPT_STAGED_COPIES = 16, /* snp_gym_step_host: D2H copies after the launch even for pinned result buffers */
+       SNP_OPT_LARGE_GRID = 32     /* snp_large_*: culled steps on the static (i-block, chunk) grid instead of the work list (tests / tuning) */ };
 
 /* Field order of the structure-of-arrays buffers (each field is a contiguous run of E*N elements). */
 enum { SNP_DYN_PX = 0, SNP_DYN_PY, SNP_DYN_VX, SNP_DYN_VY, SNP_DYN_TH, SNP_DYN_BVX, SNP_DYN_BVY, SNP_DYN_OM,

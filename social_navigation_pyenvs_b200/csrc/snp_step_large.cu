@@ -1,21 +1,23 @@
 // snp_step_large.cu -- one very large crowd: shared-memory tiled all-pairs (N-body style) social force, then the same wall /
-// desired / torque / Euler epilogue as the small-crowd kernel.  One sub-step = three launches on one stream:
+// desired / torque / Euler epilogue as the small-crowd kernel.  One sub-step on one stream:
 //
-//   k_tile_boxes   bounding box (+ max r+safety) of every 128-entity tile of the `others` view  [5][M] = x, y, vx, vy, r+s
-//   k_large_pairs  grid (i-blocks of 256 agents, j-chunks of 512 entities): every agent accumulates the force of the
-//                  chunk's entities in ascending j from shared-memory tiles and writes ONE partial sum per chunk.
-//                  A tile is skipped when its box is farther from the i-block's box than the distance at which the pair
-//                  law is identically zero in the arithmetic in use (exp underflow: r_i+s_i+r_j+s_j + 700 B in fp64,
-//                  + 88 B in fp32 with ex2.approx.ftz) -- an EXACT optimisation, the summed force is unchanged.
-//   k_large_finish per agent: partial sums added in ascending chunk order (fixed, so the result does not depend on how the
-//                  crowd is sharded over GPUs), goal switch, wall force, desired force, torque, Euler; writes the state in
-//                  place and the agent's entry of the NEXT entity view (what the other ranks all-gather).
+//   k_tile_boxes    bounding box (+ max r+safety) of every 128-entity tile of the `others` view  [5][M] = x, y, vx, vy, r+s
+//                   (first sub-step of a call only: afterwards the finish kernel writes the boxes of the tiles it produces)
+//   pair phase      unit of work = (i-block of 128 or 256 agents, j-chunk of 128 entities): every agent accumulates the force of
+//                   the chunk's entities in ascending j from a shared-memory tile and writes ONE partial sum per chunk.  A chunk
+//                   is skipped when its box is farther from the i-block's box than the distance at which the pair law is
+//                   identically zero in the arithmetic in use (exp underflow: r_i+s_i+r_j+s_j + 700 B in fp64, + 88 B in fp32
+//                   with ex2.approx.ftz) -- an EXACT optimisation, the summed force is unchanged.
+//                     all pairs:  k_large_pairs on the static (i-block, chunk) grid;
+//                     culled:     k_large_cull lists the units in reach, persistent k_large_pairs_list CTAs work the list off.
+//   k_large_finish  per agent: partial sums of the live chunks added in ascending chunk order (fixed, so the result does not depend
+//                   on how the crowd is sharded over GPUs), goal switch, wall force, desired force, torque, Euler; writes the
+//                   state in place and the agent's entry (and its tile's box) of the NEXT entity view -- on every rank.
 //
-// The chunking gives (N/256) x (M/512) CTAs -- 32768 at 65536 humans on one GPU, 4096 per GPU at 8 GPUs -- instead of N/256.  Small
-// chunks matter once culling is on: the CTAs of far chunks exit at once and only the near ones work, so with 4096-entity chunks a
-// quarter of 4096 CTAs ran long serial loops at low occupancy (measured: 2.6 ms per sub-step and no gain from a second GPU; with
-// 512-entity chunks 2.0 ms on one GPU, 1.1 ms on two).  The price is J = M/512 partial sums per agent (134 MB written and read
-// per sub-step at 65536 humans in fp64, ~45 us of HBM time).
+// Small chunks matter once culling is on and the crowd is sharded: only a few percent of the units have anything to evaluate, and
+// what one rank of an 8-way split keeps must still fill 148 SMs evenly (history: 4096-entity chunks 2.6 ms per sub-step at 65536
+// humans and no gain from a second GPU; 512: 2.0 / 1.1 ms; 256 + exact culling on compact tiles + one agent per thread: 0.75 ms on
+// one GPU, 0.158 on eight; 128 + the work list: 0.65 / 0.14).  The price is J = M/128 partial sums per LIVE chunk and agent.
 // Reference: same as snp_step_small.cu (motion_model_manager.py:354-373,424-459; forces.py:63-151).
 #include "snp_kernels.cuh"
 
@@ -25,12 +27,11 @@ namespace {
 constexpr int kTile = 128;           // entities per shared-memory tile == threads per block
 // Register tiling of the pairs kernel: every staged entity is used for APT agents of the thread.  2 halves the shared-memory
 // loads per pair (best when every ordered pair is evaluated: 7.8 vs 8.4 ms per sub-step at 65536 humans); 1 doubles the number of
-// CTAs, which is what a culled step needs once the crowd is sharded (one rank of an 8-way split keeps only ~300 live CTAs of
-// 256 agents x 512 entities -- a serial loop per CTA that no longer fills 148 SMs: 0.22 ms per rank; 128 agents x 256 entities:
-// 0.15 ms).  The summation order per agent does not depend on it, so results stay bit-identical.
+// work units, which is what a culled fp64 step needs once the crowd is sharded.  The summation order per agent does not depend
+// on it, so results stay bit-identical.
 constexpr int kMaxAgentsPerThread = 2;
 #ifndef SNP_LARGE_CHUNK
-#define SNP_LARGE_CHUNK 256
+#define SNP_LARGE_CHUNK 128
 #endif
 constexpr int kChunk = SNP_LARGE_CHUNK;  // entities per j-chunk (one partial sum each); fixed so results are sharding-independent
 
@@ -46,10 +47,19 @@ template <typename T> struct LargeArgs {
     T *peer_boxes[8];  // snp_large_run_p2p: the NEXT view's tile boxes on every rank; the finish kernel writes its own tiles' boxes there
     unsigned char *live;  // [i-blocks][J]: 1 when the (i-block, chunk) CTA evaluated at least one tile and wrote its partial sums
     int J, n_tiles;
+    int Jp;  // row stride of the `live` map: J rounded up to 16 (the finish kernel reads 16 flags per load)
     T cull_margin;  // distance beyond r+s sums at which the pair law is exactly zero; < 0 disables culling
     int boxes_ready;  // the tile boxes of `others` are already in `boxes` (written by the previous sub-step's producer)
     int apt;          // agents per thread of the pairs kernel (1 or 2): fixes the i-block size the `live` map is indexed by
+    // culled steps: the (i-block, chunk) pairs that are near each other, listed by k_large_cull and handed out to persistent CTAs
+    int *work;            // [i-blocks * J] entries i-block * J + chunk
+    int *work_counters;   // [0] entries listed, [4 + q] entries handed out from queue q; zeroed by the finish kernel for the next sub-step
+    int use_list;
+    int *live_cnt, *live_list;  // per i-block: how many chunks are in reach, and which, ascending ([i-blocks], [i-blocks][Jp]) -- what the
+                                // finish kernel walks instead of scanning the flags
 };
+constexpr int kMaxQueues = 256;                 // one queue of list entries per SM (entry k belongs to queue k mod n_queues)
+constexpr int kWorkCounters = 4 + kMaxQueues;   // ints in front of the list
 
 template <typename T> __device__ __forceinline__ T warp_min(T v) {
     for (int o = 16; o > 0; o >>= 1) { const T w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
@@ -85,47 +95,53 @@ template <typename T> __global__ void __launch_bounds__(kTile) k_tile_boxes(cons
     if (threadIdx.x < 5) boxes[(size_t)blockIdx.x * 5 + threadIdx.x] = out[threadIdx.x];
 }
 
-template <typename T, int SOC, int kAgentsPerThread>
-__global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
-    __shared__ __align__(16) unsigned char tile_raw[sizeof(Ent<T>) * kTile];
-    __shared__ T tile_rs[kTile];
-    __shared__ __align__(16) double exp_tbl_s[kExpN];
-    __shared__ T sbox[20];
-    Ent<T> *tile = reinterpret_cast<Ent<T> *>(tile_raw);
-    const KArgs<T> &a = la.k;
-    bool have_tbl = false;  // the 16 kB exp table is staged only by CTAs that evaluate at least one tile (most are culled)
+// The box of an i-block from the tile boxes alone: its agents are the entities of kAgentsPerThread consecutive tiles, whose union
+// box contains them.
+template <typename T> __device__ __forceinline__ void iblock_box(const LargeArgs<T> &la, int iblock, int apt, T *u /*[5]*/) {
+    const long long t0 = (la.self_offset + (long long)iblock * apt * kTile) / kTile;
+    const T inf = Real<T>::inf();
+    u[0] = inf; u[1] = -inf; u[2] = inf; u[3] = -inf; u[4] = T(0);
+    for (int q = 0; q < apt; ++q)
+        if (t0 + q < la.n_tiles) {
+            const T *b = la.boxes + (size_t)(t0 + q) * 5;
+            u[0] = min(u[0], b[0]); u[1] = max(u[1], b[1]); u[2] = min(u[2], b[2]); u[3] = max(u[3], b[3]); u[4] = max(u[4], b[4]);
+        }
+}
+// Is any tile of chunk `chunk` within reach of the box u?  (Beyond reach the pair law is identically zero.)
+template <typename T> __device__ __forceinline__ bool chunk_near(const LargeArgs<T> &la, const T *u, int chunk) {
+    const long long j_begin = (long long)chunk * kChunk, j_end = min(la.M, j_begin + kChunk);
+    bool near = false;
+    for (long long j0 = j_begin; j0 < j_end; j0 += kTile) {
+        const T *b = la.boxes + (size_t)(j0 / kTile) * 5;
+        const T gx = max(T(0), max(u[0] - b[1], b[0] - u[1]));
+        const T gy = max(T(0), max(u[2] - b[3], b[2] - u[3]));
+        const T reach = u[4] + b[4] + la.cull_margin;
+        near |= !(fma_<T>(gx, gx, gy * gy) > reach * reach);
+    }
+    return near;
+}
 
+template <typename T> struct PairsSmem {
+    alignas(16) unsigned char tile_raw[sizeof(Ent<T>) * kTile];
+    T tile_rs[kTile];
+    alignas(16) double exp_tbl_s[kExpN];
+    T sbox[20];
+    int item, steal;
+};
+
+// One (i-block, chunk) unit of the pair phase: the i-block's agents against the chunk's entities, one partial sum per agent.
+template <typename T, int SOC, int kAgentsPerThread>
+__device__ __forceinline__ void pairs_chunk(const LargeArgs<T> &la, PairsSmem<T> &sm, int iblock, int chunk, bool &have_tbl) {
+    Ent<T> *tile = reinterpret_cast<Ent<T> *>(sm.tile_raw);
+    T *tile_rs = sm.tile_rs;
+    double *exp_tbl_s = sm.exp_tbl_s;
+    T *sbox = sm.sbox;
+    const KArgs<T> &a = la.k;
     const long long N = a.EN, M = la.M;
     const Params<T> &P = a.P;
-    const long long j_begin = (long long)blockIdx.y * kChunk;
+    const long long j_begin = (long long)chunk * kChunk;
     const long long j_end = min(M, j_begin + kChunk);
-    unsigned char *live_flag = la.live + (size_t)blockIdx.x * la.J + blockIdx.y;
-    if (la.cull_margin >= T(0) && la.self_offset % kTile == 0) {
-        // Most CTAs of a wide crowd are far from their chunk: decide that from the tile boxes alone -- the i-block's agents are
-        // the entities of kAgentsPerThread consecutive tiles, whose union box contains them -- before any state is loaded or
-        // any barrier is reached.  A culled CTA leaves its partial sums unwritten and says so in `live`.
-        const long long t0 = (la.self_offset + (long long)blockIdx.x * kAgentsPerThread * kTile) / kTile;
-        const T inf = Real<T>::inf();
-        T u0 = inf, u1 = -inf, u2 = inf, u3 = -inf, u4 = T(0);
-#pragma unroll
-        for (int q = 0; q < kAgentsPerThread; ++q)
-            if (t0 + q < la.n_tiles) {
-                const T *b = la.boxes + (size_t)(t0 + q) * 5;
-                u0 = min(u0, b[0]); u1 = max(u1, b[1]); u2 = min(u2, b[2]); u3 = max(u3, b[3]); u4 = max(u4, b[4]);
-            }
-        bool near = false;
-        for (long long j0 = j_begin; j0 < j_end; j0 += kTile) {
-            const T *b = la.boxes + (size_t)(j0 / kTile) * 5;
-            const T gx = max(T(0), max(u0 - b[1], b[0] - u1));
-            const T gy = max(T(0), max(u2 - b[3], b[2] - u3));
-            const T reach = u4 + b[4] + la.cull_margin;
-            near |= !(fma_<T>(gx, gx, gy * gy) > reach * reach);
-        }
-        if (!near) {  // uniform across the CTA
-            if (threadIdx.x == 0) *live_flag = 0;
-            return;
-        }
-    }
+    unsigned char *live_flag = la.live + (size_t)iblock * la.Jp + chunk;
     T mx[kAgentsPerThread], my[kAgentsPerThread], mvx[kAgentsPerThread], mvy[kAgentsPerThread], mrs[kAgentsPerThread];
     long long idx[kAgentsPerThread];
     T fsx[kAgentsPerThread], fsy[kAgentsPerThread];
@@ -133,7 +149,7 @@ __global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
     T bx0 = big, bx1 = -big, by0 = big, by1 = -big, brs = T(0);
 #pragma unroll
     for (int q = 0; q < kAgentsPerThread; ++q) {
-        idx[q] = ((long long)blockIdx.x * kAgentsPerThread + q) * kTile + threadIdx.x;
+        idx[q] = ((long long)iblock * kAgentsPerThread + q) * kTile + threadIdx.x;
         const bool live = idx[q] < N;
         const long long o = la.self_offset + (live ? idx[q] : 0);
         mx[q] = la.others[o]; my[q] = la.others[M + o]; mvx[q] = la.others[2 * M + o]; mvy[q] = la.others[3 * M + o]; mrs[q] = la.others[4 * M + o];
@@ -222,9 +238,102 @@ __global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
 #pragma unroll
     for (int q = 0; q < kAgentsPerThread; ++q)
         if (idx[q] < N) {
-            la.partial[((size_t)blockIdx.y * 2 + 0) * N + idx[q]] = fsx[q];
-            la.partial[((size_t)blockIdx.y * 2 + 1) * N + idx[q]] = fsy[q];
+            la.partial[((size_t)chunk * 2 + 0) * N + idx[q]] = fsx[q];
+            la.partial[((size_t)chunk * 2 + 1) * N + idx[q]] = fsy[q];
         }
+}
+
+// Regular grid (i-block, chunk): every ordered pair, or -- with culling -- CTAs that first decide from the tile boxes whether their
+// chunk is in reach at all, before any state is loaded or any barrier is reached.  A culled CTA leaves its partial sums unwritten
+// and says so in `live`.
+template <typename T, int SOC, int kAgentsPerThread>
+__global__ void __launch_bounds__(kTile) k_large_pairs(const LargeArgs<T> la) {
+    __shared__ PairsSmem<T> sm;
+    if (la.cull_margin >= T(0) && la.self_offset % kTile == 0) {
+        T u[5];
+        iblock_box<T>(la, blockIdx.x, kAgentsPerThread, u);
+        if (!chunk_near<T>(la, u, blockIdx.y)) {  // uniform across the CTA
+            if (threadIdx.x == 0) la.live[(size_t)blockIdx.x * la.Jp + blockIdx.y] = 0;
+            return;
+        }
+    }
+    bool have_tbl = false;  // the 16 kB exp table is staged only by CTAs that evaluate at least one tile (most are culled)
+    pairs_chunk<T, SOC, kAgentsPerThread>(la, sm, blockIdx.x, blockIdx.y, have_tbl);
+}
+
+// Culled steps of a wide crowd: of the i-blocks x J grid only a few percent of the CTAs have anything to evaluate (65536 humans on
+// 512 m: 12 800 of 131 072), and what is left is too uneven for a static grid -- a rank of an 8-way split ends with 1 600 CTAs
+// for 888 resident slots.  So the reach test runs first, one thread per (i-block, chunk), and lists the pairs that are near;
+// persistent CTAs (one per resident slot, exp table staged once) then work the list off.  WHICH CTA takes which entry matters: with
+// one shared counter the ~400 entries left when every CTA has had its first land on the SMs at random -- some get 7, some none --
+// and the slowest SM sets the time (measured: 45 % over the ideal).  So entry k belongs to queue k mod n_SMs, a CTA serves the
+// queue of the SM it runs on (%smid) and only when that is empty looks for another queue with entries left: every SM gets the
+// same number of entries whatever the placement of the CTAs, and every entry is taken whichever CTAs exist.  Partial sums land
+// where the grid version puts them: results are bit-identical.
+template <typename T> __global__ void __launch_bounds__(256) k_large_cull(const LargeArgs<T> la) {
+    __shared__ int warp_cnt[8];
+    T u[5];
+    iblock_box<T>(la, blockIdx.x, la.apt, u);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int *mine = la.live_list + (size_t)blockIdx.x * la.Jp;
+    int listed = 0;  // chunks of this i-block listed so far (uniform)
+    for (int c0 = 0; c0 < la.J; c0 += blockDim.x) {
+        const int c = c0 + threadIdx.x;
+        const bool near = c < la.J && chunk_near<T>(la, u, c);
+        if (c < la.J) la.live[(size_t)blockIdx.x * la.Jp + c] = near ? 1 : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, near);
+        const int below = __popc(m & ((1u << lane) - 1u));
+        if (m) {  // the global list of work units (any order)
+            int base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(la.work_counters, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (near) la.work[base + below] = blockIdx.x * la.J + c;
+        }
+        // this i-block's own list, ascending: the order the finish kernel adds the partial sums in
+        if (lane == 0) warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const int v = warp_cnt[w]; before += w < warp ? v : 0; total += v; }
+        if (near) mine[listed + before + below] = c;
+        listed += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) la.live_cnt[blockIdx.x] = listed;
+}
+
+template <typename T, int SOC, int kAgentsPerThread>
+__global__ void __launch_bounds__(kTile) k_large_pairs_list(const LargeArgs<T> la, const int n_queues) {
+    __shared__ PairsSmem<T> sm;
+    bool have_tbl = false;
+    const int n_items = la.work_counters[0];
+    int *cursor = la.work_counters + 4;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    int q = (int)(smid % (unsigned)n_queues);
+    for (;;) {
+        __syncthreads();  // the previous unit is done with the tile, the boxes and sm.item
+        if (threadIdx.x == 0) {
+            const long long k = (long long)q + (long long)atomicAdd(cursor + q, 1) * n_queues;
+            sm.item = k < n_items ? (int)k : -1;
+            sm.steal = 0x7fffffff;
+        }
+        __syncthreads();
+        const int item = sm.item;
+        if (item >= 0) {
+            const int w = la.work[item];
+            pairs_chunk<T, SOC, kAgentsPerThread>(la, sm, w / la.J, w % la.J, have_tbl);
+            continue;
+        }
+        // this queue is empty (and stays so: the counters only grow): move to the nearest queue that still has entries, if any
+        for (int t = threadIdx.x; t < n_queues; t += kTile) {
+            const int c = *reinterpret_cast<volatile int *>(cursor + t);
+            if ((long long)t + (long long)c * n_queues < n_items) atomicMin(&sm.steal, (t - q + n_queues) % n_queues);
+        }
+        __syncthreads();
+        if (sm.steal == 0x7fffffff) return;
+        q = (q + sm.steal) % n_queues;
+    }
 }
 
 template <typename T, int OBS, int HEADED>
@@ -237,7 +346,7 @@ __global__ void __launch_bounds__(kTile) k_large_finish(const LargeArgs<T> la) {
     constexpr size_t kTbl = sizeof(double) * kExpN;
     Seg<T> *segs = reinterpret_cast<Seg<T> *>(smem_raw + kTbl);
     int *seg_cnt = reinterpret_cast<int *>(smem_raw + kTbl + ((sizeof(Seg<T>) * (size_t)nseg + 15) & ~size_t(15)));
-    if (sizeof(T) == 8) exp_table_init(exp_tbl_s);
+    if (sizeof(T) == 8 && nseg > 0) exp_table_init(exp_tbl_s);  // only the wall force evaluates exp here
     for (int k = threadIdx.x; k < nseg; k += blockDim.x) {
         const T *w = a.walls + (size_t)k * 4;
         segs[k] = make_seg<T>(w[0], w[1], w[2], w[3]);
@@ -251,6 +360,8 @@ __global__ void __launch_bounds__(kTile) k_large_finish(const LargeArgs<T> la) {
     __syncthreads();
     const long long N = a.EN, M = la.M;
     const long long i = (long long)blockIdx.x * kTile + threadIdx.x;
+    if (la.use_list && blockIdx.x == 0)  // the pair phase is over: empty list and queues for the next sub-step
+        for (int k = threadIdx.x; k < kWorkCounters; k += kTile) la.work_counters[k] = 0;
     const bool fold_boxes = la.peer_boxes[0] != nullptr;  // uniform; only offered when N is a whole number of tiles, so that every
     if (i >= N) return;                                    // thread of every block reaches the box reduction at the end
     const unsigned vote_mask = __activemask();  // the lanes that own an agent (the tail warp is partial)
@@ -273,9 +384,60 @@ __global__ void __launch_bounds__(kTile) k_large_finish(const LargeArgs<T> la) {
     const int gcnt = a.goal_cnt[i];
     m.gx = a.goals[((size_t)gidx * 2 + 0) * N + i]; m.gy = a.goals[((size_t)gidx * 2 + 1) * N + i];
     T fsx = T(0), fsy = T(0);
-    const unsigned char *lv = la.live + (size_t)(i / (kTile * la.apt)) * la.J;  // the same flags for the whole CTA
-    for (int p = 0; p < la.J; ++p)
-        if (lv[p]) { fsx += la.partial[((size_t)p * 2 + 0) * N + i]; fsy += la.partial[((size_t)p * 2 + 1) * N + i]; }
+    // Sum of the live chunks' partial sums in ascending chunk order (the order is what makes the result independent of the
+    // sharding).  The flags are the same for the whole CTA and live chunks come in runs; they are read 64 at a time, and for every
+    // 16 flags with a live one the loads of all live partial sums are issued together before the (ordered) additions -- a
+    // flag-by-flag loop serialised one L2 round trip per live chunk.
+    const uint4 *lv = reinterpret_cast<const uint4 *>(la.live + (size_t)(i / (kTile * la.apt)) * la.Jp);
+    const int n_words = la.use_list ? 0 : la.Jp >> 4;
+    if (la.use_list) {
+        // the cull kernel left the i-block's live chunks as an ascending list: sixteen indices per step, the next sixteen already on
+        // their way while the partial sums of the current ones are loaded
+        const int4 *ll = reinterpret_cast<const int4 *>(la.live_list + (size_t)(i / (kTile * la.apt)) * la.Jp);
+        const int cnt = la.live_cnt[i / (kTile * la.apt)];
+        int4 nxt[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nxt[u] = ll[u];  // (a row is Jp >= 16 entries long; entries beyond cnt are ignored)
+        for (int k = 0; k < cnt; k += 16) {
+            int4 cur[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+            if (k + 16 < cnt) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) nxt[u] = ll[(k >> 2) + 4 + u];
+            }
+            const int idx[16] = {cur[0].x, cur[0].y, cur[0].z, cur[0].w, cur[1].x, cur[1].y, cur[1].z, cur[1].w,
+                                 cur[2].x, cur[2].y, cur[2].z, cur[2].w, cur[3].x, cur[3].y, cur[3].z, cur[3].w};
+            T vx[16], vy[16];
+#pragma unroll
+            for (int b = 0; b < 16; ++b)
+                if (k + b < cnt) { vx[b] = la.partial[((size_t)idx[b] * 2 + 0) * N + i]; vy[b] = la.partial[((size_t)idx[b] * 2 + 1) * N + i]; }
+#pragma unroll
+            for (int b = 0; b < 16; ++b)
+                if (k + b < cnt) { fsx += vx[b]; fsy += vy[b]; }
+        }
+    }
+    for (int w0 = 0; w0 < n_words; w0 += 4) {
+        uint4 f[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) f[u] = (w0 + u < n_words) ? lv[w0 + u] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!(f[u].x | f[u].y | f[u].z | f[u].w)) continue;
+            const unsigned word[4] = {f[u].x, f[u].y, f[u].z, f[u].w};  // sixteen flags, one per byte
+            const int p0 = (w0 + u) << 4;
+            T vx[16], vy[16];
+            bool on[16];
+#pragma unroll
+            for (int b = 0; b < 16; ++b) {
+                on[b] = ((word[b >> 2] >> (8 * (b & 3))) & 0xffu) != 0 && p0 + b < la.J;  // (bytes beyond J are padding nobody wrote)
+                if (on[b]) { vx[b] = la.partial[((size_t)(p0 + b) * 2 + 0) * N + i]; vy[b] = la.partial[((size_t)(p0 + b) * 2 + 1) * N + i]; }
+            }
+#pragma unroll
+            for (int b = 0; b < 16; ++b)
+                if (on[b]) { fsx += vx[b]; fsy += vy[b]; }
+        }
+    }
 
     const T dg = np_norm(m.gx - m.px, m.gy - m.py);
     if (a.numba ? (dg <= m.r) : (dg < m.r)) {
@@ -375,7 +537,20 @@ template <typename T, int SOC, int OBS, int HEADED> int launch_large(const Large
     if (!la.boxes_ready) k_tile_boxes<T><<<(unsigned)la.n_tiles, kTile, 0, st>>>(la.others, la.M, la.boxes);
     const long long per_block = (long long)kTile * la.apt;
     dim3 grid((unsigned)((N + per_block - 1) / per_block), (unsigned)la.J);
-    if (la.apt == 1) k_large_pairs<T, SOC, 1><<<grid, kTile, 0, st>>>(la);
+    if (la.use_list) {
+        if (!la.boxes_ready) SNP_CUDA_OK(cudaMemsetAsync(la.work_counters, 0, kWorkCounters * sizeof(int), st));  // first sub-step of a call; later ones: the finish kernel
+        k_large_cull<T><<<grid.x, 256, 0, st>>>(la);
+        static int slots1 = 0, slots2 = 0;  // resident CTAs per SM of the two instantiations
+        const int n_queues = device_sm_count() < kMaxQueues ? device_sm_count() : kMaxQueues;
+        if (la.apt == 1) {
+            if (!slots1) SNP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slots1, k_large_pairs_list<T, SOC, 1>, kTile, 0));
+            k_large_pairs_list<T, SOC, 1><<<(unsigned)(device_sm_count() * (slots1 > 0 ? slots1 : 1)), kTile, 0, st>>>(la, n_queues);
+        } else {
+            if (!slots2) SNP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&slots2, k_large_pairs_list<T, SOC, 2>, kTile, 0));
+            k_large_pairs_list<T, SOC, 2><<<(unsigned)(device_sm_count() * (slots2 > 0 ? slots2 : 1)), kTile, 0, st>>>(la, n_queues);
+        }
+        count_launch();
+    } else if (la.apt == 1) k_large_pairs<T, SOC, 1><<<grid, kTile, 0, st>>>(la);
     else k_large_pairs<T, SOC, 2><<<grid, kTile, 0, st>>>(la);
     const size_t smem = sizeof(double) * kExpN + ((sizeof(Seg<T>) * (size_t)nseg + 15) & ~size_t(15)) + sizeof(int) * (la.k.W + 1) + 16;
     auto fin = k_large_finish<T, OBS, HEADED>;
@@ -408,11 +583,21 @@ template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, 
     a.time_now = nullptr; a.flags = nullptr; a.checks = nullptr; a.epw = 1; a.gpb = 1; a.mapping = 0; a.full_pair_loop = 1; a.respawn = 0; a.robot_type = 0; a.RP = a.P; a.robot_every = 0; a.robot_phase = 0; a.robot_dt = T(0);
     la.others = (const T *)others; la.M = M; la.self_offset = self_offset; la.next_view = (T *)next_view;
     la.J = (int)large_J(M); la.n_tiles = (int)large_tiles(M);
-    const long long need = (long long)sizeof(T) * ((long long)la.J * 2 * a.EN + (long long)la.n_tiles * 5) + large_iblocks(a.EN) * la.J;
+    la.Jp = (la.J + 15) & ~15;
+    const long long live_bytes = large_iblocks(a.EN) * la.Jp, list_entries = large_iblocks(a.EN) * la.J;
+    const long long need = (long long)sizeof(T) * ((long long)la.J * 2 * a.EN + (long long)la.n_tiles * 5) + live_bytes + 64 +
+                           4 * (kWorkCounters + list_entries + ((large_iblocks(a.EN) + 3) & ~3LL) + large_iblocks(a.EN) * la.Jp);
     if (!scratch || scratch_bytes < need) { set_error("snp_large_step: scratch of %lld bytes needed, %lld given", need, scratch_bytes); return SNP_ERR_INVALID; }
     la.partial = (T *)scratch;
     la.boxes = la.partial + (size_t)la.J * 2 * a.EN;
-    la.live = reinterpret_cast<unsigned char *>(la.boxes + (size_t)la.n_tiles * 5);
+    la.live = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(la.boxes + (size_t)la.n_tiles * 5) + 15) & ~uintptr_t(15));
+    {   // counters and work list behind the live map, 16-byte aligned
+        uintptr_t p = reinterpret_cast<uintptr_t>(la.live) + (size_t)live_bytes;
+        la.work_counters = reinterpret_cast<int *>(p);
+        la.work = la.work_counters + kWorkCounters;
+        la.live_cnt = la.work + ((list_entries + 3) & ~3LL);
+        la.live_list = la.live_cnt + ((large_iblocks(a.EN) + 3) & ~3LL);
+    }
     if (cur_boxes) la.boxes = (T *)cur_boxes;  // the view's own box table (snp_large_run_p2p)
     // exact culling distance beyond the r+s sums: where exp(rd/B) is identically zero in the arithmetic in use
     const int soc = o->type % 3;
@@ -424,6 +609,7 @@ template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, 
     }
     la.cull_margin = (T)margin;
     la.apt = (margin >= 0.0 && sizeof(T) == 8) ? 1 : kMaxAgentsPerThread;  // fp32 pair evaluations are short: the finer split only adds launch overhead there
+    la.use_list = (margin >= 0.0 && self_offset % kTile == 0 && list_entries < (1LL << 31) && !(o->reserved & SNP_OPT_LARGE_GRID)) ? 1 : 0;
     switch (o->type) {
         case 0: return launch_large<T, 0, 0, 0>(la, st);
         case 1: return launch_large<T, 1, 1, 0>(la, st);
@@ -448,7 +634,8 @@ extern "C" {
 
 int64_t snp_large_scratch_bytes(int64_t n_local, int64_t M, int32_t dtype) {
     const long long w = dtype == SNP_F64 ? 8 : 4;
-    return w * (large_J(M) * 2 * n_local + large_tiles(M) * 5) + large_iblocks(n_local) * large_J(M) + 64;
+    return w * (large_J(M) * 2 * n_local + large_tiles(M) * 5) + 9 * large_iblocks(n_local) * ((large_J(M) + 15) & ~15LL) + 4 * large_iblocks(n_local) +
+           256 + 4 * kWorkCounters;
 }
 
 int snp_large_step(const snp_crowd *c, const snp_step_opts *o, const void *others, int64_t M, int64_t self_offset, void *next_view,

@@ -75,6 +75,7 @@ class LargeCrowd:
         nbytes = int(self.eng.lib.snp_large_scratch_bytes(self.n_local, self.n_total, L.SNP_F64 if dtype == torch.float64 else L.SNP_F32))
         self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.eng.device)
         self.culling = True
+        self.work_list = True
         self.cur = 0
         if shard is not None:  # the frozen rest of the crowd: both view buffers start from the whole crowd's entries
             whole = CrowdEngine.from_reference_arrays(model, states[None], goals[None], consider_robot=False, all_params_equal=symmetric, dtype=dtype, device=device)
@@ -105,6 +106,8 @@ class LargeCrowd:
         c = self.eng._crowd()
         o = self.eng._opts(dt, 1)
         o.reserved = 0 if self.culling else 2  # SNP_OPT_NO_CULLING
+        if not self.work_list:
+            o.reserved |= 32  # SNP_OPT_LARGE_GRID: culled steps on the static grid instead of the list of near (i-block, chunk) pairs
         if self.exchange in ("p2p", "fused") and not getattr(self, "legacy_loop", False):
             # the whole sub-step loop in ONE C call: per sub-step two launches + a single-warp cross-rank barrier kernel, nothing
             # returns to Python in between

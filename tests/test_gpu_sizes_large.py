@@ -181,12 +181,17 @@ def test_large_crowd_chunked_sums_and_exact_culling(dtype, order):
     if dtype == torch.float32:
         S = S.astype(np.float32).astype(np.float64)
     out = {}
-    for cull in (True, False):
+    # culled on the list of near (i-block, chunk) pairs worked off by persistent CTAs (the default), culled on the static grid, all pairs
+    for cull, work_list in ((True, True), (True, False), (False, True)):
         crowd = LargeCrowd("hsfm_farina", S[0], G[0], dtype=dtype, symmetric=True)
-        crowd.culling = cull
+        crowd.culling, crowd.work_list = cull, work_list
         crowd.step(0.0125, n_substeps=2)
-        out[cull] = crowd.local_rows(S[0])
-    assert np.array_equal(out[True], out[False])
+        first = crowd.local_rows(S[0])
+        crowd.step(0.0125, n_substeps=1)  # (a second call: the list's counters were left empty by the first)
+        out[cull, work_list] = (first, crowd.local_rows(S[0]))
+    for k in (0, 1):
+        assert np.array_equal(out[True, True][k], out[False, True][k]) and np.array_equal(out[True, False][k], out[False, True][k])
+    out = {True: out[True, True][0]}
     cfg = OracleConfig(oracle.type_code("hsfm_farina"), False, True, False)
     params = np.tile(oracle.default_params("hsfm_farina"), (1, n, 1))
     ref, _, _ = oracle.update_humans(cfg, S, G, None, params, np.zeros((1, n)), np.zeros((1, n, 2)), 0.0125, 2)

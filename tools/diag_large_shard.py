@@ -10,11 +10,15 @@ from social_navigation_pyenvs_b200.large import LargeCrowd
 ways, rank = int(sys.argv[1]), int(sys.argv[2])
 sc = scenarios.jittered_grid_crowd(256, pitch=2.0, jitter=0.5, seed=0)
 perm = scenarios.spatial_order(sc["states"][0, :, 0:2])
+if os.environ.get("SNP_LARGE_DEAL", "1") == "1":  # the bench's load balancing: 128-human tiles dealt round-robin to the ranks
+    tiles = perm.reshape(-1, 128)
+    perm = np.concatenate([tiles[r::ways] for r in range(ways)]).reshape(-1)
 S, G = np.ascontiguousarray(sc["states"][0, perm]), np.ascontiguousarray(sc["goals"][0, perm])
 n = S.shape[0] // ways
 crowd = LargeCrowd("hsfm_farina", S, G, dtype=torch.float64, shard=(rank * n, n))
 # one sub-step per call: every call recomputes the tile boxes of the view it reads (in a real sharded run the other ranks' producers
 # write the boxes of their tiles; here the rest of the crowd is frozen and nobody would)
+crowd.work_list = os.environ.get("SNP_LARGE_GRID", "0") != "1"
 for _ in range(2):
     crowd.step(0.0125, 1)
 torch.cuda.synchronize()
@@ -23,4 +27,4 @@ a.record()
 for _ in range(10):
     crowd.step(0.0125, 1)
 b.record(); torch.cuda.synchronize()
-print(f"{ways}-way shard, rank {rank}: {a.elapsed_time(b) / 10:.4f} ms per sub-step ({crowd.exchange})")
+print(f"{ways}-way shard, rank {rank}: {a.elapsed_time(b) / 10:.4f} ms per sub-step ({crowd.exchange}, {'work list' if crowd.work_list else 'static grid'})")
