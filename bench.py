@@ -440,6 +440,7 @@ def large_crowd_probe(tdtype, rank, world, substeps_per_call=10, calls=3):
                                 "sub-step loop in one C call (snp_large_run_p2p)",
                          "fused": "single GPU: sub-step loop in one C call (snp_large_run_p2p), no exchange",
                          "nccl": "NCCL all-gather of the [5, N] view per sub-step"}[crowd.exchange],
+            "pair_phase": "k_large_cull lists the (i-block, 128-entity chunk) units in reach; persistent CTAs with one queue per SM work the list off",
             "substeps_per_call": substeps_per_call, "bit_equal_to_single_gpu": equal, "timing": "CUDA events around each call, max over ranks",
             "agent_order": "patch by patch (scenarios.spatial_order)" + (", 128-human tiles dealt round-robin to the ranks" if world > 1 and os.environ.get("SNP_LARGE_DEAL", "1") == "1" else "")}
 
