@@ -242,8 +242,10 @@ int snp_rotate_goal_rows(const snp_crowd *crowd, double *goal_rows_dev, void *cu
  * when it is sharded by agent) plus, optionally, the robot as last entry; `self_offset` = index of this crowd's agent 0
  * in that view.  Own state is updated in place; when `next_view` is non-NULL the updated x,y,vx,vy,r+safety of the own
  * agents are also written into it (same [5][M] layout, same offset), ready to be all-gathered for the next sub-step.
- * `scratch` = device workspace of at least snp_large_scratch_bytes(n_local, M, dtype) bytes (per-chunk partial sums and tile
- * boxes).  opts->reserved bit 1 (SNP_OPT_NO_CULLING) disables the exact far-tile culling. */
+ * `scratch` = device workspace of at least snp_large_scratch_bytes(n_local, M, dtype) bytes (per-chunk partial sums, tile
+ * boxes, the map and lists of the (agent block, entity chunk) units in reach, the work queues' counters).  opts->reserved bit 1
+ * (SNP_OPT_NO_CULLING) disables the exact far-tile culling; SNP_OPT_LARGE_GRID runs a culled step on the static grid of units
+ * instead of the list worked off by persistent CTAs (same results bit for bit, slower; tests / tuning). */
 int64_t snp_large_scratch_bytes(int64_t n_local, int64_t M, int32_t dtype);
 int snp_large_step(const snp_crowd *crowd, const snp_step_opts *opts, const void *others, int64_t M, int64_t self_offset,
                    void *next_view, void *scratch, int64_t scratch_bytes, void *cuda_stream);
