@@ -17,7 +17,7 @@
 // Small chunks matter once culling is on and the crowd is sharded: only a few percent of the units have anything to evaluate, and
 // what one rank of an 8-way split keeps must still fill 148 SMs evenly (history: 4096-entity chunks 2.6 ms per sub-step at 65536
 // humans and no gain from a second GPU; 512: 2.0 / 1.1 ms; 256 + exact culling on compact tiles + one agent per thread: 0.75 ms on
-// one GPU, 0.158 on eight; 128 + the work list: 0.65 / 0.14).  The price is J = M/128 partial sums per LIVE chunk and agent.
+// one GPU, 0.158 on eight; 128 + the work list + grouped evaluation: 0.61 / 0.125).  The price is J = M/128 partial sums per LIVE chunk and agent.
 // Reference: same as snp_step_small.cu (motion_model_manager.py:354-373,424-459; forces.py:63-151).
 #include "snp_kernels.cuh"
 
@@ -32,6 +32,12 @@ constexpr int kTile = 128;           // entities per shared-memory tile == threa
 constexpr int kMaxAgentsPerThread = 2;
 #ifndef SNP_LARGE_CHUNK
 #define SNP_LARGE_CHUNK 128
+#endif
+// fp64 culled steps (one agent per thread): entities evaluated together between two contact votes.  Measured on one rank's slice of
+// an 8-way split / on the whole 65536 crowd: 1 -> 0.1229 / 0.657 ms per sub-step, 2 -> 0.1167 / 0.621, 4 -> 0.1136 / 0.616 (64 -> 80
+// registers, six resident CTAs per SM instead of nine, but four independent chains per warp when few warps are left on an SM).
+#ifndef SNP_LARGE_GROUP
+#define SNP_LARGE_GROUP 4
 #endif
 constexpr int kChunk = SNP_LARGE_CHUNK;  // entities per j-chunk (one partial sum each); fixed so results are sharding-independent
 
@@ -179,8 +185,33 @@ __device__ __forceinline__ void pairs_chunk(const LargeArgs<T> &la, PairsSmem<T>
         }
         __syncthreads();
         const int cnt = (int)min((long long)kTile, j_end - j0);
+        int t_first = 0;
+#if SNP_LARGE_GROUP > 1
+        if constexpr (sizeof(T) == 8 && kAgentsPerThread == 1 && SOC != 2) {
+            // fp64, one agent per thread: SNP_LARGE_GROUP consecutive entities are evaluated branch-free and share ONE contact vote
+            // (independent chains in flight when few warps are left on the SM); added in entity order, so the sum is unchanged
+            for (; t_first + SNP_LARGE_GROUP <= cnt; t_first += SNP_LARGE_GROUP) {
+                T fx[SNP_LARGE_GROUP], fy[SNP_LARGE_GROUP];
+                bool contact = false;
+#pragma unroll
+                for (int u = 0; u < SNP_LARGE_GROUP; ++u) {
+                    const Ent<T> o = tile[t_first + u];
+                    contact |= Real<T>::positive_(pair_eval<T, SOC, false>(P, exp_tbl_s, mx[0], my[0], mvx[0], mvy[0], mrs[0], o.x, o.y, o.vx, o.vy, tile_rs[t_first + u], fx[u], fy[u]));
+                }
+                if (__any_sync(0xffffffffu, contact)) {
+#pragma unroll
+                    for (int u = 0; u < SNP_LARGE_GROUP; ++u) {
+                        const Ent<T> o = tile[t_first + u];
+                        pair_eval<T, SOC, true>(P, exp_tbl_s, mx[0], my[0], mvx[0], mvy[0], mrs[0], o.x, o.y, o.vx, o.vy, tile_rs[t_first + u], fx[u], fy[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < SNP_LARGE_GROUP; ++u) { fsx[0] += fx[u]; fsy[0] += fy[u]; }
+            }
+        }
+#endif
 #pragma unroll 2
-        for (int t = 0; t < cnt; ++t) {
+        for (int t = t_first; t < cnt; ++t) {
             const Ent<T> o = tile[t];
             const T rsj = tile_rs[t];
             const long long jj = j0 + t - la.self_offset;  // index of the entity in this crowd's numbering
@@ -216,7 +247,7 @@ __device__ __forceinline__ void pairs_chunk(const LargeArgs<T> &la, PairsSmem<T>
                 }
 #pragma unroll
                 for (int q = 0; q < kAgentsPerThread; ++q) { fsx[q] += fx[q]; fsy[q] += fy[q]; }
-            } else {  // fp64: one evaluation at a time (the grouped form costs registers the 80-register budget does not have)
+            } else {  // fp64, two agents per thread (all pairs) or the tail of a tile: one evaluation at a time
 #pragma unroll
                 for (int q = 0; q < kAgentsPerThread; ++q) {
                     T fx, fy;
