@@ -96,6 +96,20 @@ def test_operator_argument_validation_needs_no_gpu():
         update_humans_parallel(0, np.zeros((3, 13)), np.zeros((2, 1, 2)), None, np.zeros((2, 20)), 0.01, np.zeros(2))
 
 
+def test_large_crowd_scratch_size_covers_every_region():
+    """snp_large_scratch_bytes is host arithmetic (no GPU): it must cover the per-chunk partial sums, the tile boxes, the live map,
+    the list of (agent block, chunk) units, the per-block ascending lists and the queue counters -- for whole and ragged sizes."""
+    from social_navigation_pyenvs_b200 import _lib as L
+    lib = L.lib()
+    for n_local, M in ((8192, 65536), (65536, 65536), (5184, 5184), (1, 2), (130, 1000)):
+        for dtype, w in ((L.SNP_F64, 8), (L.SNP_F32, 4)):
+            J, tiles, blocks = -(-M // 128), -(-M // 128), -(-n_local // 128)
+            Jp = (J + 15) // 16 * 16
+            need = w * (J * 2 * n_local + tiles * 5) + blocks * Jp + 4 * (260 + blocks * J + (blocks + 3) // 4 * 4 + blocks * Jp) + 64
+            got = int(lib.snp_large_scratch_bytes(n_local, M, dtype))
+            assert need <= got <= need + 4096 + 4 * blocks * Jp, (n_local, M, dtype, need, got)
+
+
 def test_product_package_never_imports_the_oracle():
     """The oracle is test infrastructure: nothing under social_navigation_pyenvs_b200/ may reference it."""
     pkg = os.path.join(ROOT, "social_navigation_pyenvs_b200")
