@@ -17,7 +17,7 @@
 // Small chunks matter once culling is on and the crowd is sharded: only a few percent of the units have anything to evaluate, and
 // what one rank of an 8-way split keeps must still fill 148 SMs evenly (history: 4096-entity chunks 2.6 ms per sub-step at 65536
 // humans and no gain from a second GPU; 512: 2.0 / 1.1 ms; 256 + exact culling on compact tiles + one agent per thread: 0.75 ms on
-// one GPU, 0.158 on eight; 128 + the work list + grouped evaluation: 0.61 / 0.125).  The price is J = M/128 partial sums per LIVE chunk and agent.
+// one GPU, 0.158 on eight; 128 + the work list + grouped evaluation: 0.59 / 0.125).  The price is J = M/128 partial sums per LIVE chunk and agent.
 // Reference: same as snp_step_small.cu (motion_model_manager.py:354-373,424-459; forces.py:63-151).
 #include "snp_kernels.cuh"
 
@@ -33,11 +33,11 @@ constexpr int kMaxAgentsPerThread = 2;
 #ifndef SNP_LARGE_CHUNK
 #define SNP_LARGE_CHUNK 128
 #endif
-// fp64 culled steps (one agent per thread): entities evaluated together between two contact votes.  Measured on one rank's slice of
-// an 8-way split / on the whole 65536 crowd: 1 -> 0.1229 / 0.657 ms per sub-step, 2 -> 0.1167 / 0.621, 4 -> 0.1136 / 0.616 (64 -> 80
-// registers, six resident CTAs per SM instead of nine, but four independent chains per warp when few warps are left on an SM).
+// Culled steps (one agent per thread): entities evaluated together between two contact votes.  Measured in fp64 on one rank's slice
+// of an 8-way split / on the whole 65536 crowd: 1 -> 0.1229 / 0.657 ms per sub-step, 2 -> 0.1167 / 0.621, 4 -> 0.1136 / 0.616,
+// 8 -> 0.1106 / 0.604 (more registers, fewer resident CTAs per SM, but independent chains per warp when few warps are left on an SM).
 #ifndef SNP_LARGE_GROUP
-#define SNP_LARGE_GROUP 4
+#define SNP_LARGE_GROUP 8
 #endif
 constexpr int kChunk = SNP_LARGE_CHUNK;  // entities per j-chunk (one partial sum each); fixed so results are sharding-independent
 
@@ -187,8 +187,8 @@ __device__ __forceinline__ void pairs_chunk(const LargeArgs<T> &la, PairsSmem<T>
         const int cnt = (int)min((long long)kTile, j_end - j0);
         int t_first = 0;
 #if SNP_LARGE_GROUP > 1
-        if constexpr (sizeof(T) == 8 && kAgentsPerThread == 1 && SOC != 2) {
-            // fp64, one agent per thread: SNP_LARGE_GROUP consecutive entities are evaluated branch-free and share ONE contact vote
+        if constexpr (kAgentsPerThread == 1 && SOC != 2) {
+            // one agent per thread (culled steps): SNP_LARGE_GROUP consecutive entities are evaluated branch-free and share ONE contact vote
             // (independent chains in flight when few warps are left on the SM); added in entity order, so the sum is unchanged
             for (; t_first + SNP_LARGE_GROUP <= cnt; t_first += SNP_LARGE_GROUP) {
                 T fx[SNP_LARGE_GROUP], fy[SNP_LARGE_GROUP];
@@ -639,7 +639,9 @@ template <typename T> int run_large(const snp_crowd *c, const snp_step_opts *o, 
         else if (soc == 1 && c->params[3] > 0 && c->params[7] > 0) margin = under * (c->params[3] > c->params[7] ? c->params[3] : c->params[7]);
     }
     la.cull_margin = (T)margin;
-    la.apt = (margin >= 0.0 && sizeof(T) == 8) ? 1 : kMaxAgentsPerThread;  // fp32 pair evaluations are short: the finer split only adds launch overhead there
+    // culled steps: one agent per thread (twice the units to hand out).  Round 2 kept two for fp32 on the static grid, where the
+    // finer split only added CTAs to launch; on the work list one rank's slice of an 8-way split runs 0.0552 -> 0.0408 ms in fp32
+    la.apt = margin >= 0.0 ? 1 : kMaxAgentsPerThread;  // fp32 pair evaluations are short: the finer split only adds launch overhead there
     la.use_list = (margin >= 0.0 && self_offset % kTile == 0 && list_entries < (1LL << 31) && !(o->reserved & SNP_OPT_LARGE_GRID)) ? 1 : 0;
     switch (o->type) {
         case 0: return launch_large<T, 0, 0, 0>(la, st);
