@@ -9,6 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SNP_B200_LIB", os.path.join(_HERE, "libsnp_b200.so"))  # override: tuning experiments only
 
 SNP_F32, SNP_F64 = 0, 1
+# bits of snp_step_opts.reserved (include/snp_b200.h)
+SNP_OPT_FULL_PAIR_LOOP, SNP_OPT_NO_CULLING, SNP_OPT_MAP_WARP, SNP_OPT_MAP_BLOCK, SNP_OPT_STAGED_COPIES, SNP_OPT_LARGE_GRID = 1, 2, 4, 8, 16, 32
 # field order of the SoA buffers (include/snp_b200.h)
 DYN_PX, DYN_PY, DYN_VX, DYN_VY, DYN_TH, DYN_BVX, DYN_BVY, DYN_OM, DYN_DFX, DYN_DFY, DYN_FIELDS = range(11)
 STAT_R, STAT_M, STAT_VD, STAT_SAFETY, STAT_FIELDS = range(5)

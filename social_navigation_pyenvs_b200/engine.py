@@ -153,7 +153,7 @@ class CrowdEngine:
         o.n_substeps, o.robot_mode, o.dt = int(n_substeps), int(robot_mode), float(dt)
         o.action = self.action.data_ptr()
         o.pre_checks, o.post_checks, o.track_touch = int(pre_checks), int(post_checks), int(track_touch)
-        o.reserved = (1 if self.full_pair_loop else 0) | (self.mapping << 2)
+        o.reserved = (L.SNP_OPT_FULL_PAIR_LOOP if self.full_pair_loop else 0) | (self.mapping << 2)  # mapping 1 / 2 = SNP_OPT_MAP_WARP / _BLOCK
         o.consts = (ctypes.c_double * 6)(*self.consts)
         o.time_now = self.time_now.data_ptr() if (advance_time or pre_checks or int(post_checks) == 2) else None
         o.flags, o.checks = self.flags.data_ptr(), self.checks.data_ptr()
@@ -323,7 +323,7 @@ class CrowdEngine:
         if cached is None or cached[0] != key:
             o = self._opts(dt, n_substeps, robot_mode=1, pre_checks=pre_checks, post_checks=post_checks, track_touch=track_touch, advance_time=True)
             if staged:
-                o.reserved |= 16
+                o.reserved |= L.SNP_OPT_STAGED_COPIES
             cached = self._host_call = (key, self._crowd(), o)
         hp = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr() if torch.is_tensor(t) else t.ctypes.data)
         L.check(self.lib.snp_gym_step_host(ctypes.byref(cached[1]), ctypes.byref(cached[2]), hp(action_host), hp(obs_host), hp(flags_host),

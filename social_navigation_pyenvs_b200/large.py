@@ -105,9 +105,9 @@ class LargeCrowd:
     def step(self, dt=0.0125, n_substeps=1):
         c = self.eng._crowd()
         o = self.eng._opts(dt, 1)
-        o.reserved = 0 if self.culling else 2  # SNP_OPT_NO_CULLING
+        o.reserved = 0 if self.culling else L.SNP_OPT_NO_CULLING
         if not self.work_list:
-            o.reserved |= 32  # SNP_OPT_LARGE_GRID: culled steps on the static grid instead of the list of near (i-block, chunk) pairs
+            o.reserved |= L.SNP_OPT_LARGE_GRID  # culled steps on the static grid instead of the list of near (i-block, chunk) pairs
         if self.exchange in ("p2p", "fused") and not getattr(self, "legacy_loop", False):
             # the whole sub-step loop in ONE C call: per sub-step two launches + a single-warp cross-rank barrier kernel, nothing
             # returns to Python in between

@@ -55,6 +55,23 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
             assert int(out[f"{cname}.{f}"]) == getattr(cls, f).offset, (cname, f)
 
 
+def test_python_constants_match_the_header_enums(tmp_path):
+    """The option bits, dtype codes, field counts and flag bits the Python side uses are the header's."""
+    import subprocess
+    from social_navigation_pyenvs_b200 import _lib as L
+    names = ["SNP_F32", "SNP_F64", "SNP_OPT_FULL_PAIR_LOOP", "SNP_OPT_NO_CULLING", "SNP_OPT_MAP_WARP", "SNP_OPT_MAP_BLOCK", "SNP_OPT_STAGED_COPIES",
+             "SNP_OPT_LARGE_GRID"]
+    src = tmp_path / "enums.c"
+    src.write_text('#include <stdio.h>\n#include "snp_b200.h"\nint main(void) {\n' + "\n".join(f'printf("{n} %d\\n", (int){n});' for n in names) +
+                   '\nprintf("DYN_FIELDS %d\\nSTAT_FIELDS %d\\nROBOT_FIELDS %d\\n", (int)SNP_DYN_FIELDS, (int)SNP_STAT_FIELDS, (int)SNP_ROBOT_FIELDS);\nreturn 0; }\n')
+    exe = tmp_path / "enums"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for n in names:
+        assert int(out[n]) == getattr(L, n), n
+    assert (int(out["DYN_FIELDS"]), int(out["STAT_FIELDS"]), int(out["ROBOT_FIELDS"])) == (L.DYN_FIELDS, L.STAT_FIELDS, L.ROBOT_FIELDS)
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from social_navigation_pyenvs_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
