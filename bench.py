@@ -402,8 +402,7 @@ def large_crowd_probe(tdtype, rank, world, substeps_per_call=10, calls=3):
         # load balance: the 128-human tiles (compact patches) are dealt to the ranks round-robin, so every rank owns patches from
         # all over the crowd instead of one block of strips (an interior block has ~25 % more near neighbours than a corner one).
         # The numbering is the caller's; no force depends on it.
-        tiles = perm.reshape(-1, 128)
-        perm = np.concatenate([tiles[r::world] for r in range(world)]).reshape(-1)
+        perm = scenarios.deal_tiles(perm, world)
     S, G = np.ascontiguousarray(sc["states"][0, perm]), np.ascontiguousarray(sc["goals"][0, perm])
     n = S.shape[0]
     crowd = LargeCrowd("hsfm_farina", S, G, dtype=tdtype, rank=rank, world=world, exchange=os.environ.get("SNP_EXCHANGE", "auto"))

@@ -3,6 +3,7 @@ trajectory fixtures).  CPU only."""
 import os
 
 import numpy as np
+import pytest
 
 from helpers import GOLDEN, load_traj
 from social_navigation_pyenvs_b200 import scenarios
@@ -138,3 +139,27 @@ def test_spatial_order_is_a_permutation_with_compact_runs():
         p = rng.normal(0.0, 30.0, (n, 2)) ** 3 / 900.0   # heavy-tailed, clustered near the origin
         q = scenarios.spatial_order(p)
         assert np.array_equal(np.sort(q), np.arange(n))
+
+
+def test_deal_tiles_gives_every_rank_whole_tiles_from_all_over_the_crowd():
+    """scenarios.deal_tiles: a permutation; rank r's contiguous slice (parallel.agent_shard) is exactly the tiles r, r + world, ... of
+    the spatial order, each kept whole and in order; every slice reaches across the crowd (all strips in x, at least two distant
+    patches of every strip in y) instead of being one compact block."""
+    from social_navigation_pyenvs_b200.parallel import agent_shard
+    sc = scenarios.jittered_grid_crowd(128, pitch=2.0, jitter=0.5, seed=1)  # 16384 humans: 8 strips of 16 tiles
+    pos = sc["states"][0, :, 0:2]
+    perm = scenarios.spatial_order(pos)
+    n = len(perm)
+    assert np.array_equal(scenarios.deal_tiles(perm, 1), perm)
+    for world in (2, 4, 8):
+        dealt = scenarios.deal_tiles(perm, world)
+        assert np.array_equal(np.sort(dealt), np.arange(n))
+        tiles = perm.reshape(-1, 128)
+        for r in range(world):
+            off, cnt = agent_shard(n, r, world)
+            assert np.array_equal(dealt[off:off + cnt].reshape(-1, 128), tiles[r::world])
+            span = np.ptp(pos[dealt[off:off + cnt]], axis=0)
+            full = np.ptp(pos, axis=0)
+            assert span[0] > 0.8 * full[0] and span[1] > 0.4 * full[1]
+    with pytest.raises(ValueError):
+        scenarios.deal_tiles(np.arange(130), 2)

@@ -8,8 +8,7 @@ from social_navigation_pyenvs_b200.large import LargeCrowd
 ways, rank = int(sys.argv[1]), int(sys.argv[2])
 sc = scenarios.jittered_grid_crowd(256, pitch=2.0, jitter=0.5, seed=0)
 perm = scenarios.spatial_order(sc["states"][0, :, 0:2])
-tiles = perm.reshape(-1, 128)
-perm = np.concatenate([tiles[r::ways] for r in range(ways)]).reshape(-1)
+perm = scenarios.deal_tiles(perm, ways)
 S, G = np.ascontiguousarray(sc["states"][0, perm]), np.ascontiguousarray(sc["goals"][0, perm])
 n = S.shape[0] // ways
 crowd = LargeCrowd("hsfm_farina", S, G, dtype=torch.float32, shard=(rank * n, n))

@@ -11,8 +11,7 @@ ways, rank = int(sys.argv[1]), int(sys.argv[2])
 sc = scenarios.jittered_grid_crowd(256, pitch=2.0, jitter=0.5, seed=0)
 perm = scenarios.spatial_order(sc["states"][0, :, 0:2])
 if os.environ.get("SNP_LARGE_DEAL", "1") == "1":  # the bench's load balancing: 128-human tiles dealt round-robin to the ranks
-    tiles = perm.reshape(-1, 128)
-    perm = np.concatenate([tiles[r::ways] for r in range(ways)]).reshape(-1)
+    perm = scenarios.deal_tiles(perm, ways)
 S, G = np.ascontiguousarray(sc["states"][0, perm]), np.ascontiguousarray(sc["goals"][0, perm])
 n = S.shape[0] // ways
 crowd = LargeCrowd("hsfm_farina", S, G, dtype=torch.float64, shard=(rank * n, n))
